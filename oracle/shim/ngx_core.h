@@ -1,0 +1,1 @@
+/* TEST INFRASTRUCTURE — intentionally empty stand-in (see ngx_config.h). */
