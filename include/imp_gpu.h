@@ -1,0 +1,169 @@
+/*
+ * imp_gpu.h — C ABI of libimp_gpu.so: the B200 (sm_100a) implementation of IMP's decoded-pixel
+ * hot path (RunJob steps 3-7, /root/reference/bridge.c:574-656): crop, resize, filter chain,
+ * watermark alpha-composite, alpha flatten.
+ *
+ * This is the drop-in boundary below bridge.c. Host code stays C; every entry point takes plain
+ * pointers and sizes (no CUDA, torch or C++ types), returns the reference's own IMP_* codes
+ * (required.h:27-41) and never throws or exits. There is NO CPU fallback: without a usable CUDA
+ * device every compute entry point returns IMP_ERROR_GPU.
+ *
+ * What each group replaces in the reference:
+ *   imp_gpu_init / imp_gpu_shutdown        OnEnvStart / OnEnvDestroy      bridge.c:10-16 (no-ops there;
+ *                                          called per worker from module.c:100-107, i.e. after fork)
+ *   imp_gpu_request + imp_gpu_config       the strings RunJob extracts from the query (bridge.c:346-372)
+ *                                          and the Config fields the ops read (required.h:110-120)
+ *   imp_gpu_plan_create                    argument validation of Crop (bridge.c:18-128), Resize
+ *                                          (bridge.c:143-190), Filter + 14 callbacks (filters.c:43-455),
+ *                                          Watermark placement (bridge.c:254-274): same grammar, same
+ *                                          codes, same failing step, before any pixel is touched
+ *   imp_gpu_run_host / _run_device         the per-frame loops bridge.c:576-656 for ONE frame
+ *   imp_gpu_batch_*                        the same loops over album.Frames[] (GIF frames) and over
+ *                                          concurrent requests: one fused launch per kernel variant
+ *   imp_gpu_farm_run_host                  independent frames sharded round-robin over the GPUs of
+ *                                          one box (no collective: nothing crosses GPUs)
+ * The reference-signature operator layer (Crop/Resize/Filter/Watermark/BlendWithPaper on IplImage)
+ * is declared in imp_ops.h and is implemented on top of this ABI.
+ */
+#ifndef IMP_GPU_H
+#define IMP_GPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes: required.h:27-41, plus one new code for CUDA failures (maps to HTTP 500) ---- */
+#define IMP_OK                      0
+#define IMP_ERROR_UNSUPPORTED       1
+#define IMP_ERROR_MALLOC_FAILED     2
+#define IMP_ERROR_INVALID_ARGS      50
+#define IMP_ERROR_UPSCALE           51
+#define IMP_ERROR_NO_SUCH_FILTER    52
+#define IMP_ERROR_NO_SUCH_WATERMARK 53
+#define IMP_ERROR_TOO_BIG_TARGET    54
+#define IMP_ERROR_TOO_MUCH_FILTERS  55
+#define IMP_ERROR_FEATURE_DISABLED  56
+#define IMP_ERROR_GPU               100
+
+/* ---- job steps: required.h:46-54 ---------------------------------------------------------------- */
+#define IMP_STEP_CROP      3
+#define IMP_STEP_RESIZE    4
+#define IMP_STEP_FILTERING 5
+#define IMP_STEP_WATERMARK 6
+#define IMP_STEP_ENCODE    8
+
+/* ---- resize interpolation override (extension; 0 keeps the reference rule bridge.c:190) --------- */
+#define IMP_INTERP_REFERENCE 0   /* simple ? NN : (upscale ? CUBIC : AREA) */
+#define IMP_INTERP_LINEAR    1   /* cv::INTER_LINEAR instead of CUBIC/AREA (north_star "bilinear") */
+
+/* The decoded watermark as PrepareWatermark leaves it in the conf pool (RecoverInfo, required.h:101-108,
+ * bridge.c:221-234) plus its placement (Position, required.h:86-91) and opacity (module.c directive). */
+typedef struct imp_gpu_watermark {
+    const unsigned char* pixels;   /* RecoverInfo.Pointer: 8-bit B,G,R[,A] interleaved, host memory */
+    int  width, height;            /* RecoverInfo.Size */
+    int  channels;                 /* RecoverInfo.Channels: 3 or 4 */
+    int  step;                     /* RecoverInfo.Step (bytes per row) */
+    char gravity_x, gravity_y;     /* Position.GravityX/Y: 'l'|'c'|'r', 't'|'c'|'b' */
+    int  offset_x, offset_y;       /* Position.OffsetX/Y */
+    int  opacity;                  /* Config.WatermarkOpacity, 1..100 */
+} imp_gpu_watermark;
+
+/* The Config fields the hot path reads (required.h:110-120). */
+typedef struct imp_gpu_config {
+    unsigned int max_target_w, max_target_h;   /* MaxTargetDimensions (0 = unlimited) */
+    int max_filters;                           /* MaxFiltersCount */
+    int allow_experiments;                     /* AllowExperiments */
+    const imp_gpu_watermark* watermark;        /* WatermarkInfo or NULL */
+} imp_gpu_config;
+
+/* What RunJob hands to steps 3-7 (bridge.c:318-372, 594, 642-656). Strings are the raw GET values,
+ * NUL-terminated, caller-owned and never modified (the reference's in-place tokenising of `gravity`,
+ * bridge.c:73, is not reproduced: every frame of a job sees the same string). */
+typedef struct imp_gpu_request {
+    const char*        crop;          /* "W,H[,gx,gy]" or NULL */
+    const char*        gravity;       /* "gx,gy" or NULL */
+    const char*        resize;        /* "W[,H[,up]]" or NULL */
+    const char* const* filters;       /* filter_count strings "name=args" (text after "filter-") */
+    int                filter_count;
+    int                simple_resize; /* 1 when the encoder is GIF -> INTER_NN (bridge.c:594) */
+    int                flatten;       /* 1 when the encoder has no alpha -> BlendWithPaper (bridge.c:642-656) */
+    int                interp;        /* IMP_INTERP_* */
+} imp_gpu_request;
+
+typedef struct imp_gpu_plan  imp_gpu_plan;    /* validated, lowered, device-resident job recipe */
+typedef struct imp_gpu_batch imp_gpu_batch;   /* a set of (plan, source, destination) jobs launched together */
+
+/* ---- lifetime ----------------------------------------------------------------------------------- */
+/* Creates the CUDA context on `device` for this process (call after fork). Idempotent per device. */
+int  imp_gpu_init(int device);
+void imp_gpu_shutdown(void);
+int  imp_gpu_device_count(void);
+/* Selects which initialised device subsequent calls from THIS thread use. */
+int  imp_gpu_set_device(int device);
+const char* imp_gpu_last_error(void);          /* thread-local text of the last IMP_ERROR_GPU */
+/* Kernels launched by this library since process start (all devices). */
+unsigned long long imp_gpu_launch_count(void);
+
+/* ---- plans -------------------------------------------------------------------------------------- */
+/* Validates `req` against a source frame of src_w x src_h x src_c (8-bit, c in {1,3,4}) exactly as the
+ * reference's operators would, in the reference's order; on success returns IMP_OK and a plan, else the
+ * reference's error code with *step = the IMP_STEP_* at which RunJob would have stopped. */
+int  imp_gpu_plan_create(const imp_gpu_request* req, const imp_gpu_config* cfg,
+                         int src_w, int src_h, int src_c, imp_gpu_plan** plan, int* step);
+void imp_gpu_plan_destroy(imp_gpu_plan* plan);
+void imp_gpu_plan_output(const imp_gpu_plan* plan, int* w, int* h, int* c);
+/* Source window the plan actually reads (the crop window), for callers that upload only those rows. */
+void imp_gpu_plan_source_window(const imp_gpu_plan* plan, int* x, int* y, int* w, int* h);
+/* Number of kernel passes (1 unless a blur splits the chain) and algorithmic bytes. */
+int  imp_gpu_plan_passes(const imp_gpu_plan* plan);
+unsigned long long imp_gpu_plan_algorithmic_bytes(const imp_gpu_plan* plan);
+
+/* ---- one frame ---------------------------------------------------------------------------------- */
+/* Host buffers: H2D of the crop window, kernels, D2H; synchronous. dst must hold out_h rows of dst_step. */
+int  imp_gpu_run_host(imp_gpu_plan* plan, const unsigned char* src, int src_step,
+                      unsigned char* dst, int dst_step);
+/* Device buffers (pitches multiples of 16, bases 16-byte aligned); asynchronous on `stream`
+ * (a cudaStream_t passed as void*, NULL = the library's stream for this device). */
+int  imp_gpu_run_device(imp_gpu_plan* plan, const void* d_src, int src_pitch,
+                        void* d_dst, int dst_pitch, void* stream);
+
+/* ---- batches: GIF frames / concurrent requests ---------------------------------------------------- */
+int  imp_gpu_batch_create(imp_gpu_batch** batch);
+void imp_gpu_batch_destroy(imp_gpu_batch* batch);
+int  imp_gpu_batch_clear(imp_gpu_batch* batch);
+int  imp_gpu_batch_add(imp_gpu_batch* batch, imp_gpu_plan* plan, const void* d_src, int src_pitch,
+                       void* d_dst, int dst_pitch);
+/* Uploads the job table once (until the next add/clear) and launches one kernel per pass and kernel
+ * variant over all jobs; asynchronous on `stream`. */
+int  imp_gpu_batch_launch(imp_gpu_batch* batch, void* stream);
+int  imp_gpu_batch_size(const imp_gpu_batch* batch);
+unsigned long long imp_gpu_batch_algorithmic_bytes(const imp_gpu_batch* batch);
+int  imp_gpu_batch_launches_per_run(const imp_gpu_batch* batch);
+
+/* End to end over host buffers: n jobs staged through pinned buffers and `n_streams` CUDA streams
+ * (H2D / kernels / D2H overlapped), on the current device; synchronous. */
+int  imp_gpu_batch_run_host(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs,
+                            const int* src_steps, unsigned char* const* dsts, const int* dst_steps,
+                            int n_streams);
+/* Same, sharded round-robin (job i -> GPU i mod n_gpus) over devices 0..n_gpus-1 with one host thread
+ * per GPU; no inter-GPU traffic. All devices are initialised on demand. */
+int  imp_gpu_farm_run_host(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs,
+                           const int* src_steps, unsigned char* const* dsts, const int* dst_steps,
+                           int n_gpus, int n_streams);
+
+/* ---- memory helpers so a C host needs no CUDA headers --------------------------------------------- */
+int  imp_gpu_malloc(void** d_ptr, size_t bytes);
+int  imp_gpu_free(void* d_ptr);
+int  imp_gpu_malloc_pitch(void** d_ptr, int* pitch, int width_bytes, int height);
+int  imp_gpu_host_alloc(void** h_ptr, size_t bytes);      /* pinned */
+int  imp_gpu_host_free(void* h_ptr);
+int  imp_gpu_upload_2d(void* d_dst, int d_pitch, const void* h_src, int h_step, int width_bytes, int height, void* stream);
+int  imp_gpu_download_2d(void* h_dst, int h_step, const void* d_src, int d_pitch, int width_bytes, int height, void* stream);
+int  imp_gpu_sync(void* stream);                          /* NULL = whole device */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMP_GPU_H */

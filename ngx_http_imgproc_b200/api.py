@@ -1,0 +1,265 @@
+"""
+ctypes binding of libimp_gpu.so (include/imp_gpu.h) — the call a user of the reference's operator
+layer makes, from Python. Used by tests/ and bench.py; it adds no arithmetic of its own.
+
+The library is the product: if it is missing, cannot be loaded, or no B200 is visible, everything
+here raises. There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import build as _build
+
+IMP_OK = 0
+IMP_ERROR_INVALID_ARGS = 50
+IMP_ERROR_NO_SUCH_FILTER = 52
+IMP_ERROR_NO_SUCH_WATERMARK = 53
+IMP_ERROR_TOO_BIG_TARGET = 54
+IMP_ERROR_TOO_MUCH_FILTERS = 55
+IMP_ERROR_GPU = 100
+INTERP_REFERENCE, INTERP_LINEAR = 0, 1
+
+
+class CWatermark(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("channels", C.c_int),
+                ("step", C.c_int), ("gravity_x", C.c_char), ("gravity_y", C.c_char),
+                ("offset_x", C.c_int), ("offset_y", C.c_int), ("opacity", C.c_int)]
+
+
+class CConfig(C.Structure):
+    _fields_ = [("max_target_w", C.c_uint), ("max_target_h", C.c_uint), ("max_filters", C.c_int),
+                ("allow_experiments", C.c_int), ("watermark", C.POINTER(CWatermark))]
+
+
+class CRequest(C.Structure):
+    _fields_ = [("crop", C.c_char_p), ("gravity", C.c_char_p), ("resize", C.c_char_p),
+                ("filters", C.POINTER(C.c_char_p)), ("filter_count", C.c_int),
+                ("simple_resize", C.c_int), ("flatten", C.c_int), ("interp", C.c_int)]
+
+
+@dataclass
+class Config:
+    """The Config fields the hot path reads (required.h:110-120), with module.c:117-190's defaults."""
+    max_w: int = 2000
+    max_h: int = 2000
+    max_filters: int = 5
+    allow_experiments: bool = False
+    watermark: Optional[np.ndarray] = None      # decoded overlay, HxWx{3,4} uint8
+    wm_gravity_x: str = "l"
+    wm_gravity_y: str = "t"
+    wm_offset_x: int = 0
+    wm_offset_y: int = 0
+    wm_opacity: int = 100
+
+    def to_c(self):
+        keep = []
+        c = CConfig(self.max_w, self.max_h, self.max_filters, 1 if self.allow_experiments else 0, None)
+        if self.watermark is not None:
+            wm = np.ascontiguousarray(self.watermark, dtype=np.uint8)
+            w = CWatermark(wm.ctypes.data, wm.shape[1], wm.shape[0], wm.shape[2], wm.strides[0],
+                           self.wm_gravity_x.encode(), self.wm_gravity_y.encode(), self.wm_offset_x, self.wm_offset_y, self.wm_opacity)
+            keep += [wm, w]
+            c.watermark = C.pointer(w)
+        keep.append(c)
+        return c, keep
+
+
+def make_request(crop=None, gravity=None, resize=None, filters: Sequence[str] = (), simple=False, flatten=False, interp=0):
+    keep = []
+    enc = lambda s: None if s is None else s.encode("latin-1")
+    arr = (C.c_char_p * max(1, len(filters)))(*[enc(f) for f in filters])
+    keep.append(arr)
+    r = CRequest(enc(crop), enc(gravity), enc(resize), arr, len(filters), 1 if simple else 0, 1 if flatten else 0, interp)
+    keep.append(r)
+    return r, keep
+
+
+class ImpError(RuntimeError):
+    def __init__(self, code, step=None, msg=""):
+        super().__init__(f"IMP code {code} step {step} {msg}")
+        self.code, self.step = code, step
+
+
+class Library:
+    """libimp_gpu.so loaded through ctypes."""
+
+    def __init__(self, path: Optional[str] = None):
+        path = path or _build.LIB
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -m ngx_http_imgproc_b200.build` "
+                               "(nvcc, sm_100a). There is no CPU fallback.")
+        self.path = path
+        L = self.lib = C.CDLL(path)
+        L.imp_gpu_last_error.restype = C.c_char_p
+        L.imp_gpu_launch_count.restype = C.c_ulonglong
+        L.imp_gpu_plan_algorithmic_bytes.restype = C.c_ulonglong
+        L.imp_gpu_plan_algorithmic_bytes.argtypes = [C.c_void_p]
+        L.imp_gpu_batch_algorithmic_bytes.restype = C.c_ulonglong
+        L.imp_gpu_batch_algorithmic_bytes.argtypes = [C.c_void_p]
+        L.imp_gpu_plan_create.argtypes = [C.POINTER(CRequest), C.POINTER(CConfig), C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        L.imp_gpu_plan_destroy.argtypes = [C.c_void_p]
+        L.imp_gpu_plan_output.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
+        L.imp_gpu_plan_source_window.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        L.imp_gpu_plan_passes.argtypes = [C.c_void_p]
+        L.imp_gpu_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.imp_gpu_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.imp_gpu_batch_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.imp_gpu_batch_destroy.argtypes = [C.c_void_p]
+        L.imp_gpu_batch_clear.argtypes = [C.c_void_p]
+        L.imp_gpu_batch_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.imp_gpu_batch_launch.argtypes = [C.c_void_p, C.c_void_p]
+        L.imp_gpu_batch_size.argtypes = [C.c_void_p]
+        L.imp_gpu_batch_launches_per_run.argtypes = [C.c_void_p]
+        L.imp_gpu_batch_run_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.imp_gpu_farm_run_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.imp_gpu_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.imp_gpu_free.argtypes = [C.c_void_p]
+        L.imp_gpu_malloc_pitch.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int]
+        L.imp_gpu_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.imp_gpu_host_free.argtypes = [C.c_void_p]
+        L.imp_gpu_upload_2d.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.imp_gpu_download_2d.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.imp_gpu_sync.argtypes = [C.c_void_p]
+
+    # ---- lifetime ---------------------------------------------------------------------------------
+    def last_error(self) -> str:
+        return (self.lib.imp_gpu_last_error() or b"").decode()
+
+    def check(self, rc, step=None):
+        if rc != IMP_OK:
+            raise ImpError(rc, step, self.last_error() if rc == IMP_ERROR_GPU else "")
+
+    def init(self, device: int = 0):
+        self.check(self.lib.imp_gpu_init(device))
+
+    def set_device(self, device: int):
+        self.check(self.lib.imp_gpu_set_device(device))
+
+    def shutdown(self):
+        self.lib.imp_gpu_shutdown()
+
+    def device_count(self) -> int:
+        return self.lib.imp_gpu_device_count()
+
+    def launch_count(self) -> int:
+        return int(self.lib.imp_gpu_launch_count())
+
+    # ---- plans --------------------------------------------------------------------------------------
+    def plan(self, w, h, c, cfg: Optional[Config] = None, **req) -> "Plan":
+        cfg = cfg or Config()
+        ccfg, keep1 = cfg.to_c()
+        creq, keep2 = make_request(**req)
+        out, step = C.c_void_p(), C.c_int(-1)
+        rc = self.lib.imp_gpu_plan_create(C.byref(creq), C.byref(ccfg), w, h, c, C.byref(out), C.byref(step))
+        if rc != IMP_OK:
+            raise ImpError(rc, step.value)
+        return Plan(self, out, (w, h, c))
+
+    def try_plan(self, w, h, c, cfg: Optional[Config] = None, **req):
+        """Returns (code, step, plan-or-None) without raising on validation errors."""
+        try:
+            p = self.plan(w, h, c, cfg, **req)
+            return IMP_OK, 8, p
+        except ImpError as e:
+            return e.code, e.step, None
+
+    # ---- one call: host image in, host image out (the e2e path) ---------------------------------------
+    def run(self, img: np.ndarray, cfg: Optional[Config] = None, **req) -> np.ndarray:
+        img = np.ascontiguousarray(img if img.ndim == 3 else img[:, :, None], dtype=np.uint8)
+        p = self.plan(img.shape[1], img.shape[0], img.shape[2], cfg, **req)
+        try:
+            return p.run_host(img)
+        finally:
+            p.close()
+
+
+class Plan:
+    def __init__(self, lib: Library, handle, src_shape):
+        self.L, self.h, self.src = lib, handle, src_shape
+        w, h, c = C.c_int(), C.c_int(), C.c_int()
+        lib.lib.imp_gpu_plan_output(handle, C.byref(w), C.byref(h), C.byref(c))
+        self.out_w, self.out_h, self.out_c = w.value, h.value, c.value
+        x, y = C.c_int(), C.c_int()
+        lib.lib.imp_gpu_plan_source_window(handle, C.byref(x), C.byref(y), C.byref(w), C.byref(h))
+        self.window = (x.value, y.value, w.value, h.value)
+        self.passes = lib.lib.imp_gpu_plan_passes(handle)
+        self.algorithmic_bytes = int(lib.lib.imp_gpu_plan_algorithmic_bytes(handle))
+
+    def close(self):
+        if self.h:
+            self.L.lib.imp_gpu_plan_destroy(self.h)
+            self.h = None
+
+    def run_host(self, img: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        img = np.ascontiguousarray(img if img.ndim == 3 else img[:, :, None], dtype=np.uint8)
+        assert (img.shape[1], img.shape[0], img.shape[2]) == self.src
+        if out is None:
+            out = np.empty((self.out_h, self.out_w, self.out_c), np.uint8)
+        self.L.check(self.L.lib.imp_gpu_run_host(self.h, img.ctypes.data, img.strides[0], out.ctypes.data, out.strides[0]))
+        return out
+
+    def run_device(self, d_src: int, src_pitch: int, d_dst: int, dst_pitch: int, stream: int = 0):
+        self.L.check(self.L.lib.imp_gpu_run_device(self.h, d_src, src_pitch, d_dst, dst_pitch, stream))
+
+
+class Batch:
+    def __init__(self, lib: Library):
+        self.L = lib
+        self.h = C.c_void_p()
+        lib.check(lib.lib.imp_gpu_batch_create(C.byref(self.h)))
+
+    def add(self, plan: Plan, d_src: int, src_pitch: int, d_dst: int, dst_pitch: int):
+        self.L.check(self.L.lib.imp_gpu_batch_add(self.h, plan.h, d_src, src_pitch, d_dst, dst_pitch))
+
+    def launch(self, stream: int = 0):
+        self.L.check(self.L.lib.imp_gpu_batch_launch(self.h, stream))
+
+    def clear(self):
+        self.L.lib.imp_gpu_batch_clear(self.h)
+
+    @property
+    def algorithmic_bytes(self) -> int:
+        return int(self.L.lib.imp_gpu_batch_algorithmic_bytes(self.h))
+
+    @property
+    def launches_per_run(self) -> int:
+        return self.L.lib.imp_gpu_batch_launches_per_run(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.lib.imp_gpu_batch_destroy(self.h)
+            self.h = None
+
+
+def run_host_batch(lib: Library, plans: List[Plan], srcs: List[np.ndarray], dsts: List[np.ndarray], n_streams=4, n_gpus=0):
+    """imp_gpu_batch_run_host / imp_gpu_farm_run_host over numpy (or pinned) buffers."""
+    n = len(plans)
+    P = (C.c_void_p * n)(*[p.h for p in plans])
+    S = (C.c_void_p * n)(*[s.ctypes.data for s in srcs])
+    D = (C.c_void_p * n)(*[d.ctypes.data for d in dsts])
+    SS = (C.c_int * n)(*[s.strides[0] for s in srcs])
+    DS = (C.c_int * n)(*[d.strides[0] for d in dsts])
+    if n_gpus:
+        lib.check(lib.lib.imp_gpu_farm_run_host(n, P, S, SS, D, DS, n_gpus, n_streams))
+    else:
+        lib.check(lib.lib.imp_gpu_batch_run_host(n, P, S, SS, D, DS, n_streams))
+
+
+_default: Optional[Library] = None
+
+
+def library() -> Library:
+    """The process-wide library handle (built on demand when nvcc is present)."""
+    global _default
+    if _default is None:
+        if _build.stale():
+            _build.build()
+        _default = Library()
+    return _default

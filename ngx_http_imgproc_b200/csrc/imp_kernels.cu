@@ -1,0 +1,198 @@
+// imp_kernels.cu — sm_100a kernels of the decoded-pixel path and their launchers.
+//
+// Round-1 layout: one thread per base-frame pixel, 32x8 pixel tiles, one CTA per (tile, job).
+// Each CTA stages its pass's op list + LUTs in shared memory once; the gather reads the source through
+// the read-only path, the op list runs in registers, and the store applies the accumulated
+// flip/rotate map. A whole batch (GIF frames, concurrent requests) is one launch per kernel variant:
+// grid = (tiles, jobs). See DESIGN.md §Kernels for the roofline of each variant.
+#include "imp_internal.h"
+#include "imp_gather.cuh"
+
+#include <atomic>
+static std::atomic<unsigned long long> g_imp_launches{0};
+unsigned long long imp_launches() { return g_imp_launches.load(); }
+
+namespace {
+
+constexpr int TILE_W = 32, TILE_H = 8;
+
+struct OpsSmem {
+    const ImpOp* ops; const uint8_t* lut;
+};
+
+// Copies ops[] + LUT area (contiguous in the blob, 16-byte aligned) into shared memory.
+__device__ __forceinline__ OpsSmem stage_ops(const ImpPass* P, const uint8_t* blob, uint8_t* smem) {
+    const int bytes = P->nops * (int)sizeof(ImpOp) + P->lut_bytes;
+    const uint4* g = reinterpret_cast<const uint4*>(blob + P->ops_off);
+    uint4* s = reinterpret_cast<uint4*>(smem);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    for (int i = tid; i < (bytes + 15) / 16; i += nt) s[i] = __ldg(g + i);
+    __syncthreads();
+    OpsSmem o;
+    o.ops = reinterpret_cast<const ImpOp*>(smem);
+    o.lut = smem + P->nops * sizeof(ImpOp);
+    return o;
+}
+
+template <int DC>
+__device__ __forceinline__ void store_px(const ImpJob& job, const ImpPass* P, int bx, int by, const ImpPx& p) {
+    int X, Y;
+    imp_map_xy(P->out, bx, by, X, Y);
+    uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * DC;
+    if (DC == 4) {
+        *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
+    } else {
+        d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r;
+    }
+}
+
+template <int SC>
+__device__ __forceinline__ void promote(const int* v, ImpPx& p) {
+    if (SC == 1) { p.b = p.g = p.r = v[0]; p.a = 255; }
+    else { p.b = v[0]; p.g = v[1]; p.r = v[2]; p.a = (SC == 4) ? v[3] : 255; }
+}
+
+template <int KIND, int SC>
+__global__ void __launch_bounds__(TILE_W * TILE_H)
+imp_pass_kernel(const ImpJob* __restrict__ jobs, int first, int count, const ImpJob one) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int j = blockIdx.y + blockIdx.z * 65535;
+    if (j >= count) return;
+    const ImpJob job = jobs ? jobs[first + j] : one;
+    const uint8_t* blob = job.pass;
+    const ImpPass* __restrict__ P = reinterpret_cast<const ImpPass*>(blob);
+    const int bw = P->bw, bh = P->bh;
+    const int tiles_x = (bw + TILE_W - 1) / TILE_W, tiles_y = (bh + TILE_H - 1) / TILE_H;
+    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
+    OpsSmem os = stage_ops(P, blob, smem);
+    const int bx = (blockIdx.x % tiles_x) * TILE_W + threadIdx.x;
+    const int by = (blockIdx.x / tiles_x) * TILE_H + threadIdx.y;
+    if (bx >= bw || by >= bh) return;
+
+    ImpSrcGlobal<SC> S;
+    S.base = job.src + (size_t)P->sy0 * job.src_pitch + (size_t)P->sx0 * SC;
+    S.pitch = job.src_pitch;
+    int v[4] = {0, 0, 0, 255};
+    if (KIND == IMP_G_COPY) {
+        imp_gather_copy<SC>(S, bx, by, v);
+    } else if (KIND == IMP_G_NN) {
+        imp_gather_nn<SC>(S, reinterpret_cast<const int*>(blob + P->xofs_off), reinterpret_cast<const int*>(blob + P->yofs_off), bx, by, v);
+    } else if (KIND == IMP_G_AREA_INT) {
+        imp_gather_area_int<SC>(S, P->nx, P->ny, P->area_scale, bx, by, v);
+    } else if (KIND == IMP_G_AREA_FRAC) {
+        imp_gather_area_frac<SC>(S, reinterpret_cast<const ImpRange*>(blob + P->xofs_off), reinterpret_cast<const ImpAreaTap*>(blob + P->xcoef_off),
+                                 reinterpret_cast<const ImpRange*>(blob + P->yofs_off), reinterpret_cast<const ImpAreaTap*>(blob + P->ycoef_off), bx, by, v);
+    } else if (KIND == IMP_G_CUBIC) {
+        imp_gather_cubic<SC>(S, P->sw, P->sh, reinterpret_cast<const int*>(blob + P->xofs_off), reinterpret_cast<const short*>(blob + P->xcoef_off),
+                             reinterpret_cast<const int*>(blob + P->yofs_off), reinterpret_cast<const short*>(blob + P->ycoef_off), P->simd_end, bx, by, v);
+    } else if (KIND == IMP_G_LINEAR) {
+        imp_gather_linear<SC>(S, P->sw, P->sh, reinterpret_cast<const int*>(blob + P->xofs_off), reinterpret_cast<const short*>(blob + P->xcoef_off),
+                              reinterpret_cast<const int*>(blob + P->yofs_off), reinterpret_cast<const short*>(blob + P->ycoef_off), bx, by, v);
+    }
+    ImpPx p;
+    promote<SC>(v, p);
+    const int oc = P->oc;
+    imp_run_ops(p, oc, bx, by, os.ops, P->nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
+    if (oc == 4) store_px<4>(job, P, bx, by, p); else store_px<3>(job, P, bx, by, p);
+}
+
+// ---- generic Gaussian (any sigma): horizontal pass to a u16 scratch, vertical pass + ops + store ----
+template <int SC>
+__global__ void __launch_bounds__(256) imp_blur_h_kernel(const ImpJob job, uint16_t* __restrict__ tmp) {
+    const uint8_t* blob = job.pass;
+    const ImpPass* __restrict__ P = reinterpret_cast<const ImpPass*>(blob);
+    const int w = P->sw, h = P->sh, n = P->ksize, r = n / 2;
+    const int x = blockIdx.x * TILE_W + threadIdx.x, y = blockIdx.y * TILE_H + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int* taps = reinterpret_cast<const int*>(blob + P->taps_off);
+    const uint8_t* row = job.src + (size_t)(P->sy0 + y) * job.src_pitch + (size_t)P->sx0 * SC;
+    unsigned acc[SC];
+#pragma unroll
+    for (int c = 0; c < SC; c++) acc[c] = 0;
+    for (int i = 0; i < n; i++) {
+        const int sx = min(max(x + i - r, 0), w - 1);
+        const unsigned k = (unsigned)__ldg(taps + i);
+#pragma unroll
+        for (int c = 0; c < SC; c++) acc[c] += (unsigned)__ldg(row + sx * SC + c) * k;
+    }
+#pragma unroll
+    for (int c = 0; c < SC; c++) tmp[((size_t)y * w + x) * SC + c] = (uint16_t)acc[c];
+}
+
+template <int SC>
+__global__ void __launch_bounds__(256) imp_blur_v_kernel(const ImpJob job, const uint16_t* __restrict__ tmp) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint8_t* blob = job.pass;
+    const ImpPass* __restrict__ P = reinterpret_cast<const ImpPass*>(blob);
+    OpsSmem os = stage_ops(P, blob, smem);
+    const int w = P->sw, h = P->sh, n = P->ksize, r = n / 2;
+    const int x = blockIdx.x * TILE_W + threadIdx.x, y = blockIdx.y * TILE_H + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int* taps = reinterpret_cast<const int*>(blob + P->taps_off);
+    unsigned acc[SC];
+#pragma unroll
+    for (int c = 0; c < SC; c++) acc[c] = 0;
+    for (int jj = 0; jj < n; jj++) {
+        const int sy = min(max(y + jj - r, 0), h - 1);
+        const unsigned k = (unsigned)__ldg(taps + jj);
+#pragma unroll
+        for (int c = 0; c < SC; c++) acc[c] += (unsigned)__ldg(tmp + ((size_t)sy * w + x) * SC + c) * k;
+    }
+    int v[4] = {0, 0, 0, 255};
+#pragma unroll
+    for (int c = 0; c < SC; c++) v[c] = (int)((acc[c] + 32768u) >> 16);
+    ImpPx p;
+    promote<SC>(v, p);
+    const int oc = P->oc;
+    imp_run_ops(p, oc, x, y, os.ops, P->nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
+    if (oc == 4) store_px<4>(job, P, x, y, p); else store_px<3>(job, P, x, y, p);
+}
+
+template <int KIND>
+cudaError_t launch_kind(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st) {
+    const int tiles = g.max_tiles;
+    const ImpJob dummy{};
+    const ImpJob& o = one ? *one : dummy;
+    dim3 block(TILE_W, TILE_H);
+    dim3 grid(tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);
+    switch (g.sc) {
+        case 1: imp_pass_kernel<KIND, 1><<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o); break;
+        case 3: imp_pass_kernel<KIND, 3><<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o); break;
+        case 4: imp_pass_kernel<KIND, 4><<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o); break;
+        default: return cudaErrorInvalidValue;
+    }
+    g_imp_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st) {
+    switch (g.kind) {
+        case IMP_G_COPY:      return launch_kind<IMP_G_COPY>(g, d_jobs, one, st);
+        case IMP_G_NN:        return launch_kind<IMP_G_NN>(g, d_jobs, one, st);
+        case IMP_G_AREA_INT:  return launch_kind<IMP_G_AREA_INT>(g, d_jobs, one, st);
+        case IMP_G_AREA_FRAC: return launch_kind<IMP_G_AREA_FRAC>(g, d_jobs, one, st);
+        case IMP_G_CUBIC:     return launch_kind<IMP_G_CUBIC>(g, d_jobs, one, st);
+        case IMP_G_LINEAR:    return launch_kind<IMP_G_LINEAR>(g, d_jobs, one, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t imp_launch_blur_generic(const ImpJob& job, const ImpPass& hdr, uint16_t* d_scratch, int smem_bytes, cudaStream_t st) {
+    dim3 block(TILE_W, TILE_H);
+    dim3 grid((hdr.sw + TILE_W - 1) / TILE_W, (hdr.sh + TILE_H - 1) / TILE_H);
+    switch (hdr.sc) {
+        case 3:
+            imp_blur_h_kernel<3><<<grid, block, 0, st>>>(job, d_scratch);
+            imp_blur_v_kernel<3><<<grid, block, smem_bytes, st>>>(job, d_scratch);
+            break;
+        case 4:
+            imp_blur_h_kernel<4><<<grid, block, 0, st>>>(job, d_scratch);
+            imp_blur_v_kernel<4><<<grid, block, smem_bytes, st>>>(job, d_scratch);
+            break;
+        default: return cudaErrorInvalidValue;
+    }
+    g_imp_launches += 2;
+    return cudaGetLastError();
+}

@@ -1,0 +1,252 @@
+// imp_pixel.cuh — per-pixel arithmetic of the filter chain, written once for device and host.
+//
+// Device code is the product. The host instantiation exists only so that the test suite can walk this
+// exact source on a machine without a GPU (a test-only harness under tests/, built with g++); the
+// shipped library never runs pixel math on the CPU.
+//
+// Every float operation below rounds exactly once, in the order the reference's C evaluates it
+// (SURVEY §8a "Spec check"): device code uses the __f*_rn intrinsics (never contracted into FMA), host
+// code is compiled with -ffp-contract=off. Stores through the reference's `char* imageData`
+// (helpers.h:2) are "truncate toward zero, keep the low byte", with x86's out-of-range result
+// (INT_MIN) reproduced by f2i_x86().
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include "imp_plan.h"
+
+#if defined(__CUDACC__)
+#define IMP_HD __host__ __device__ __forceinline__
+#else
+#define IMP_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define IMP_FMUL(a, b) __fmul_rn((a), (b))
+#define IMP_FADD(a, b) __fadd_rn((a), (b))
+#define IMP_FSUB(a, b) __fsub_rn((a), (b))
+#define IMP_FDIV(a, b) __fdiv_rn((a), (b))
+#define IMP_RINT(a)    __float2int_rn(a)
+#else
+#define IMP_FMUL(a, b) ((float)(a) * (float)(b))
+#define IMP_FADD(a, b) ((float)(a) + (float)(b))
+#define IMP_FSUB(a, b) ((float)(a) - (float)(b))
+#define IMP_FDIV(a, b) ((float)(a) / (float)(b))
+#define IMP_RINT(a)    ((int)lrintf(a))
+#endif
+
+struct ImpPx { int b, g, r, a; };
+
+// x86 cvttss2si: truncate; NaN / out of range -> 0x80000000.
+IMP_HD int imp_f2i_x86(float v) {
+    return (v > -2147483904.0f && v < 2147483648.0f) ? (int)v : (int)0x80000000;
+}
+IMP_HD int imp_f2b(float v) { return imp_f2i_x86(v) & 255; }
+IMP_HD int imp_sat8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+IMP_HD int imp_min(int a, int b) { return a < b ? a : b; }
+IMP_HD int imp_max(int a, int b) { return a > b ? a : b; }
+
+IMP_HD void imp_map_xy(const ImpFrameMap& m, int bx, int by, int& x, int& y) {
+    int u = m.swap ? by : bx, v = m.swap ? bx : by;
+    x = m.flipx ? m.w - 1 - u : u;
+    y = m.flipy ? m.h - 1 - v : v;
+}
+
+// helpers.c:70-107 RGB2HSV (integer; C division truncates toward zero).
+IMP_HD void imp_rgb2hsv(int b, int g, int r, int& h, int& s, int& v) {
+    int mn = imp_min(b, imp_min(g, r)), mx = imp_max(b, imp_max(g, r));
+    int delta = mx - mn;
+    h = 0; s = 0; v = mx;
+    if (v != 0) s = 255 * delta / v;
+    if (s != 0) {
+        if (mx == r)      h = 30 * (g - b) / delta;
+        else if (mx == g) h = 60 + 30 * (b - r) / delta;
+        else              h = 120 + 30 * (r - g) / delta;
+    }
+    if (h < 0) h += 180;
+}
+
+// helpers.c:109-176 HSV2RGB (float32; `default:` also takes sector 6, i.e. H == 180).
+// Inputs are the BYTES the reference would have stored (0..255).
+IMP_HD void imp_hsv2rgb(int H, int S, int V, int& b, int& g, int& r) {
+    float v = (float)V;
+    if (S == 0) { r = g = b = V; return; }
+    float s = IMP_FDIV((float)S, 255.0f);
+    float h = IMP_FDIV((float)(H * 2), 60.0f);
+    int i = (int)floorf(h);
+    float f = IMP_FSUB(h, (float)i);
+    // v in [0,255], factors in [0,1]: plain truncation is in range
+    int p = (int)IMP_FMUL(v, IMP_FSUB(1.0f, s));
+    int q = (int)IMP_FMUL(v, IMP_FSUB(1.0f, IMP_FMUL(s, f)));
+    int t = (int)IMP_FMUL(v, IMP_FSUB(1.0f, IMP_FMUL(s, IMP_FSUB(1.0f, f))));
+    switch (i) {
+        case 0:  r = V; g = t; b = p; break;
+        case 1:  r = q; g = V; b = p; break;
+        case 2:  r = p; g = V; b = t; break;
+        case 3:  r = p; g = q; b = V; break;
+        case 4:  r = t; g = p; b = V; break;
+        default: r = V; g = p; b = q; break;
+    }
+    b &= 255; g &= 255; r &= 255;
+}
+
+// filters.c:524-547: (int)fmin(c*k/100.0, 255) stored through char == C-truncating (c*k)/100 capped at
+// 255, low byte (SURVEY §8a "Simplifications"); the int product wraps like the reference's.
+IMP_HD int imp_modulate_scale(int c, int k) {
+    int t = (int)((unsigned)c * (unsigned)k);
+    int q = t / 100;
+    return (q > 255 ? 255 : q) & 255;
+}
+
+IMP_HD void imp_op_modulate(ImpPx& p, int dh, int ks, int kv) {
+    int h, s, v;
+    imp_rgb2hsv(p.b, p.g, p.r, h, s, v);
+    if (dh != 0) { h += dh; if (h > 180) h -= 180; h &= 255; }
+    s = imp_modulate_scale(s, ks);
+    v = imp_modulate_scale(v, kv);
+    imp_hsv2rgb(h, s, v, p.b, p.g, p.r);
+}
+
+// filters.c:608-616: px[c] = (char)(beta*px[c] + rgb[2-c]*alpha); ca[] = rgb[2-c]*alpha from the host.
+IMP_HD void imp_op_addcolor(ImpPx& p, float beta, float cb, float cg, float cr) {
+    p.b = imp_f2b(IMP_FADD(IMP_FMUL(beta, (float)p.b), cb));
+    p.g = imp_f2b(IMP_FADD(IMP_FMUL(beta, (float)p.g), cg));
+    p.r = imp_f2b(IMP_FADD(IMP_FMUL(beta, (float)p.r), cr));
+}
+
+// filters.c:595-605: val = (int)(ct*val + br*255); clamp to [0,255]. br255 = br*255 from the host.
+IMP_HD int imp_contrast1(int v, float ct, float br255) {
+    return imp_sat8(imp_f2i_x86(IMP_FADD(IMP_FMUL(ct, (float)v), br255)));
+}
+
+// filters.c:335-346: fmax(fmin(v*1.5-50,255),0) truncated == (3v-100)>>1 clamped.
+IMP_HD int imp_lomo1(int v) {
+    int t = 3 * v - 100;
+    return t < 0 ? 0 : imp_min(t >> 1, 255);
+}
+
+// filters.c:356-403 Rainbow on HSV bytes; returns via hsv2rgb. Hue bytes are (char)(hue/2.0).
+IMP_HD void imp_op_rainbow(ImpPx& p, int sat) {
+    int h, s, v;
+    imp_rgb2hsv(p.b, p.g, p.r, h, s, v);
+    int hue = h * 2, light = v, saturation = sat, hb;
+    if (light < 20) { light = 0; saturation = 0; hb = h; }
+    else if (light > 254) { saturation = 0; hb = h; }
+    else if (hue <= 10 || hue > 340) hb = 0;
+    else if (hue < 35) hb = 15;
+    else if (hue < 68) hb = 30;
+    else if (hue < 150) hb = 60;
+    else if (hue < 200) hb = 97;     // 195/2.0 = 97.5 -> 97
+    else if (hue < 250) hb = 112;    // 225/2.0 = 112.5 -> 112
+    else hb = 142;                   // 285/2.0 = 142.5 -> 142 (run-time truncation, App. C-1)
+    imp_hsv2rgb(hb, saturation & 255, light, p.b, p.g, p.r);
+}
+
+// filters.c:405-455 Scanline: every row takes the HSV round trip; rows with freq <= (y mod period) <
+// freq+width get S,V overwritten (closed form of the row state machine).
+IMP_HD void imp_op_scanline(ImpPx& p, int y, int period, int freq, int sbyte, int vbyte) {
+    int h, s, v;
+    imp_rgb2hsv(p.b, p.g, p.r, h, s, v);
+    int ph = y % period;
+    if (ph >= freq && ph < period - 1) { s = sbyte; v = vbyte; }
+    imp_hsv2rgb(h, s, v, p.b, p.g, p.r);
+}
+
+// filters.c:693-703 RadialGradient + helpers.c:46-48 Dist for one pixel.
+// dx*dx+dy*dy is exact in double, sqrt is correctly rounded, narrowing matches the reference; cos and
+// the 4th power are double, then narrowed (libm vs CUDA may differ in the last double ulp, which the
+// float narrowing hides except with probability ~2^-29: tested as <= 1 LSB).
+IMP_HD float imp_vignette_mask(int x, int y, int cx, int cy, float maxr, float intensity) {
+    double dx = (double)(cx - x), dy = (double)(cy - y);
+    float distance = (float)sqrt(dx * dx + dy * dy);
+    float raw = IMP_FMUL(IMP_FDIV(distance, maxr), intensity);
+    double c = cos((double)raw);
+    double c2 = c * c;
+    return (float)(c2 * c2);
+}
+
+IMP_HD void imp_op_vignette(ImpPx& p, int x, int y, int cx, int cy, float maxr, float intensity) {
+    float mask = imp_vignette_mask(x, y, cx, cy, maxr, intensity);
+    int h, s, v;
+    imp_rgb2hsv(p.b, p.g, p.r, h, s, v);
+    v = imp_f2b(IMP_FMUL((float)v, mask));
+    imp_hsv2rgb(h, s, v, p.b, p.g, p.r);
+}
+
+// x/255.0 narrowed to float == x/255.0f correctly rounded for every byte x (checked exhaustively in
+// the CPU test suite, test_alpha_unit_identity), so one IEEE float division replaces the double divide + narrowing.
+IMP_HD float imp_alpha_unit(int a) { return IMP_FDIV((float)a, 255.0f); }
+
+// filters.c:619-662 AlphaBlendOver for one pixel. alpha = 1 - opacity (host float).
+// dst_has_a / src_has_a: nChannels == 4.
+IMP_HD void imp_op_over(ImpPx& d, bool dst_has_a, int sb, int sg, int sr, int sa, bool src_has_a, float alpha) {
+    float dA = dst_has_a ? imp_alpha_unit(d.a) : 1.0f;
+    float sA = src_has_a ? imp_alpha_unit(sa) : 1.0f;
+    sA = IMP_FSUB(sA, alpha);
+    sA = sA > 0.0f ? sA : 0.0f;                      // fmax(sA - alpha, 0)
+    float one_m = IMP_FSUB(1.0f, sA);
+    float tA = IMP_FADD(sA, IMP_FMUL(dA, one_m));
+    if (tA == 0.0f) { d.b = d.g = d.r = 0; }
+    else {
+        d.b = imp_f2i_x86(IMP_FDIV(IMP_FADD(IMP_FMUL((float)sb, sA), IMP_FMUL(IMP_FMUL((float)d.b, dA), one_m)), tA)) & 255;
+        d.g = imp_f2i_x86(IMP_FDIV(IMP_FADD(IMP_FMUL((float)sg, sA), IMP_FMUL(IMP_FMUL((float)d.g, dA), one_m)), tA)) & 255;
+        d.r = imp_f2i_x86(IMP_FDIV(IMP_FADD(IMP_FMUL((float)sr, sA), IMP_FMUL(IMP_FMUL((float)d.r, dA), one_m)), tA)) & 255;
+    }
+    if (dst_has_a) d.a = imp_f2b(IMP_FMUL(tA, 255.0f));
+}
+
+// filters.c:666-687 BlendWithPaper for one pixel.
+IMP_HD void imp_op_paper(ImpPx& p) {
+    float diff = (float)(255 - p.a);
+    float pa = imp_alpha_unit(p.a);
+    p.b = imp_f2i_x86(IMP_FADD(diff, IMP_FMUL((float)p.b, pa))) & 255;
+    p.g = imp_f2i_x86(IMP_FADD(diff, IMP_FMUL((float)p.g, pa))) & 255;
+    p.r = imp_f2i_x86(IMP_FADD(diff, IMP_FMUL((float)p.r, pa))) & 255;
+    p.a = 255;
+}
+
+// Runs the op list of a pass on one pixel at base coordinates (bx,by).
+// lut: the pass's LUT area; wm*: this job's watermark.
+IMP_HD void imp_run_ops(ImpPx& p, int oc, int bx, int by, const ImpOp* ops, int nops, const uint8_t* lut,
+                        const uint8_t* wm, int wm_pitch, int wm_c) {
+    for (int k = 0; k < nops; k++) {
+        const ImpOp& op = ops[k];
+        switch (op.kind) {
+            case IMP_OP_MODULATE: imp_op_modulate(p, op.i[0], op.i[1], op.i[2]); break;
+            case IMP_OP_ADDCOLOR: imp_op_addcolor(p, op.f[0], op.f[1], op.f[2], op.f[3]); break;
+            case IMP_OP_LUT_ALL: {
+                const uint8_t* t = lut + op.i[0];
+                p.b = t[p.b]; p.g = t[p.g]; p.r = t[p.r];
+                if (oc == 4) p.a = t[p.a];
+            } break;
+            case IMP_OP_CONTRAST:
+                p.b = imp_contrast1(p.b, op.f[0], op.f[1]);
+                p.g = imp_contrast1(p.g, op.f[0], op.f[1]);
+                p.r = imp_contrast1(p.r, op.f[0], op.f[1]);
+                break;
+            case IMP_OP_GRADMAP: {
+                const uint8_t* t = lut + op.i[0] + ((p.r + p.g + p.b) / 3) * 3;
+                p.r = t[0]; p.g = t[1]; p.b = t[2];
+            } break;
+            case IMP_OP_VIGNETTE: {
+                int x, y; imp_map_xy(op.map, bx, by, x, y);
+                imp_op_vignette(p, x, y, op.i[0], op.i[1], op.f[0], op.f[1]);
+            } break;
+            case IMP_OP_LOMO: p.g = imp_lomo1(p.g); p.r = imp_lomo1(p.r); break;
+            case IMP_OP_RAINBOW: imp_op_rainbow(p, op.i[0]); break;
+            case IMP_OP_SCANLINE: {
+                int x, y; imp_map_xy(op.map, bx, by, x, y);
+                imp_op_scanline(p, y, op.i[0], op.i[1], op.i[3], op.i[4]);
+            } break;
+            case IMP_OP_WATERMARK: {
+                int x, y; imp_map_xy(op.map, bx, by, x, y);
+                int wx = x - op.i[0], wy = y - op.i[1];
+                if (wx >= 0 && wy >= 0 && wx < op.i[2] && wy < op.i[3]) {
+                    const uint8_t* s = wm + (size_t)wy * wm_pitch + (size_t)wx * wm_c;
+                    imp_op_over(p, oc == 4, s[0], s[1], s[2], wm_c == 4 ? s[3] : 255, wm_c == 4, op.f[0]);
+                }
+            } break;
+            case IMP_OP_PAPER: if (oc == 4) imp_op_paper(p); break;
+            default: break;
+        }
+    }
+}

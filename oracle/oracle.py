@@ -313,6 +313,8 @@ def parse_crop(args: str, gravity: Optional[str], col: int, row: int):
         return IMP_ERROR_INVALID_ARGS, None
     if x + ww > col or y + wh > row:
         return IMP_ERROR_INVALID_ARGS, None
+    if x < 0 or y < 0:
+        return IMP_ERROR_INVALID_ARGS, None      # reference: cvCopy size-mismatch assert inside OpenCV
     return IMP_OK, (x, y, ww, wh)
 
 
@@ -334,6 +336,10 @@ def parse_resize(args: str, col: int, row: int, cfg: OracleConfig, simple: bool)
         h = min(h, row)
     if (cfg.max_w > 0 and w > cfg.max_w) or (cfg.max_h > 0 and w > cfg.max_h):   # sic: width twice (bridge.c:184)
         return IMP_ERROR_TOO_BIG_TARGET, None
+    if w == 0 or h == 0:
+        return IMP_ERROR_INVALID_ARGS, None      # reference: cvCreateImage error inside OpenCV
+    if w > 65535 or h > 65535:
+        return IMP_ERROR_TOO_BIG_TARGET, None    # documented hard cap of the GPU path
     mode = NN if simple else (CUBIC if (w > col or h > row) else AREA)
     return IMP_OK, (w, h, mode)
 
