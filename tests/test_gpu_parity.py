@@ -1,0 +1,273 @@
+"""GPU parity tests (run on a real B200 with -m gpu). Everything goes through the C ABI of
+libimp_gpu.so (ngx_http_imgproc_b200.api is a thin ctypes binding) and is compared with the oracle:
+bit-exact everywhere except Vignette, where CUDA's and glibc's double-precision cos may differ in the
+last ulp (tolerance 1 LSB, and the mismatch count must stay tiny)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import golden_util as G
+from conftest import rnd_image, smooth_image
+from ngx_http_imgproc_b200 import api
+from test_planner_host import REQS, _oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_run(gpu, img, cfgkw, rq):
+    code, step, plan = gpu.try_plan(img.shape[1], img.shape[0], img.shape[2], api.Config(**cfgkw), **rq)
+    if code:
+        return code, step, None
+    try:
+        return 0, step, plan.run_host(img)
+    finally:
+        plan.close()
+
+
+def _assert_same(out, ref, rq, tol_ok):
+    assert out.shape == ref.shape, (rq, out.shape, ref.shape)
+    d = np.abs(out.astype(int) - ref.astype(int))
+    if tol_ok:
+        assert d.max() <= G.VIGNETTE_TOL, (rq, int(d.max()))
+        assert (d > 0).mean() < 1e-3, (rq, float((d > 0).mean()))
+    else:
+        assert d.max() == 0, (rq, int(d.max()), int((d > 0).sum()), d.size)
+
+
+def _has_vignette(rq):
+    return any("vignette" in f for f in rq.get("filters", []) or [])
+
+
+def test_kernels_actually_launch(gpu):
+    before = gpu.launch_count()
+    out = gpu.run(rnd_image(0, 16, 16, 3), resize="8,8")
+    assert out.shape == (8, 8, 3) and gpu.launch_count() > before
+
+
+@pytest.mark.parametrize("case", G.load(), ids=lambda c: c["name"])
+def test_golden_vectors(gpu, case):
+    """Vectors produced by the reference's own code + cv2 in the build container."""
+    req = G.split_query(case["query"])
+    code, step, out = _gpu_run(gpu, case["img"], case["cfgkw"], req)
+    assert code == case["code"]
+    if code:
+        return
+    _assert_same(out, case["out"], case["query"], "vignette" in case["query"])
+
+
+def test_request_matrix_vs_oracle(gpu, orc):
+    wm, wm3 = rnd_image(7, 12, 20, 4), rnd_image(8, 7, 9, 3)
+    cfgkws = [dict(),
+              dict(allow_experiments=True, max_filters=8, watermark=wm, wm_gravity_x="r", wm_gravity_y="b", wm_offset_x=3, wm_offset_y=2, wm_opacity=60),
+              dict(allow_experiments=True, watermark=wm3, wm_gravity_x="c", wm_gravity_y="c", wm_offset_x=-4, wm_offset_y=5, wm_opacity=100),
+              dict(max_w=100, max_h=50, watermark=wm, wm_gravity_x="l", wm_gravity_y="t", wm_offset_x=-5, wm_offset_y=-3, wm_opacity=37)]
+    n = 0
+    for ci, kw in enumerate(cfgkws):
+        for (h, w, c) in [(60, 80, 3), (45, 64, 4), (33, 47, 1), (48, 64, 3)]:
+            img = rnd_image(100 + ci, h, w, c) if ci % 2 == 0 else smooth_image(100 + ci, h, w, c)
+            for rq in REQS:
+                code, step, out = _gpu_run(gpu, img, kw, rq)
+                c2, s2, o2 = _oracle(orc, img, rq, kw)
+                assert code == c2 and (not code or step == s2), (ci, rq)
+                if not code:
+                    _assert_same(out, o2, (ci, (h, w, c), rq), _has_vignette(rq))
+                n += 1
+    assert n > 800
+
+
+FILTERS = ["flip=10", "flip=01", "flip=11", "rotate=90", "rotate=180", "rotate=270", "modulate=0,0,100", "modulate=60,70,80",
+           "modulate=100,500,500", "modulate=180,-50,100", "colorize=704214,0.6", "colorize=ff0000", "gamma=1.3", "gamma=0.5",
+           "contrast=1.5", "contrast=0.5", "contrast=3.7", "gradmap=306090,eecc00", "gradmap=000000,ff0000,ffffff", "vignette=0.8",
+           "vignette=4,3", "vignette=0.5,0.7", "gotham=1", "lomo=1", "kelvin=1", "rainbow=full", "rainbow=mid", "rainbow=pale",
+           "scanline=0", "scanline=0.5,0.25,1,1", "scanline=0.3,0.9,2,3", "blur=0.5", "blur=1", "blur=2.3", "blur=6"]
+
+
+@pytest.mark.parametrize("f", FILTERS)
+def test_each_filter_all_byte_values(gpu, orc, f):
+    """Every filter on an image holding all 2^24 BGR triples' worth of variety: a 256x256 ramp grid + noise,
+    3- and 4-channel, odd sizes so that widthStep != w*C."""
+    kw = dict(allow_experiments=True)
+    b, g = np.mgrid[0:256, 0:256].astype(np.uint8)
+    for c in (3, 4):
+        img = np.zeros((256, 256, c), np.uint8)
+        img[:, :, 0], img[:, :, 1] = b, g
+        img[:, :, 2] = rnd_image(1, 256, 256, 1)[:, :, 0]
+        if c == 4:
+            img[:, :, 3] = rnd_image(2, 256, 256, 1)[:, :, 0]
+        for im in (img, rnd_image(5, 131, 67, c)):
+            code, _, out = _gpu_run(gpu, im, kw, dict(filters=[f]))
+            c2, _, o2 = _oracle(orc, im, dict(filters=[f]), kw)
+            assert code == c2 == 0
+            _assert_same(out, o2, f, "vignette" in f)
+
+
+def test_resize_fuzz_vs_oracle(gpu, orc):
+    """Random size pairs for every interpolation the path has (NN, AREA int/frac, CUBIC, LINEAR)."""
+    rng = np.random.default_rng(42)
+    cfg = dict(max_w=0, max_h=0)
+    for it in range(150):
+        sw, sh = int(rng.integers(1, 200)), int(rng.integers(1, 150))
+        dw, dh = int(rng.integers(1, 260)), int(rng.integers(1, 200))
+        c = int(rng.choice([1, 3, 4]))
+        img = rng.integers(0, 256, (sh, sw, c), dtype=np.uint8)
+        for rq in (dict(resize=f"{dw},{dh},up"), dict(resize=f"{dw},{dh},up", simple=True), dict(resize=f"{dw},{dh},up", interp=1), dict(resize=f"{dw},{dh}")):
+            code, _, out = _gpu_run(gpu, img, cfg, rq)
+            c2, _, o2 = _oracle(orc, img, rq, cfg)
+            assert code == c2 == 0, rq
+            _assert_same(out, o2, (sw, sh, c, rq), False)
+
+
+def test_edge_shapes(gpu, orc):
+    kw = dict(allow_experiments=True, max_filters=8)
+    for (h, w, c) in [(1, 1, 3), (1, 1, 4), (1, 7, 1), (9, 1, 4), (2, 3, 3), (8, 32, 4), (9, 33, 3), (257, 3, 3)]:
+        img = rnd_image(h * 31 + w, h, w, c)
+        for rq in [dict(), dict(filters=["blur=2.3"]), dict(filters=["blur=12"]), dict(resize="5,4,up"), dict(resize="1,1"),
+                   dict(filters=["rotate=90", "vignette=0.8", "blur=1"]), dict(filters=["gotham=1", "rotate=270"]), dict(flatten=True)]:
+            code, _, out = _gpu_run(gpu, img, kw, rq)
+            c2, _, o2 = _oracle(orc, img, rq, kw)
+            assert code == c2, ((h, w, c), rq)
+            if not code:
+                _assert_same(out, o2, ((h, w, c), rq), _has_vignette(rq))
+    for v in (0, 255):
+        img = np.full((40, 50, 4), v, np.uint8)
+        for rq in [dict(filters=["kelvin=1"]), dict(resize="20,13"), dict(flatten=True), dict(filters=["modulate=90,200,50"])]:
+            _, _, out = _gpu_run(gpu, img, kw, rq)
+            _assert_same(out, _oracle(orc, img, rq, kw)[2], rq, False)
+
+
+# ---- the five BASELINE.json configurations ------------------------------------------------------------------
+def test_cfg1_1080p_to_640x360(gpu, orc):
+    img = rnd_image(1, 1080, 1920, 3)
+    for rq in (dict(resize="640,360"), dict(resize="640,360", interp=1)):
+        out = _gpu_run(gpu, img, {}, rq)[2]
+        _assert_same(out, _oracle(orc, img, rq, {})[2], rq, False)
+
+
+def test_cfg2_4k_crop_area_watermark_full_size(gpu, orc):
+    img = smooth_image(2, 2160, 3840, 4)
+    wm = rnd_image(3, 64, 256, 4)
+    wm[:, :, 3] = np.linspace(0, 255, 256).astype(np.uint8)[None, :]
+    kw = dict(watermark=wm, wm_gravity_x="r", wm_gravity_y="b", wm_offset_x=10, wm_offset_y=10, wm_opacity=60)
+    rq = dict(crop="3600px,2025px,c,c", resize="800,450")
+    out = _gpu_run(gpu, img, kw, rq)[2]
+    assert out.shape == (450, 800, 4)
+    _assert_same(out, _oracle(orc, img, rq, kw)[2], rq, False)
+
+
+def test_cfg3_gif_frames_cubic_sepia_batched(gpu, orc):
+    """200 frames 480x270x4 -> cubic 2x + sepia as ONE batch launch; every frame checked."""
+    base = smooth_image(4, 270, 480, 4)
+    base[:, :, 3] = np.where(base[:, :, 3] > 127, 255, 0)
+    frames = [np.roll(base, (i, 2 * i), (0, 1)) for i in range(200)]
+    rq = dict(resize="960,540,up", filters=["modulate=0,0,100", "colorize=704214,0.6"])
+    outs = _device_batch(gpu, frames, [rq] * 200, {})
+    for i in (0, 1, 57, 199):
+        _assert_same(outs[i], _oracle(orc, frames[i], rq, {})[2], (i, rq), False)
+    nn = dict(resize="960,540,up", simple=True, filters=rq["filters"])
+    _assert_same(_gpu_run(gpu, frames[3], {}, nn)[2], _oracle(orc, frames[3], nn, {})[2], nn, False)
+
+
+def test_cfg4_12mp_blur_vignette_rotate_full_size(gpu, orc):
+    img = smooth_image(5, 3000, 4000, 3)
+    kw = dict(allow_experiments=True)
+    rq = dict(filters=["blur=2.3", "vignette=0.8", "rotate=90"])
+    out = _gpu_run(gpu, img, kw, rq)[2]
+    assert out.shape == (4000, 3000, 3)
+    _assert_same(out, _oracle(orc, img, rq, kw)[2], rq, True)
+
+
+def test_cfg5_thumbnail_farm_sample(gpu, orc):
+    """Mixed-size sources -> 256x256 + watermark in one batch (sizes as in SURVEY §8d cfg5, 24 jobs)."""
+    rng = np.random.default_rng(6)
+    wm = rnd_image(61, 64, 64, 4)
+    kw = dict(max_w=0, max_h=0, watermark=wm, wm_gravity_x="r", wm_gravity_y="b", wm_offset_x=8, wm_offset_y=8, wm_opacity=100)
+    imgs, rqs = [], []
+    for i in range(24):
+        w, h = int(rng.integers(320, 2049)), int(rng.integers(240, 1537))
+        c = 3 if rng.random() < 0.75 else 4
+        imgs.append(rnd_image(600 + i, h, w, c))
+        rqs.append(dict(resize="256,256"))
+    imgs.append(rnd_image(700, 512, 1024, 3)); rqs.append(dict(resize="256,256"))      # integer 4x2
+    outs = _device_batch(gpu, imgs, rqs, kw)
+    for i in range(len(imgs)):
+        _assert_same(outs[i], _oracle(orc, imgs[i], rqs[i], kw)[2], (i, imgs[i].shape), False)
+
+
+# ---- batch / farm API ------------------------------------------------------------------------------------------
+def _device_batch(gpu, imgs, rqs, cfgkw):
+    """imp_gpu_batch_* over device-resident frames (uploads with the ABI's own helpers)."""
+    L = gpu.lib
+    plans, bufs, outs = [], [], []
+    batch = api.Batch(gpu)
+    for img, rq in zip(imgs, rqs):
+        img = np.ascontiguousarray(img)
+        p = gpu.plan(img.shape[1], img.shape[0], img.shape[2], api.Config(**cfgkw), **rq)
+        d_in, d_out, pi, po = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+        gpu.check(L.imp_gpu_malloc_pitch(C.byref(d_in), C.byref(pi), img.shape[1] * img.shape[2], img.shape[0]))
+        gpu.check(L.imp_gpu_malloc_pitch(C.byref(d_out), C.byref(po), p.out_w * p.out_c, p.out_h))
+        gpu.check(L.imp_gpu_upload_2d(d_in, pi.value, img.ctypes.data, img.strides[0], img.shape[1] * img.shape[2], img.shape[0], None))
+        batch.add(p, d_in.value, pi.value, d_out.value, po.value)
+        plans.append(p); bufs.append((d_in, d_out, po.value))
+    gpu.check(L.imp_gpu_sync(None))
+    before = gpu.launch_count()
+    batch.launch()
+    gpu.check(L.imp_gpu_sync(None))
+    assert gpu.launch_count() - before == batch.launches_per_run
+    for p, (d_in, d_out, po) in zip(plans, bufs):
+        out = np.empty((p.out_h, p.out_w, p.out_c), np.uint8)
+        gpu.check(L.imp_gpu_download_2d(out.ctypes.data, out.strides[0], d_out, po, p.out_w * p.out_c, p.out_h, None))
+        outs.append(out)
+    gpu.check(L.imp_gpu_sync(None))
+    for p, (d_in, d_out, po) in zip(plans, bufs):
+        L.imp_gpu_free(d_in); L.imp_gpu_free(d_out); p.close()
+    batch.close()
+    return outs
+
+
+def test_batch_mixed_plans_one_launch_per_variant(gpu, orc):
+    kw = dict(allow_experiments=True, max_filters=8)
+    rqs = [dict(resize="40,30"), dict(resize="41,29"), dict(filters=["blur=1.5", "gamma=1.2"]), dict(resize="100,90,up"),
+           dict(filters=["rotate=90"]), dict(resize="20,20", filters=["blur=2", "kelvin=1", "blur=0.7"]), dict(crop="30px,30px,c,c", resize="17,19")]
+    imgs = [rnd_image(i, 50 + i, 60 + 2 * i, 3 if i % 2 else 4) for i in range(len(rqs))]
+    outs = _device_batch(gpu, imgs, rqs, kw)
+    for img, rq, out in zip(imgs, rqs, outs):
+        _assert_same(out, _oracle(orc, img, rq, kw)[2], rq, False)
+
+
+def test_host_batch_and_farm_match_single_runs(gpu, orc):
+    kw = dict(max_w=0, max_h=0)
+    imgs = [smooth_image(i, 300 + 7 * i, 400 + 5 * i, 3 if i % 3 else 4) for i in range(9)]
+    rq = dict(crop="1,1", resize="128,128", filters=["gamma=1.1"])
+    plans = [gpu.plan(im.shape[1], im.shape[0], im.shape[2], api.Config(**kw), **rq) for im in imgs]
+    dsts = [np.zeros((p.out_h, p.out_w, p.out_c), np.uint8) for p in plans]
+    api.run_host_batch(gpu, plans, imgs, dsts, n_streams=3)
+    for im, d in zip(imgs, dsts):
+        _assert_same(d, _oracle(orc, im, rq, kw)[2], rq, False)
+    n_gpus = min(2, gpu.device_count())
+    dsts2 = [np.zeros_like(d) for d in dsts]
+    api.run_host_batch(gpu, plans, imgs, dsts2, n_streams=2, n_gpus=n_gpus)
+    for a, b in zip(dsts, dsts2):
+        assert np.array_equal(a, b)
+    for p in plans:
+        p.close()
+
+
+# ---- size-independent properties at full sizes --------------------------------------------------------------------
+def test_properties_full_size(gpu):
+    img = rnd_image(9, 3000, 4000, 3)
+    r = img
+    for _ in range(4):
+        r = gpu.run(r, filters=["rotate=90"])
+    assert np.array_equal(r, img)                                             # four quarter turns = identity
+    assert np.array_equal(gpu.run(gpu.run(img, filters=["flip=11"]), filters=["rotate=180"]), img)
+    assert np.array_equal(gpu.run(img, filters=["rotate=90"]), np.ascontiguousarray(np.rot90(img, -1)))
+    assert np.array_equal(gpu.run(img, crop="1000px,700px,37px,91px"), img[91:791, 37:1037])
+    a = gpu.run(img, crop="3000px,2000px,c,c", resize="750,500")
+    b = gpu.run(np.ascontiguousarray(img[500:2500, 500:3500]), resize="750,500")
+    assert np.array_equal(a, b)                                               # crop folded into the gather == crop then resize
+    c1 = gpu.run(img, filters=["blur=2.3", "rotate=90"])
+    c2 = gpu.run(gpu.run(img, filters=["rotate=90"]), filters=["blur=2.3"])
+    assert np.array_equal(c1, c2)                                             # blur commutes with the dihedral maps
+    flat = np.full((1500, 2000, 4), 77, np.uint8)
+    assert (gpu.run(flat, resize="333,211") == 77).all() and (gpu.run(flat, filters=["blur=6"]) == 77).all()
