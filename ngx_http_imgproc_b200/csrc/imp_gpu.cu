@@ -146,6 +146,21 @@ ImpJob make_job(const imp_gpu_plan* p, int d, size_t k, const uint8_t* src, int 
 
 int pass_tiles(const ImpPass& h) { return ((h.bw + 31) / 32) * ((h.bh + 7) / 8); }
 
+// Tile (shared-memory, TMA-staged) variant: needs 16-byte addressable source rows — pitch % 16 == 0 and
+// either the image rows or the window rows start 16-byte aligned (imp_tiles.cuh) — and a footprint that fits.
+int pick_variant(const ImpPass& h, const ImpJob& j) {
+    if (h.tile_smem <= 0) return 0;
+    if (j.src_pitch % 16) return 0;
+    const uintptr_t img = (uintptr_t)j.src;
+    const uintptr_t win = img + (size_t)h.sy0 * j.src_pitch + (size_t)h.sx0 * h.sc;
+    if (img % 16 && win % 16) return 0;
+    return 1;
+}
+int tile_smem_bytes(const ImpPass& h) {
+    const int ops = (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15;
+    return 16 + ((ops + 127) & ~127) + 112 + h.tile_smem + 64;      // +64: padded taps of the last row
+}
+
 int batch_compile(imp_gpu_batch* b) {
     const int d = t_dev;
     b->dev = d;
@@ -167,21 +182,26 @@ int batch_compile(imp_gpu_batch* b) {
         CK(cudaMalloc((void**)&b->d_scratch, scratch));
         b->scratch_cap = scratch;
     }
-    struct Pending { int kind, sc; ImpJob job; ImpPass hdr; size_t boff; };
+    struct Pending { int kind, sc, variant, tmax; ImpJob job; ImpPass hdr; size_t boff; };
     for (int k = 0; k < max_passes; k++) {
         std::vector<Pending> pend;
         for (size_t i = 0; i < b->items.size(); i++) {
             const auto& it = b->items[i];
             if ((int)it.plan->passes.size() <= k) continue;
             const ImpHostPass& hp = it.plan->passes[k];
-            pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->d_scratch, off[i]), hp.hdr, boff[i][k]});
+            ImpJob jb = make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->d_scratch, off[i]);
+            const int variant = pick_variant(hp.hdr, jb);
+            pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, 0, jb, hp.hdr, boff[i][k]});
         }
         std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& c) {
-            return a.kind != c.kind ? a.kind < c.kind : a.sc < c.sc; });
+            if (a.kind != c.kind) return a.kind < c.kind;
+            if (a.sc != c.sc) return a.sc < c.sc;
+            if (a.variant != c.variant) return a.variant < c.variant;
+            return a.tmax < c.tmax; });
         size_t s = 0;
         while (s < pend.size()) {
             size_t e = s;
-            while (e < pend.size() && pend[e].kind == pend[s].kind && pend[e].sc == pend[s].sc) e++;
+            while (e < pend.size() && pend[e].kind == pend[s].kind && pend[e].sc == pend[s].sc && pend[e].variant == pend[s].variant && pend[e].tmax == pend[s].tmax) e++;
             if (pend[s].kind == IMP_G_BLUR) {
                 for (size_t j = s; j < e; j++) {
                     imp_gpu_batch::Step st{};
@@ -194,10 +214,10 @@ int batch_compile(imp_gpu_batch* b) {
                 imp_gpu_batch::Step st{};
                 st.generic_blur = false;
                 st.g.kind = pend[s].kind; st.g.sc = pend[s].sc; st.g.first = (int)b->h_jobs.size(); st.g.count = (int)(e - s);
-                st.g.max_tiles = 0; st.g.smem_bytes = 16;
+                st.g.max_tiles = 0; st.g.smem_bytes = 16; st.g.variant = pend[s].variant; st.g.tmax = pend[s].tmax;
                 for (size_t j = s; j < e; j++) {
                     st.g.max_tiles = std::max(st.g.max_tiles, pass_tiles(pend[j].hdr));
-                    st.g.smem_bytes = std::max(st.g.smem_bytes, ops_smem(pend[j].hdr));
+                    st.g.smem_bytes = std::max(st.g.smem_bytes, pend[s].variant ? tile_smem_bytes(pend[j].hdr) : ops_smem(pend[j].hdr));
                     b->h_jobs.push_back(pend[j].job);
                 }
                 b->steps.push_back(st); b->launches += 1;
@@ -227,7 +247,9 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
         if (hp.hdr.kind == IMP_G_BLUR) {
             CK(imp_launch_blur_generic(j, hp.hdr, (uint16_t*)(scratch + boff[k]), ops_smem(hp.hdr), st));
         } else {
-            ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, pass_tiles(hp.hdr), ops_smem(hp.hdr)};
+            const int variant = pick_variant(hp.hdr, j);
+            ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, pass_tiles(hp.hdr), variant ? tile_smem_bytes(hp.hdr) : ops_smem(hp.hdr),
+                             variant, 0};
             CK(imp_launch_group(g, nullptr, &j, st));
         }
     }

@@ -7,6 +7,7 @@
 // grid = (tiles, jobs). See DESIGN.md §Kernels for the roofline of each variant.
 #include "imp_internal.h"
 #include "imp_gather.cuh"
+#include "imp_tiles.cuh"
 
 #include <atomic>
 static std::atomic<unsigned long long> g_imp_launches{0};
@@ -167,7 +168,34 @@ cudaError_t launch_kind(const ImpLaunchGroup& g, const ImpJob* d_jobs, const Imp
 
 }  // namespace
 
+template <int SC>
+cudaError_t launch_area_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
+    static bool attr_set[16] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    auto kern = imp_tiles::imp_area_frac_tile_kernel<SC>;
+    if (!attr_set[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 15] = true;
+    }
+    dim3 block(imp_tiles::TW, imp_tiles::TH);
+    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);
+    kern<<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o);
+    g_imp_launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st) {
+    if (g.variant == 1 && g.kind == IMP_G_AREA_FRAC) {
+        const ImpJob dummy{};
+        const ImpJob& o = one ? *one : dummy;
+        switch (g.sc) {
+            case 1: return launch_area_tile<1>(g, d_jobs, o, st);
+            case 3: return launch_area_tile<3>(g, d_jobs, o, st);
+            case 4: return launch_area_tile<4>(g, d_jobs, o, st);
+        }
+        return cudaErrorInvalidValue;
+    }
     switch (g.kind) {
         case IMP_G_COPY:      return launch_kind<IMP_G_COPY>(g, d_jobs, one, st);
         case IMP_G_NN:        return launch_kind<IMP_G_NN>(g, d_jobs, one, st);

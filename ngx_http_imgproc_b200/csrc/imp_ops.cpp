@@ -1,0 +1,229 @@
+// imp_ops.cpp — reference-signature operators (include/imp_ops.h): record + validate now, run fused later.
+#include "../../include/imp_ops.h"
+#include "imp_internal.h"
+#include <string.h>
+#include <stdlib.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Pending {
+    // the decoded frame as it was before the first recorded op
+    char* data; int w, h, c, step;
+    // what the header was last set to (to recognise a recycled IplImage address)
+    int cur_w, cur_h, cur_c;
+    bool has_crop = false, has_gravity = false, has_resize = false;
+    std::string crop, gravity, resize;
+    std::vector<std::string> filters;
+    int simple = 0, flatten = 0, allow = 0, n_ops = 0;
+    bool has_wm = false; imp_gpu_watermark wm{};
+    unsigned max_w = 0, max_h = 0;
+};
+
+std::map<const IplImage*, Pending> g_pending;
+std::mutex g_ops_mu;
+imp_ops_create_image_fn g_create = nullptr;
+imp_ops_release_image_fn g_release = nullptr;
+
+IplImage* default_create(int w, int h, int depth, int c) {
+    IplImage* im = (IplImage*)calloc(1, sizeof(IplImage));
+    if (!im) return nullptr;
+    im->nSize = (int)sizeof(IplImage); im->nChannels = c; im->depth = depth; im->width = w; im->height = h; im->align = 4;
+    im->widthStep = (w * c + 3) & ~3;                 // cvCreateImage's 4-byte row alignment
+    im->imageSize = im->widthStep * h;
+    im->imageData = im->imageDataOrigin = (char*)malloc(im->imageSize > 0 ? (size_t)im->imageSize : 1);
+    if (!im->imageData) { free(im); return nullptr; }
+    return im;
+}
+void default_release(IplImage** p) {
+    if (p && *p) { free((*p)->imageDataOrigin); free((*p)->roi); free(*p); *p = nullptr; }
+}
+
+Pending& entry(IplImage* im) {
+    auto it = g_pending.find(im);
+    if (it != g_pending.end()) {
+        Pending& p = it->second;
+        if (p.data == im->imageData && p.cur_w == im->width && p.cur_h == im->height && p.cur_c == im->nChannels) return p;
+        g_pending.erase(it);                              // a different image now lives at this address
+    }
+    Pending p;
+    p.data = im->imageData; p.w = p.cur_w = im->width; p.h = p.cur_h = im->height; p.c = p.cur_c = im->nChannels; p.step = im->widthStep;
+    return g_pending.emplace(im, p).first->second;
+}
+
+struct Built { imp_gpu_request req; imp_gpu_config cfg; std::vector<const char*> fp; };
+void to_request(const Pending& p, Built& b) {
+    b.fp.clear();
+    for (const std::string& f : p.filters) b.fp.push_back(f.c_str());
+    b.req.crop = p.has_crop ? p.crop.c_str() : nullptr;
+    b.req.gravity = p.has_gravity ? p.gravity.c_str() : nullptr;
+    b.req.resize = p.has_resize ? p.resize.c_str() : nullptr;
+    b.req.filters = b.fp.empty() ? nullptr : b.fp.data();
+    b.req.filter_count = (int)b.fp.size();
+    b.req.simple_resize = p.simple; b.req.flatten = p.flatten; b.req.interp = IMP_INTERP_REFERENCE;
+    b.cfg.max_target_w = p.max_w; b.cfg.max_target_h = p.max_h;
+    b.cfg.max_filters = 1 << 20;                         // RunJob enforces the count while parsing (bridge.c:361)
+    b.cfg.allow_experiments = p.allow;
+    b.cfg.watermark = p.has_wm ? &p.wm : nullptr;
+}
+
+// Validates the recorded chain (the newest op included); on success fixes the header up.
+int validate(IplImage* im, Pending& p) {
+    Built b; to_request(p, b);
+    imp_gpu_plan plan;
+    int step = 0;
+    int rc = imp_build_plan(&b.req, &b.cfg, p.w, p.h, p.c, &plan, &step);
+    if (rc) return rc;
+    im->width = p.cur_w = plan.out_w; im->height = p.cur_h = plan.out_h; im->nChannels = p.cur_c = plan.out_c;
+    // imageData still holds the undisturbed source; widthStep/imageSize keep describing THAT buffer until imp_Flush
+    p.n_ops++;
+    return IMP_OK;
+}
+
+int run_one(IplImage** pointer, Pending& p, imp_gpu_plan** plan_out, IplImage** out_img) {
+    Built b; to_request(p, b);
+    int step = 0;
+    int rc = imp_gpu_plan_create(&b.req, &b.cfg, p.w, p.h, p.c, plan_out, &step);
+    if (rc) return rc;
+    imp_ops_create_image_fn create = g_create ? g_create : default_create;
+    IplImage* out = create((*plan_out)->out_w, (*plan_out)->out_h, (*pointer)->depth ? (*pointer)->depth : 8, (*plan_out)->out_c);
+    if (!out) { imp_gpu_plan_destroy(*plan_out); *plan_out = nullptr; return IMP_ERROR_MALLOC_FAILED; }
+    *out_img = out;
+    return IMP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void imp_ops_set_image_allocator(imp_ops_create_image_fn create, imp_ops_release_image_fn release) {
+    std::lock_guard<std::mutex> lk(g_ops_mu);
+    g_create = create; g_release = release;
+}
+
+int imp_Crop(IplImage** pointer, char* args, char* gravity) {
+    if (!pointer || !*pointer || !args) return IMP_ERROR_INVALID_ARGS;
+    std::lock_guard<std::mutex> lk(g_ops_mu);
+    Pending& p = entry(*pointer);
+    if (p.has_crop || p.has_resize || !p.filters.empty() || p.has_wm || p.flatten) return IMP_ERROR_UNSUPPORTED;   // RunJob's order is fixed: flush first
+    Pending saved = p;
+    p.has_crop = true; p.crop = args;
+    p.has_gravity = gravity != nullptr; if (gravity) p.gravity = gravity;
+    int rc = validate(*pointer, p);
+    if (rc) p = saved;
+    return rc;
+}
+
+int imp_Resize(IplImage** pointer, char* args, const imp_gpu_config* config, int simple) {
+    if (!pointer || !*pointer || !args) return IMP_ERROR_INVALID_ARGS;
+    std::lock_guard<std::mutex> lk(g_ops_mu);
+    Pending& p = entry(*pointer);
+    if (p.has_resize || !p.filters.empty() || p.has_wm || p.flatten) return IMP_ERROR_UNSUPPORTED;
+    Pending saved = p;
+    p.has_resize = true; p.resize = args; p.simple = simple ? 1 : 0;
+    p.max_w = config ? config->max_target_w : 0; p.max_h = config ? config->max_target_h : 0;
+    int rc = validate(*pointer, p);
+    if (rc) p = saved;
+    return rc;
+}
+
+int imp_Filter(IplImage** pointer, char* request, int allowExperiments) {
+    if (!pointer || !*pointer || !request) return IMP_ERROR_INVALID_ARGS;
+    std::lock_guard<std::mutex> lk(g_ops_mu);
+    Pending& p = entry(*pointer);
+    if (p.has_wm || p.flatten) return IMP_ERROR_UNSUPPORTED;
+    Pending saved = p;
+    p.filters.push_back(request); p.allow = allowExperiments ? 1 : 0;
+    int rc = validate(*pointer, p);
+    if (rc) p = saved;
+    return rc;
+}
+
+int imp_Watermark(IplImage* image, const imp_gpu_config* config) {
+    if (!image) return IMP_ERROR_INVALID_ARGS;
+    if (!config || !config->watermark) return IMP_OK;
+    std::lock_guard<std::mutex> lk(g_ops_mu);
+    Pending& p = entry(image);
+    if (p.has_wm || p.flatten) return IMP_ERROR_UNSUPPORTED;
+    Pending saved = p;
+    p.has_wm = true; p.wm = *config->watermark;
+    int rc = validate(image, p);
+    if (rc) p = saved;
+    return rc;
+}
+
+int imp_BlendWithPaper(IplImage* image) {
+    if (!image) return IMP_ERROR_INVALID_ARGS;
+    std::lock_guard<std::mutex> lk(g_ops_mu);
+    Pending& p = entry(image);
+    Pending saved = p;
+    p.flatten = 1;
+    int rc = validate(image, p);
+    if (rc) p = saved;
+    return rc;
+}
+
+int imp_ops_pending(const IplImage* image) {
+    std::lock_guard<std::mutex> lk(g_ops_mu);
+    auto it = g_pending.find(image);
+    return it == g_pending.end() ? 0 : it->second.n_ops;
+}
+
+void imp_Discard(IplImage* image) {
+    std::lock_guard<std::mutex> lk(g_ops_mu);
+    auto it = g_pending.find(image);
+    if (it == g_pending.end()) return;
+    // restore the header to the buffer it really describes
+    image->width = it->second.w; image->height = it->second.h; image->nChannels = it->second.c;
+    g_pending.erase(it);
+}
+
+int imp_FlushAll(IplImage** frames, int count) {
+    if (!frames || count < 0) return IMP_ERROR_INVALID_ARGS;
+    std::vector<imp_gpu_plan*> plans; std::vector<IplImage*> outs; std::vector<int> idx;
+    std::vector<const unsigned char*> srcs; std::vector<unsigned char*> dsts; std::vector<int> ss, ds;
+    int rc = IMP_OK;
+    {
+        std::lock_guard<std::mutex> lk(g_ops_mu);
+        for (int i = 0; i < count && rc == IMP_OK; i++) {
+            if (!frames[i]) continue;
+            auto it = g_pending.find(frames[i]);
+            if (it == g_pending.end() || it->second.n_ops == 0) { if (it != g_pending.end()) g_pending.erase(it); continue; }
+            Pending& p = it->second;
+            imp_gpu_plan* plan = nullptr; IplImage* out = nullptr;
+            rc = run_one(&frames[i], p, &plan, &out);
+            if (rc) break;
+            plans.push_back(plan); outs.push_back(out); idx.push_back(i);
+            srcs.push_back((const unsigned char*)p.data); ss.push_back(p.step);
+            dsts.push_back((unsigned char*)out->imageData); ds.push_back(out->widthStep);
+        }
+    }
+    if (rc == IMP_OK && !plans.empty())
+        rc = imp_gpu_batch_run_host((int)plans.size(), plans.data(), srcs.data(), ss.data(), dsts.data(), ds.data(), 4);
+    imp_ops_release_image_fn release = g_release ? g_release : default_release;
+    {
+        std::lock_guard<std::mutex> lk(g_ops_mu);
+        for (size_t k = 0; k < plans.size(); k++) {
+            IplImage* old = frames[idx[k]];
+            if (rc == IMP_OK) {
+                g_pending.erase(old);
+                frames[idx[k]] = outs[k];
+                release(&old);
+            } else {
+                release(&outs[k]);
+            }
+            imp_gpu_plan_destroy(plans[k]);
+        }
+    }
+    return rc;
+}
+
+int imp_Flush(IplImage** pointer) {
+    if (!pointer || !*pointer) return IMP_ERROR_INVALID_ARGS;
+    return imp_FlushAll(pointer, 1);
+}
+
+}  // extern "C"

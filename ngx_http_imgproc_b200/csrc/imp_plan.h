@@ -72,6 +72,8 @@ struct ImpPass {
     int yofs_off, ycoef_off;  // AREA_FRAC: int2 range[b] (first tap, count) + coef = {int si; float a}[taps]
     int taps_off;             // BLUR: int taps[n]
     int max_xtaps, max_ytaps; // AREA_FRAC: largest tap count per output column / row
+    int tile_rs, tile_rows;   // tile kernels: shared-memory row stride (bytes) and max source rows per 32x8 tile
+    int tile_smem;            // tile kernels: source-tile bytes (tile_rs*tile_rows); 0 = no tile variant for this pass
     int nops;
     int ops_off;              // ImpOp[nops]
     int lut_off, lut_bytes;   // LUT area (gamma 256 B each, gradmap 768 B each)
