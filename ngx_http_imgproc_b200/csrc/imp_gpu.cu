@@ -158,7 +158,8 @@ int pick_variant(const ImpPass& h, const ImpJob& j) {
 }
 int tile_smem_bytes(const ImpPass& h) {
     const int ops = (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15;
-    return 16 + ((ops + 127) & ~127) + 112 + h.tile_smem + 64;      // +64: padded taps of the last row
+    const int stage = (h.tile_smem + 64 + 127) & ~127;              // +64: padded taps of the last row
+    return 32 + ((ops + 127) & ~127) + 96 + 2 * stage;               // two-stage ring (imp_tiles.cuh)
 }
 
 int batch_compile(imp_gpu_batch* b) {
@@ -216,7 +217,7 @@ int batch_compile(imp_gpu_batch* b) {
                 st.g.kind = pend[s].kind; st.g.sc = pend[s].sc; st.g.first = (int)b->h_jobs.size(); st.g.count = (int)(e - s);
                 st.g.max_tiles = 0; st.g.smem_bytes = 16; st.g.variant = pend[s].variant; st.g.tmax = pend[s].tmax;
                 for (size_t j = s; j < e; j++) {
-                    st.g.max_tiles = std::max(st.g.max_tiles, pass_tiles(pend[j].hdr));
+                    st.g.max_tiles = std::max(st.g.max_tiles, pend[s].variant ? (pend[j].hdr.bw + 31) / 32 : pass_tiles(pend[j].hdr));
                     st.g.smem_bytes = std::max(st.g.smem_bytes, pend[s].variant ? tile_smem_bytes(pend[j].hdr) : ops_smem(pend[j].hdr));
                     b->h_jobs.push_back(pend[j].job);
                 }
@@ -248,7 +249,7 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
             CK(imp_launch_blur_generic(j, hp.hdr, (uint16_t*)(scratch + boff[k]), ops_smem(hp.hdr), st));
         } else {
             const int variant = pick_variant(hp.hdr, j);
-            ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, pass_tiles(hp.hdr), variant ? tile_smem_bytes(hp.hdr) : ops_smem(hp.hdr),
+            ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, variant ? (hp.hdr.bw + 31) / 32 : pass_tiles(hp.hdr), variant ? tile_smem_bytes(hp.hdr) : ops_smem(hp.hdr),
                              variant, 0};
             CK(imp_launch_group(g, nullptr, &j, st));
         }

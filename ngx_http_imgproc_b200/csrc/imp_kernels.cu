@@ -172,14 +172,14 @@ template <int SC>
 cudaError_t launch_area_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
     static bool attr_set[16] = {false};
     int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_area_frac_tile_kernel<SC>;
+    auto kern = imp_tiles::imp_area_frac_strip_kernel<SC>;
     if (!attr_set[dev & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 15] = true;
     }
-    dim3 block(imp_tiles::TW, imp_tiles::TH);
-    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);
+    dim3 block(imp_tiles::STRIP_THREADS);
+    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);      // max_tiles = strips (tile columns)
     kern<<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o);
     g_imp_launches++;
     return cudaGetLastError();

@@ -497,18 +497,25 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
                 P.kind = IMP_G_AREA_FRAC;
                 // footprint of the 32x8 output tiles of the shared-memory kernel (imp_tiles.cuh)
                 int span = 0, rows = 0;
+                std::vector<int> xtile, ytile;
                 for (int x0 = 0; x0 < rw; x0 += 32) {
                     int x1 = std::min(x0 + 32, rw) - 1;
-                    span = std::max(span, xt[xr[x1].first + xr[x1].count - 1].si - xt[xr[x0].first].si + 1);
+                    int p0 = xt[xr[x0].first].si, p1 = xt[xr[x1].first + xr[x1].count - 1].si;
+                    xtile.push_back(p0); xtile.push_back(p1);
+                    span = std::max(span, p1 - p0 + 1);
                 }
                 for (int y0 = 0; y0 < rh; y0 += 8) {
                     int y1 = std::min(y0 + 8, rh) - 1;
-                    rows = std::max(rows, yt[yr[y1].first + yr[y1].count - 1].si - yt[yr[y0].first].si + 1);
+                    int p0 = yt[yr[y0].first].si, p1 = yt[yr[y1].first + yr[y1].count - 1].si;
+                    ytile.push_back(p0); ytile.push_back(p1 - p0 + 1);
+                    rows = std::max(rows, p1 - p0 + 1);
                 }
+                P.xtile_off = L.bb.add(xtile.data(), xtile.size() * 4);
+                P.ytile_off = L.bb.add(ytile.data(), ytile.size() * 4);
                 P.tile_rs = ((span + 2) * c + 15 + 15) & ~15;     // +2 px: zero-weight padded taps of narrower columns
                 if ((P.tile_rs / 4) % 32 == 0) P.tile_rs += 16;
                 P.tile_rows = rows;
-                P.tile_smem = (P.max_xtaps <= 12 && (long long)P.tile_rs * rows <= 96 * 1024) ? P.tile_rs * rows : 0;
+                P.tile_smem = (P.max_xtaps <= 12 && (long long)P.tile_rs * rows <= 100 * 1024) ? P.tile_rs * rows : 0;
                 P.xofs_off = L.bb.add(xr.data(), xr.size() * sizeof(Range));
                 P.xcoef_off = L.bb.add(xt.data(), xt.size() * sizeof(AreaTap));
                 P.yofs_off = L.bb.add(yr.data(), yr.size() * sizeof(Range));

@@ -48,31 +48,9 @@ __device__ __forceinline__ float u8_times(uint32_t byte, float a, float neg_a23)
 constexpr int TW = 32, TH = 8;          // output tile
 constexpr int MAX_SMEM = 96 * 1024;     // source-tile budget per CTA
 
-struct Geom {
-    int bx0, by0;            // tile origin in the base frame
-    int px0, py0;            // first source pixel column / row staged (window-relative)
-    int rows;                // source rows staged
-    int row_bytes;           // bytes copied per row (multiple of 16)
-    int shift;               // byte offset of pixel px0 inside the first 16-byte block
-};
-
-// Stage rows [py0, py0+rows) x pixel columns [px0, px1] of the job's source window. Called by all threads.
-template <int SC>
-__device__ __forceinline__ void stage_source(const ImpJob& job, const ImpPass* P, Geom& g, int px1, uint8_t* tile, int rs, uint64_t* bar) {
-    const uint8_t* w0 = job.src + (size_t)P->sy0 * job.src_pitch + (size_t)P->sx0 * SC;     // window origin
-    const uint8_t* first = w0 + (size_t)g.py0 * job.src_pitch + (size_t)g.px0 * SC;
-    g.shift = (int)((uintptr_t)first & 15);
-    g.row_bytes = (g.shift + (px1 - g.px0 + 1) * SC + 15) & ~15;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    if (tid == 0) mbar_expect_tx(bar, (uint32_t)(g.row_bytes * g.rows));
-    if (tid < 32) {
-        for (int r = tid; r < g.rows; r += 32)
-            bulk_g2s(tile + (size_t)r * rs, first - g.shift + (size_t)r * job.src_pitch, (uint32_t)g.row_bytes, bar);
-    }
-}
-
 // ---- INTER_AREA, fractional scale, from a shared-memory tile ----------------------------
 // One thread per output pixel; a warp is one output row of the tile, so the y taps are warp-uniform.
+// area_rows() accumulates one output pixel from the staged rows.
 // The x taps of a column are NT contiguous source pixels whose weights sit in registers. Columns with
 // fewer taps than NT are zero-padded on the right: the padded products are exactly +0, and adding +0
 // leaves a running float sum bit-identical, so the result equals OpenCV's ordered accumulation.
@@ -110,21 +88,73 @@ __device__ __forceinline__ void area_rows(const uint8_t* __restrict__ col0, int 
     }
 }
 
+// Persistent strip kernel. A CTA owns a strip of 32 output columns of one job and walks down its 8-row
+// tiles. Warp 8 is the TMA producer: it stages the source rows of tile t+1 into the other half of a
+// two-stage shared-memory ring while warps 0-7 (one output row each) consume tile t. full[]/empty[]
+// mbarriers carry the hand-off; the per-thread x weights are loaded once per strip.
+//   blob tables (host, imp_planner.cpp): xtile[tx] = {first source px, last source px} of tile column tx,
+//   ytile[ty] = {first source row, number of source rows} of tile row ty.
+constexpr int STRIP_CONSUMERS = TW * TH;          // 256 threads, 8 warps
+constexpr int STRIP_THREADS = STRIP_CONSUMERS + 32;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int SC, int NT>
-__device__ __forceinline__ void area_pixel(const uint8_t* __restrict__ col0, int rs, int py0, const ImpAreaTap* __restrict__ xt, const ImpRange rx,
-                                           const ImpAreaTap* __restrict__ yt, const ImpRange ry, float (&sum)[SC]) {
+__device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* __restrict__ blob,
+                                                   const uint8_t* tile0, int stage_bytes, uint64_t* full, uint64_t* empty,
+                                                   const uint8_t* s_ops, int nops, int bx0, int col_off, int tiles_y) {
+    const ImpRange* __restrict__ xr = reinterpret_cast<const ImpRange*>(blob + P->xofs_off);
+    const ImpAreaTap* __restrict__ xt = reinterpret_cast<const ImpAreaTap*>(blob + P->xcoef_off);
+    const ImpRange* __restrict__ yr = reinterpret_cast<const ImpRange*>(blob + P->yofs_off);
+    const ImpAreaTap* __restrict__ yt = reinterpret_cast<const ImpAreaTap*>(blob + P->ycoef_off);
+    const int2* __restrict__ ytile = reinterpret_cast<const int2*>(blob + P->ytile_off);
+    const int bw = P->bw, bh = P->bh, rs = P->tile_rs, oc = P->oc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool in_x = bx0 + lane < bw;
+    const int bx = min(bx0 + lane, bw - 1);
+    const int2 rxv = __ldg(reinterpret_cast<const int2*>(xr + bx));
     float a[NT], na[NT];
 #pragma unroll
     for (int k = 0; k < NT; k++) {
-        a[k] = (k < rx.count) ? __int_as_float(__ldg(reinterpret_cast<const int2*>(xt + rx.first + k)).y) : 0.0f;
+        a[k] = (k < rxv.y) ? __int_as_float(__ldg(reinterpret_cast<const int2*>(xt + rxv.x + k)).y) : 0.0f;
         na[k] = -8388608.0f * a[k];
     }
-    area_rows<SC, NT>(col0, rs, py0, yt, ry.first, ry.count, a, na, sum);
+    const int my_off = col_off + __ldg(reinterpret_cast<const int*>(xt + rxv.x)) * SC;    // byte offset of my first tap in a tile row
+    const ImpFrameMap om = P->out;
+
+    for (int t = 0; t < tiles_y; t++) {
+        const int stage = t & 1, phase = (t >> 1) & 1;
+        const int by = min(t * TH + warp, bh - 1);
+        const bool in_y = t * TH + warp < bh;
+        const int2 ryv = __ldg(reinterpret_cast<const int2*>(yr + by));
+        const int py0 = __ldg(ytile + t).x;
+        mbar_wait(full + stage, phase);
+        float sum[SC];
+        area_rows<SC, NT>(tile0 + stage * stage_bytes + my_off, rs, py0, yt, ryv.x, ryv.y, a, na, sum);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
+        if (in_x && in_y) {
+            ImpPx p;
+            if (SC == 1) { p.b = p.g = p.r = imp_sat8(__float2int_rn(sum[0])); p.a = 255; }
+            else {
+                p.b = imp_sat8(__float2int_rn(sum[0])); p.g = imp_sat8(__float2int_rn(sum[SC > 1 ? 1 : 0])); p.r = imp_sat8(__float2int_rn(sum[SC > 2 ? 2 : 0]));
+                p.a = (SC == 4) ? imp_sat8(__float2int_rn(sum[SC - 1])) : 255;
+            }
+            if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+            int X, Y;
+            imp_map_xy(om, bx, by, X, Y);
+            uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * oc;
+            if (oc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
+            else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
+        }
+    }
 }
 
 template <int SC>
-__global__ void __launch_bounds__(TW * TH)
-imp_area_frac_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, const ImpJob one) {
+__global__ void __launch_bounds__(STRIP_THREADS, 3)
+imp_area_frac_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const ImpJob one) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int jn = blockIdx.y + blockIdx.z * 65535;
     if (jn >= count) return;
@@ -133,78 +163,67 @@ imp_area_frac_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count,
     const ImpPass* __restrict__ P = reinterpret_cast<const ImpPass*>(blob);
     const int bw = P->bw, bh = P->bh;
     const int tiles_x = (bw + TW - 1) / TW, tiles_y = (bh + TH - 1) / TH;
-    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
+    if ((int)blockIdx.x >= tiles_x) return;
 
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);               // [2]
+    uint64_t* empty = full + 2;                                       // [2]
     const int nops = P->nops;
     const int ops_bytes = (nops * (int)sizeof(ImpOp) + P->lut_bytes + 15) & ~15;
-    uint8_t* s_ops = smem + 16;
-    uint8_t* tile = s_ops + ((ops_bytes + 127) & ~127) + 112;       // keeps the tile 128-byte aligned
-    const int tid = threadIdx.y * TW + threadIdx.x;
-    if (tid == 0) mbar_init(bar, 1);
-
-    const ImpRange* __restrict__ xr = reinterpret_cast<const ImpRange*>(blob + P->xofs_off);
-    const ImpAreaTap* __restrict__ xt = reinterpret_cast<const ImpAreaTap*>(blob + P->xcoef_off);
-    const ImpRange* __restrict__ yr = reinterpret_cast<const ImpRange*>(blob + P->yofs_off);
-    const ImpAreaTap* __restrict__ yt = reinterpret_cast<const ImpAreaTap*>(blob + P->ycoef_off);
-    auto ldr = [](const ImpRange* p) { const int2 v = __ldg(reinterpret_cast<const int2*>(p)); ImpRange r; r.first = v.x; r.count = v.y; return r; };
-    auto ldsi = [](const ImpAreaTap* p) { return __ldg(reinterpret_cast<const int*>(p)); };
-
-    Geom g;
-    g.bx0 = (blockIdx.x % tiles_x) * TW; g.by0 = (blockIdx.x / tiles_x) * TH;
-    const int bx1 = min(g.bx0 + TW, bw) - 1, by1 = min(g.by0 + TH, bh) - 1;
-    const ImpRange rx0 = ldr(xr + g.bx0), rx1 = ldr(xr + bx1), ry0 = ldr(yr + g.by0), ry1 = ldr(yr + by1);
-    g.px0 = ldsi(xt + rx0.first);
-    const int px1 = ldsi(xt + rx1.first + rx1.count - 1);
-    g.py0 = ldsi(yt + ry0.first);
-    g.rows = ldsi(yt + ry1.first + ry1.count - 1) - g.py0 + 1;
+    uint8_t* s_ops = smem + 32;
+    uint8_t* tile0 = s_ops + ((ops_bytes + 127) & ~127) + 96;         // 128-byte aligned
     const int rs = P->tile_rs;
-    const int ntx = P->max_xtaps;
-    __syncthreads();                                                 // barrier init visible to every thread
-    stage_source<SC>(job, P, g, px1, tile, rs, bar);
-
-    // while the TMA engine fills the tile: ops + LUTs into shared memory
+    const int stage_bytes = (rs * P->tile_rows + 64 + 127) & ~127;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(full + 0, 1); mbar_init(full + 1, 1);
+        mbar_init(empty + 0, TH); mbar_init(empty + 1, TH);
+    }
     {
         const uint4* gsrc = reinterpret_cast<const uint4*>(blob + P->ops_off);
         uint4* sdst = reinterpret_cast<uint4*>(s_ops);
-        for (int i = tid; i < ops_bytes / 16; i += TW * TH) sdst[i] = __ldg(gsrc + i);
+        for (int i = tid; i < ops_bytes / 16; i += STRIP_THREADS) sdst[i] = __ldg(gsrc + i);
     }
-    const int bx = min(g.bx0 + (int)threadIdx.x, bw - 1), by = min(g.by0 + (int)threadIdx.y, bh - 1);
-    const ImpRange rx = ldr(xr + bx), ry = ldr(yr + by);
-    const uint8_t* col0 = tile + g.shift + (ldsi(xt + rx.first) - g.px0) * SC;     // this thread's first tap in tile row 0
+    const int2 xt_tile = __ldg(reinterpret_cast<const int2*>(blob + P->xtile_off) + blockIdx.x);     // {px0, px1}
+    const uint8_t* w0 = job.src + (size_t)P->sy0 * job.src_pitch + (size_t)P->sx0 * SC;            // window origin
+    const uint8_t* col_first = w0 + (size_t)xt_tile.x * SC;
+    const int shift = (int)((uintptr_t)col_first & 15);
+    const int row_bytes = (shift + (xt_tile.y - xt_tile.x + 1) * SC + 15) & ~15;
     __syncthreads();
-    mbar_wait(bar, 0);
 
-    float sum[SC];
-    switch (ntx) {                                                   // uniform over the whole pass
-        case 1:  area_pixel<SC, 1>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        case 2:  area_pixel<SC, 2>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        case 3:  area_pixel<SC, 3>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        case 4:  area_pixel<SC, 4>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        case 5:  area_pixel<SC, 5>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        case 6:  area_pixel<SC, 6>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        case 7:  area_pixel<SC, 7>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        case 8:  area_pixel<SC, 8>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        case 9:  area_pixel<SC, 9>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        case 10: area_pixel<SC, 10>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        case 11: area_pixel<SC, 11>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
-        default: area_pixel<SC, 12>(col0, rs, g.py0, xt, rx, yt, ry, sum); break;
+    if (tid >= STRIP_CONSUMERS) {
+        // ---- TMA producer warp ----
+        const int lane = tid & 31;
+        const int2* __restrict__ ytile = reinterpret_cast<const int2*>(blob + P->ytile_off);
+        for (int t = 0; t < tiles_y; t++) {
+            const int stage = t & 1, phase = (t >> 1) & 1;
+            const int2 yt_tile = __ldg(ytile + t);                                                  // {py0, rows}
+            mbar_wait(empty + stage, phase ^ 1);
+            if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(row_bytes * yt_tile.y));
+            __syncwarp();
+            uint8_t* dst = tile0 + stage * stage_bytes;
+            const uint8_t* src = col_first - shift + (size_t)yt_tile.x * job.src_pitch;
+            for (int r = lane; r < yt_tile.y; r += 32)
+                bulk_g2s(dst + (size_t)r * rs, src + (size_t)r * job.src_pitch, (uint32_t)row_bytes, full + stage);
+        }
+        return;
     }
-    if ((int)threadIdx.x + g.bx0 >= bw || (int)threadIdx.y + g.by0 >= bh) return;
-
-    ImpPx p;
-    if (SC == 1) { p.b = p.g = p.r = imp_sat8(__float2int_rn(sum[0])); p.a = 255; }
-    else {
-        p.b = imp_sat8(__float2int_rn(sum[0])); p.g = imp_sat8(__float2int_rn(sum[SC > 1 ? 1 : 0])); p.r = imp_sat8(__float2int_rn(sum[SC > 2 ? 2 : 0]));
-        p.a = (SC == 4) ? imp_sat8(__float2int_rn(sum[SC - 1])) : 255;
+    // ---- consumers ----
+    const int col_off = shift - xt_tile.x * SC;                       // tile byte offset of source pixel 0
+    const int bx0 = blockIdx.x * TW;
+    switch (P->max_xtaps) {                                           // uniform over the pass
+        case 1:  area_strip_consume<SC, 1>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 2:  area_strip_consume<SC, 2>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 3:  area_strip_consume<SC, 3>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 4:  area_strip_consume<SC, 4>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 5:  area_strip_consume<SC, 5>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 6:  area_strip_consume<SC, 6>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 7:  area_strip_consume<SC, 7>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 8:  area_strip_consume<SC, 8>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 9:  area_strip_consume<SC, 9>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 10: area_strip_consume<SC, 10>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 11: area_strip_consume<SC, 11>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        default: area_strip_consume<SC, 12>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
     }
-    const int oc = P->oc;
-    if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
-    int X, Y;
-    imp_map_xy(P->out, bx, by, X, Y);
-    uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * oc;
-    if (oc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
-    else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
 }
 
 }  // namespace imp_tiles
