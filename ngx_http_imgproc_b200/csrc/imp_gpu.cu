@@ -5,6 +5,7 @@
 #include "imp_internal.h"
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <atomic>
 #include <map>
@@ -156,10 +157,17 @@ int pick_variant(const ImpPass& h, const ImpJob& j) {
     if (img % 16 && win % 16) return 0;
     return 1;
 }
-int tile_smem_bytes(const ImpPass& h) {
+int tile_stage_bytes(const ImpPass& h) { return (h.tile_smem + 64 + 127) & ~127; }       // +64: padded taps of the last row
+// three ring stages while three CTAs still fit an SM's shared memory, else two
+int tile_stages(const ImpPass& h) {
+    static const int forced = [] { const char* e = getenv("IMP_GPU_STAGES"); return e ? atoi(e) : 0; }();     // tuning knob
+    if (forced == 2 || forced == 3) return forced;
+    (void)h;
+    return 2;                                                     // measured: a third stage buys nothing on cfg2 and costs occupancy on cfg5
+}
+int tile_smem_bytes(const ImpPass& h, int stages) {
     const int ops = (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15;
-    const int stage = (h.tile_smem + 64 + 127) & ~127;              // +64: padded taps of the last row
-    return 32 + ((ops + 127) & ~127) + 96 + 2 * stage;               // two-stage ring (imp_tiles.cuh)
+    return 64 + ((ops + 127) & ~127) + 64 + stages * tile_stage_bytes(h);
 }
 
 int batch_compile(imp_gpu_batch* b) {
@@ -192,7 +200,7 @@ int batch_compile(imp_gpu_batch* b) {
             const ImpHostPass& hp = it.plan->passes[k];
             ImpJob jb = make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->d_scratch, off[i]);
             const int variant = pick_variant(hp.hdr, jb);
-            pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, 0, jb, hp.hdr, boff[i][k]});
+            pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, variant ? tile_stages(hp.hdr) : 0, jb, hp.hdr, boff[i][k]});
         }
         std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& c) {
             if (a.kind != c.kind) return a.kind < c.kind;
@@ -218,7 +226,7 @@ int batch_compile(imp_gpu_batch* b) {
                 st.g.max_tiles = 0; st.g.smem_bytes = 16; st.g.variant = pend[s].variant; st.g.tmax = pend[s].tmax;
                 for (size_t j = s; j < e; j++) {
                     st.g.max_tiles = std::max(st.g.max_tiles, pend[s].variant ? (pend[j].hdr.bw + 31) / 32 : pass_tiles(pend[j].hdr));
-                    st.g.smem_bytes = std::max(st.g.smem_bytes, pend[s].variant ? tile_smem_bytes(pend[j].hdr) : ops_smem(pend[j].hdr));
+                    st.g.smem_bytes = std::max(st.g.smem_bytes, pend[s].variant ? tile_smem_bytes(pend[j].hdr, pend[s].tmax) : ops_smem(pend[j].hdr));
                     b->h_jobs.push_back(pend[j].job);
                 }
                 b->steps.push_back(st); b->launches += 1;
@@ -249,8 +257,8 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
             CK(imp_launch_blur_generic(j, hp.hdr, (uint16_t*)(scratch + boff[k]), ops_smem(hp.hdr), st));
         } else {
             const int variant = pick_variant(hp.hdr, j);
-            ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, variant ? (hp.hdr.bw + 31) / 32 : pass_tiles(hp.hdr), variant ? tile_smem_bytes(hp.hdr) : ops_smem(hp.hdr),
-                             variant, 0};
+            ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, variant ? (hp.hdr.bw + 31) / 32 : pass_tiles(hp.hdr), variant ? tile_smem_bytes(hp.hdr, tile_stages(hp.hdr)) : ops_smem(hp.hdr),
+                             variant, variant ? tile_stages(hp.hdr) : 0};
             CK(imp_launch_group(g, nullptr, &j, st));
         }
     }
@@ -291,6 +299,7 @@ int imp_gpu_init(int device) {
             }
             CK(cudaFree(0));
             CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            CK(imp_upload_tables());
             c.ready = true;
         }
     }

@@ -46,10 +46,11 @@ struct ImpLaunchGroup {
     int max_tiles;               // largest tile count of any job in the group (grid.x)
     int smem_bytes;              // ops + LUT staging (+ source tile for tile variants)
     int variant;                 // 0 = direct-from-global kernel, 1 = shared-memory tile kernel (imp_tiles.cuh)
-    int tmax;                    // tile variant: register tap budget (6 or 12)
+    int tmax;                    // tile variant: number of ring stages (2 or 3)
 };
 // d_jobs == nullptr: a single job passed by value (`one`), no device job table needed.
 cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st);
 // Two-kernel Gaussian through a u16 scratch (any sigma). One job, passed by value.
 cudaError_t imp_launch_blur_generic(const ImpJob& job, const ImpPass& hdr, uint16_t* d_scratch, int smem_bytes, cudaStream_t st);
 unsigned long long imp_launches();
+cudaError_t imp_upload_tables();          // per-device constant tables of imp_pixel.cuh

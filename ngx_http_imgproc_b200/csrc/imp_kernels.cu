@@ -13,6 +13,17 @@
 static std::atomic<unsigned long long> g_imp_launches{0};
 unsigned long long imp_launches() { return g_imp_launches.load(); }
 
+__device__ float g_imp_div255[256];
+__device__ float g_imp_div30[256];
+
+cudaError_t imp_upload_tables() {
+    float a[256], b[256];
+    for (int i = 0; i < 256; i++) { a[i] = (float)i / 255.0f; b[i] = (float)(i * 2) / 60.0f; }     // IEEE float division on the host
+    cudaError_t e = cudaMemcpyToSymbol(g_imp_div255, a, sizeof a);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(g_imp_div30, b, sizeof b);
+}
+
 namespace {
 
 constexpr int TILE_W = 32, TILE_H = 8;
@@ -168,11 +179,11 @@ cudaError_t launch_kind(const ImpLaunchGroup& g, const ImpJob* d_jobs, const Imp
 
 }  // namespace
 
-template <int SC>
+template <int SC, int NSTAGE>
 cudaError_t launch_area_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
     static bool attr_set[16] = {false};
     int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_area_frac_strip_kernel<SC>;
+    auto kern = imp_tiles::imp_area_frac_strip_kernel<SC, NSTAGE>;
     if (!attr_set[dev & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
@@ -189,10 +200,18 @@ cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, cons
     if (g.variant == 1 && g.kind == IMP_G_AREA_FRAC) {
         const ImpJob dummy{};
         const ImpJob& o = one ? *one : dummy;
-        switch (g.sc) {
-            case 1: return launch_area_tile<1>(g, d_jobs, o, st);
-            case 3: return launch_area_tile<3>(g, d_jobs, o, st);
-            case 4: return launch_area_tile<4>(g, d_jobs, o, st);
+        if (g.tmax == 3) {
+            switch (g.sc) {
+                case 1: return launch_area_tile<1, 3>(g, d_jobs, o, st);
+                case 3: return launch_area_tile<3, 3>(g, d_jobs, o, st);
+                case 4: return launch_area_tile<4, 3>(g, d_jobs, o, st);
+            }
+        } else {
+            switch (g.sc) {
+                case 1: return launch_area_tile<1, 2>(g, d_jobs, o, st);
+                case 3: return launch_area_tile<3, 2>(g, d_jobs, o, st);
+                case 4: return launch_area_tile<4, 2>(g, d_jobs, o, st);
+            }
         }
         return cudaErrorInvalidValue;
     }

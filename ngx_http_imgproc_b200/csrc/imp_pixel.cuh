@@ -36,6 +36,30 @@
 
 struct ImpPx { int b, g, r, a; };
 
+// ---- device-only fast paths that keep int<->float conversions and divisions off the XU pipe -----------------
+// (16 lanes/clk/SM on sm_100 vs 64+ for the ALU/FMA pipes; the first ncu capture of the pass kernel showed
+// I2F alone at >100 % of the XU pipe). All of them are exact for the ranges stated.
+#if defined(__CUDA_ARCH__)
+// x/255.0f and (2x)/60.0f for every byte x, divided on the host with IEEE float division (imp_gpu_init).
+extern __device__ float g_imp_div255[256];
+extern __device__ float g_imp_div30[256];
+// 0 <= x < 2^23 -> float, exact (LOP3 + FADD)
+__device__ __forceinline__ float imp_u2f(int x) { return __fadd_rn(__uint_as_float(0x4B000000u | (unsigned)x), -8388608.0f); }
+// 0 <= x < 2^23 -> trunc(x) (FADD.RZ + LOP3); NaN -> 0x400000 (low byte 0, like x86's INT_MIN)
+__device__ __forceinline__ int imp_f2u(float x) { return __float_as_int(__fadd_rz(x, 8388608.0f)) & 0x7FFFFF; }
+// n / d for 0 <= n <= 65535, 1 <= d <= 255, exact: the approximate reciprocal is biased up by 2^-18, more than its
+// own error (2^-22) and less than the 1/d gap that separates a non-integer quotient from the next integer.
+__device__ __forceinline__ int imp_udiv16(int n, int d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(imp_u2f(d)));
+    return imp_f2u(__fmul_rn(imp_u2f(n), __fmul_rn(r, 1.000003814697265625f)));
+}
+#else
+inline float imp_u2f(int x) { return (float)x; }
+inline int imp_f2u(float x) { return (x == x) ? (int)x : 0x400000; }
+inline int imp_udiv16(int n, int d) { return n / d; }
+#endif
+
 // x86 cvttss2si: truncate; NaN / out of range -> 0x80000000.
 IMP_HD int imp_f2i_x86(float v) {
     return (v > -2147483904.0f && v < 2147483648.0f) ? (int)v : (int)0x80000000;
@@ -56,11 +80,14 @@ IMP_HD void imp_rgb2hsv(int b, int g, int r, int& h, int& s, int& v) {
     int mn = imp_min(b, imp_min(g, r)), mx = imp_max(b, imp_max(g, r));
     int delta = mx - mn;
     h = 0; s = 0; v = mx;
-    if (v != 0) s = 255 * delta / v;
+    if (v != 0) s = imp_udiv16(255 * delta, v);
     if (s != 0) {
-        if (mx == r)      h = 30 * (g - b) / delta;
-        else if (mx == g) h = 60 + 30 * (b - r) / delta;
-        else              h = 120 + 30 * (r - g) / delta;
+        int num, base;
+        if (mx == r)      { num = g - b; base = 0; }
+        else if (mx == g) { num = b - r; base = 60; }
+        else              { num = r - g; base = 120; }
+        const int q = imp_udiv16(30 * (num < 0 ? -num : num), delta);      // C division truncates toward zero
+        h = base + (num < 0 ? -q : q);
     }
     if (h < 0) h += 180;
 }
@@ -68,16 +95,21 @@ IMP_HD void imp_rgb2hsv(int b, int g, int r, int& h, int& s, int& v) {
 // helpers.c:109-176 HSV2RGB (float32; `default:` also takes sector 6, i.e. H == 180).
 // Inputs are the BYTES the reference would have stored (0..255).
 IMP_HD void imp_hsv2rgb(int H, int S, int V, int& b, int& g, int& r) {
-    float v = (float)V;
     if (S == 0) { r = g = b = V; return; }
-    float s = IMP_FDIV((float)S, 255.0f);
-    float h = IMP_FDIV((float)(H * 2), 60.0f);
-    int i = (int)floorf(h);
-    float f = IMP_FSUB(h, (float)i);
+    const float v = imp_u2f(V);
+#if defined(__CUDA_ARCH__)
+    const float s = __ldg(&g_imp_div255[S]);
+    const float h = __ldg(&g_imp_div30[H]);
+#else
+    const float s = IMP_FDIV((float)S, 255.0f);
+    const float h = IMP_FDIV((float)(H * 2), 60.0f);
+#endif
+    const int i = imp_f2u(h);                                               // h >= 0: floor == trunc
+    const float f = IMP_FSUB(h, imp_u2f(i));
     // v in [0,255], factors in [0,1]: plain truncation is in range
-    int p = (int)IMP_FMUL(v, IMP_FSUB(1.0f, s));
-    int q = (int)IMP_FMUL(v, IMP_FSUB(1.0f, IMP_FMUL(s, f)));
-    int t = (int)IMP_FMUL(v, IMP_FSUB(1.0f, IMP_FMUL(s, IMP_FSUB(1.0f, f))));
+    const int p = imp_f2u(IMP_FMUL(v, IMP_FSUB(1.0f, s)));
+    const int q = imp_f2u(IMP_FMUL(v, IMP_FSUB(1.0f, IMP_FMUL(s, f))));
+    const int t = imp_f2u(IMP_FMUL(v, IMP_FSUB(1.0f, IMP_FMUL(s, IMP_FSUB(1.0f, f)))));
     switch (i) {
         case 0:  r = V; g = t; b = p; break;
         case 1:  r = q; g = V; b = p; break;
@@ -107,15 +139,25 @@ IMP_HD void imp_op_modulate(ImpPx& p, int dh, int ks, int kv) {
 }
 
 // filters.c:608-616: px[c] = (char)(beta*px[c] + rgb[2-c]*alpha); ca[] = rgb[2-c]*alpha from the host.
-IMP_HD void imp_op_addcolor(ImpPx& p, float beta, float cb, float cg, float cr) {
-    p.b = imp_f2b(IMP_FADD(IMP_FMUL(beta, (float)p.b), cb));
-    p.g = imp_f2b(IMP_FADD(IMP_FMUL(beta, (float)p.g), cg));
-    p.r = imp_f2b(IMP_FADD(IMP_FMUL(beta, (float)p.r), cr));
+IMP_HD void imp_op_addcolor(ImpPx& p, float beta, float cb, float cg, float cr, bool nonneg) {
+    if (nonneg) {           // beta, cb, cg, cr >= 0 (host-checked): sums are in [0, 2^23)
+        p.b = imp_f2u(IMP_FADD(IMP_FMUL(beta, imp_u2f(p.b)), cb)) & 255;
+        p.g = imp_f2u(IMP_FADD(IMP_FMUL(beta, imp_u2f(p.g)), cg)) & 255;
+        p.r = imp_f2u(IMP_FADD(IMP_FMUL(beta, imp_u2f(p.r)), cr)) & 255;
+    } else {
+        p.b = imp_f2b(IMP_FADD(IMP_FMUL(beta, (float)p.b), cb));
+        p.g = imp_f2b(IMP_FADD(IMP_FMUL(beta, (float)p.g), cg));
+        p.r = imp_f2b(IMP_FADD(IMP_FMUL(beta, (float)p.r), cr));
+    }
 }
 
 // filters.c:595-605: val = (int)(ct*val + br*255); clamp to [0,255]. br255 = br*255 from the host.
 IMP_HD int imp_contrast1(int v, float ct, float br255) {
-    return imp_sat8(imp_f2i_x86(IMP_FADD(IMP_FMUL(ct, (float)v), br255)));
+    const float x = IMP_FADD(IMP_FMUL(ct, imp_u2f(v)), br255);
+    // (int)x on x86 then clamp: x < 0 -> 0; x < 256 -> trunc; x < 2^31 -> 255; x >= 2^31, inf, NaN -> INT_MIN -> 0
+    if (!(x < 2147483648.0f)) return 0;
+    const float c = x < 0.0f ? 0.0f : (x > 255.0f ? 255.0f : x);
+    return imp_f2u(c);
 }
 
 // filters.c:335-346: fmax(fmin(v*1.5-50,255),0) truncated == (3v-100)>>1 clamped.
@@ -168,13 +210,19 @@ IMP_HD void imp_op_vignette(ImpPx& p, int x, int y, int cx, int cy, float maxr, 
     float mask = imp_vignette_mask(x, y, cx, cy, maxr, intensity);
     int h, s, v;
     imp_rgb2hsv(p.b, p.g, p.r, h, s, v);
-    v = imp_f2b(IMP_FMUL((float)v, mask));
+    v = imp_f2u(IMP_FMUL(imp_u2f(v), mask)) & 255;          // mask = cos^4 >= 0 (NaN -> low byte 0, as on x86)
     imp_hsv2rgb(h, s, v, p.b, p.g, p.r);
 }
 
 // x/255.0 narrowed to float == x/255.0f correctly rounded for every byte x (checked exhaustively in
 // the CPU test suite, test_alpha_unit_identity), so one IEEE float division replaces the double divide + narrowing.
-IMP_HD float imp_alpha_unit(int a) { return IMP_FDIV((float)a, 255.0f); }
+IMP_HD float imp_alpha_unit(int a) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(&g_imp_div255[a]);
+#else
+    return IMP_FDIV((float)a, 255.0f);
+#endif
+}
 
 // filters.c:619-662 AlphaBlendOver for one pixel. alpha = 1 - opacity (host float).
 // dst_has_a / src_has_a: nChannels == 4.
@@ -187,20 +235,21 @@ IMP_HD void imp_op_over(ImpPx& d, bool dst_has_a, int sb, int sg, int sr, int sa
     float tA = IMP_FADD(sA, IMP_FMUL(dA, one_m));
     if (tA == 0.0f) { d.b = d.g = d.r = 0; }
     else {
-        d.b = imp_f2i_x86(IMP_FDIV(IMP_FADD(IMP_FMUL((float)sb, sA), IMP_FMUL(IMP_FMUL((float)d.b, dA), one_m)), tA)) & 255;
-        d.g = imp_f2i_x86(IMP_FDIV(IMP_FADD(IMP_FMUL((float)sg, sA), IMP_FMUL(IMP_FMUL((float)d.g, dA), one_m)), tA)) & 255;
-        d.r = imp_f2i_x86(IMP_FDIV(IMP_FADD(IMP_FMUL((float)sr, sA), IMP_FMUL(IMP_FMUL((float)d.r, dA), one_m)), tA)) & 255;
+        // all terms are >= 0 and the quotients stay far below 2^23
+        d.b = imp_f2u(IMP_FDIV(IMP_FADD(IMP_FMUL(imp_u2f(sb), sA), IMP_FMUL(IMP_FMUL(imp_u2f(d.b), dA), one_m)), tA)) & 255;
+        d.g = imp_f2u(IMP_FDIV(IMP_FADD(IMP_FMUL(imp_u2f(sg), sA), IMP_FMUL(IMP_FMUL(imp_u2f(d.g), dA), one_m)), tA)) & 255;
+        d.r = imp_f2u(IMP_FDIV(IMP_FADD(IMP_FMUL(imp_u2f(sr), sA), IMP_FMUL(IMP_FMUL(imp_u2f(d.r), dA), one_m)), tA)) & 255;
     }
-    if (dst_has_a) d.a = imp_f2b(IMP_FMUL(tA, 255.0f));
+    if (dst_has_a) d.a = imp_f2u(IMP_FMUL(tA, 255.0f)) & 255;
 }
 
 // filters.c:666-687 BlendWithPaper for one pixel.
 IMP_HD void imp_op_paper(ImpPx& p) {
-    float diff = (float)(255 - p.a);
+    float diff = imp_u2f(255 - p.a);
     float pa = imp_alpha_unit(p.a);
-    p.b = imp_f2i_x86(IMP_FADD(diff, IMP_FMUL((float)p.b, pa))) & 255;
-    p.g = imp_f2i_x86(IMP_FADD(diff, IMP_FMUL((float)p.g, pa))) & 255;
-    p.r = imp_f2i_x86(IMP_FADD(diff, IMP_FMUL((float)p.r, pa))) & 255;
+    p.b = imp_f2u(IMP_FADD(diff, IMP_FMUL(imp_u2f(p.b), pa))) & 255;
+    p.g = imp_f2u(IMP_FADD(diff, IMP_FMUL(imp_u2f(p.g), pa))) & 255;
+    p.r = imp_f2u(IMP_FADD(diff, IMP_FMUL(imp_u2f(p.r), pa))) & 255;
     p.a = 255;
 }
 
@@ -212,7 +261,7 @@ IMP_HD void imp_run_ops(ImpPx& p, int oc, int bx, int by, const ImpOp* ops, int 
         const ImpOp& op = ops[k];
         switch (op.kind) {
             case IMP_OP_MODULATE: imp_op_modulate(p, op.i[0], op.i[1], op.i[2]); break;
-            case IMP_OP_ADDCOLOR: imp_op_addcolor(p, op.f[0], op.f[1], op.f[2], op.f[3]); break;
+            case IMP_OP_ADDCOLOR: imp_op_addcolor(p, op.f[0], op.f[1], op.f[2], op.f[3], op.i[0] != 0); break;
             case IMP_OP_LUT_ALL: {
                 const uint8_t* t = lut + op.i[0];
                 p.b = t[p.b]; p.g = t[p.g]; p.r = t[p.r];

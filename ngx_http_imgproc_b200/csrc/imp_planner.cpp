@@ -227,6 +227,7 @@ void push_addcolor(Lower& L, const int* rgb, float alpha) {     // filters.c:608
     ImpOp o{}; o.kind = IMP_OP_ADDCOLOR;
     float beta = 1 - alpha;
     o.f[0] = beta; o.f[1] = (float)rgb[2] * alpha; o.f[2] = (float)rgb[1] * alpha; o.f[3] = (float)rgb[0] * alpha;
+    o.i[0] = (beta >= 0 && o.f[1] >= 0 && o.f[2] >= 0 && o.f[3] >= 0) ? 1 : 0;     // enables the XU-free truncation path
     L.ops.push_back(o);
 }
 void push_gamma(Lower& L, float g) { uint8_t lut[256]; gamma_lut(g, lut); ImpOp o{}; o.kind = IMP_OP_LUT_ALL; o.i[0] = L.add_lut(lut, 256); L.ops.push_back(o); }

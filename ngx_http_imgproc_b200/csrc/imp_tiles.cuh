@@ -101,7 +101,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int SC, int NT>
+template <int SC, int NT, int NSTAGE>
 __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* __restrict__ blob,
                                                    const uint8_t* tile0, int stage_bytes, uint64_t* full, uint64_t* empty,
                                                    const uint8_t* s_ops, int nops, int bx0, int col_off, int tiles_y) {
@@ -124,8 +124,8 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
     const int my_off = col_off + __ldg(reinterpret_cast<const int*>(xt + rxv.x)) * SC;    // byte offset of my first tap in a tile row
     const ImpFrameMap om = P->out;
 
+    int stage = 0, phase = 0;
     for (int t = 0; t < tiles_y; t++) {
-        const int stage = t & 1, phase = (t >> 1) & 1;
         const int by = min(t * TH + warp, bh - 1);
         const bool in_y = t * TH + warp < bh;
         const int2 ryv = __ldg(reinterpret_cast<const int2*>(yr + by));
@@ -149,10 +149,11 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
             if (oc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
             else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
         }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
 
-template <int SC>
+template <int SC, int NSTAGE>
 __global__ void __launch_bounds__(STRIP_THREADS, 3)
 imp_area_frac_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const ImpJob one) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -165,18 +166,17 @@ imp_area_frac_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count
     const int tiles_x = (bw + TW - 1) / TW, tiles_y = (bh + TH - 1) / TH;
     if ((int)blockIdx.x >= tiles_x) return;
 
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);               // [2]
-    uint64_t* empty = full + 2;                                       // [2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);               // [NSTAGE]
+    uint64_t* empty = full + NSTAGE;                                  // [NSTAGE]
     const int nops = P->nops;
     const int ops_bytes = (nops * (int)sizeof(ImpOp) + P->lut_bytes + 15) & ~15;
-    uint8_t* s_ops = smem + 32;
-    uint8_t* tile0 = s_ops + ((ops_bytes + 127) & ~127) + 96;         // 128-byte aligned
+    uint8_t* s_ops = smem + 64;
+    uint8_t* tile0 = s_ops + ((ops_bytes + 127) & ~127) + 64;         // 128-byte aligned
     const int rs = P->tile_rs;
     const int stage_bytes = (rs * P->tile_rows + 64 + 127) & ~127;
     const int tid = threadIdx.x;
     if (tid == 0) {
-        mbar_init(full + 0, 1); mbar_init(full + 1, 1);
-        mbar_init(empty + 0, TH); mbar_init(empty + 1, TH);
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 1); mbar_init(empty + i, TH); }
     }
     {
         const uint4* gsrc = reinterpret_cast<const uint4*>(blob + P->ops_off);
@@ -194,8 +194,8 @@ imp_area_frac_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count
         // ---- TMA producer warp ----
         const int lane = tid & 31;
         const int2* __restrict__ ytile = reinterpret_cast<const int2*>(blob + P->ytile_off);
+        int stage = 0, phase = 0;
         for (int t = 0; t < tiles_y; t++) {
-            const int stage = t & 1, phase = (t >> 1) & 1;
             const int2 yt_tile = __ldg(ytile + t);                                                  // {py0, rows}
             mbar_wait(empty + stage, phase ^ 1);
             if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(row_bytes * yt_tile.y));
@@ -204,6 +204,7 @@ imp_area_frac_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count
             const uint8_t* src = col_first - shift + (size_t)yt_tile.x * job.src_pitch;
             for (int r = lane; r < yt_tile.y; r += 32)
                 bulk_g2s(dst + (size_t)r * rs, src + (size_t)r * job.src_pitch, (uint32_t)row_bytes, full + stage);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
         return;
     }
@@ -211,18 +212,18 @@ imp_area_frac_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count
     const int col_off = shift - xt_tile.x * SC;                       // tile byte offset of source pixel 0
     const int bx0 = blockIdx.x * TW;
     switch (P->max_xtaps) {                                           // uniform over the pass
-        case 1:  area_strip_consume<SC, 1>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 2:  area_strip_consume<SC, 2>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 3:  area_strip_consume<SC, 3>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 4:  area_strip_consume<SC, 4>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 5:  area_strip_consume<SC, 5>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 6:  area_strip_consume<SC, 6>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 7:  area_strip_consume<SC, 7>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 8:  area_strip_consume<SC, 8>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 9:  area_strip_consume<SC, 9>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 10: area_strip_consume<SC, 10>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 11: area_strip_consume<SC, 11>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        default: area_strip_consume<SC, 12>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 1:  area_strip_consume<SC, 1, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 2:  area_strip_consume<SC, 2, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 3:  area_strip_consume<SC, 3, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 4:  area_strip_consume<SC, 4, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 5:  area_strip_consume<SC, 5, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 6:  area_strip_consume<SC, 6, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 7:  area_strip_consume<SC, 7, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 8:  area_strip_consume<SC, 8, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 9:  area_strip_consume<SC, 9, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 10: area_strip_consume<SC, 10, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 11: area_strip_consume<SC, 11, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        default: area_strip_consume<SC, 12, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
     }
 }
 
