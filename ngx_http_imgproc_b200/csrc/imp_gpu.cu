@@ -3,6 +3,7 @@
 // No CPU fallback exists anywhere in this file: if CUDA is unusable every compute call fails with
 // IMP_ERROR_GPU and a message in imp_gpu_last_error().
 #include "imp_internal.h"
+#include <cuda.h>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
@@ -149,25 +150,62 @@ int pass_tiles(const ImpPass& h) { return ((h.bw + 31) / 32) * ((h.bh + 7) / 8);
 
 // Tile (shared-memory, TMA-staged) variant: needs 16-byte addressable source rows — pitch % 16 == 0 and
 // either the image rows or the window rows start 16-byte aligned (imp_tiles.cuh) — and a footprint that fits.
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// Tensor map over the job's source window for the strip kernels: 8-byte elements, rows = window rows, origin =
+// the window's first byte aligned down to 16; box = tile_rs bytes x tile_rows rows. Out-of-range box parts are
+// zero-filled by the TMA unit, so edge tiles never touch memory outside the window's rows.
+int encode_job_tmap(const ImpPass& h, ImpJob& j) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail_msg("cuTensorMapEncodeTiled is unavailable in this driver");
+    const uintptr_t win = (uintptr_t)j.src + (size_t)h.sy0 * j.src_pitch + (size_t)h.sx0 * h.sc;
+    const uintptr_t a0 = win & ~uintptr_t(15);
+    j.tm_x0 = (int)(win - a0);
+    const cuuint64_t gdim[2] = {(cuuint64_t)((j.tm_x0 + (size_t)h.sw * h.sc + 7) / 8), (cuuint64_t)h.sh};
+    const cuuint64_t gstride[1] = {(cuuint64_t)j.src_pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)(h.tile_rs / 8), (cuuint32_t)h.tile_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    CUtensorMap tm;
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)a0, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(t_err, sizeof t_err, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return IMP_ERROR_GPU; }
+    memcpy(j.tmap, &tm, 128);
+    return IMP_OK;
+}
+
 int pick_variant(const ImpPass& h, const ImpJob& j) {
-    if (h.tile_smem <= 0) return 0;
+    if (h.tile_smem <= 0 || !encode_tiled()) return 0;
     if (j.src_pitch % 16) return 0;
     const uintptr_t img = (uintptr_t)j.src;
     const uintptr_t win = img + (size_t)h.sy0 * j.src_pitch + (size_t)h.sx0 * h.sc;
     if (img % 16 && win % 16) return 0;
     return 1;
 }
-int tile_stage_bytes(const ImpPass& h) { return (h.tile_smem + 64 + 127) & ~127; }       // +64: padded taps of the last row
+int tile_stage_bytes(const ImpPass& h) { return (h.tile_smem + 127) & ~127; }
 // three ring stages while three CTAs still fit an SM's shared memory, else two
+// Ring depth: as many stages as fit ~64 KB (so three CTAs still share an SM), between 2 and 8. Small tiles
+// (cfg1: 7 KB) need the depth to keep enough bytes in flight; big ones (cfg2: 23 KB) are fine with 2.
 int tile_stages(const ImpPass& h) {
     static const int forced = [] { const char* e = getenv("IMP_GPU_STAGES"); return e ? atoi(e) : 0; }();     // tuning knob
-    if (forced == 2 || forced == 3) return forced;
-    (void)h;
-    return 2;                                                     // measured: a third stage buys nothing on cfg2 and costs occupancy on cfg5
+    if (forced >= 2 && forced <= 8) return forced;
+    return std::max(2, std::min(8, (64 * 1024) / tile_stage_bytes(h)));
 }
 int tile_smem_bytes(const ImpPass& h, int stages) {
     const int ops = (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15;
-    return 64 + ((ops + 127) & ~127) + 64 + stages * tile_stage_bytes(h);
+    return 128 + ((ops + 127) & ~127) + stages * tile_stage_bytes(h) + 64;      // +64: padded taps past the last row
 }
 
 int batch_compile(imp_gpu_batch* b) {
@@ -200,6 +238,7 @@ int batch_compile(imp_gpu_batch* b) {
             const ImpHostPass& hp = it.plan->passes[k];
             ImpJob jb = make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->d_scratch, off[i]);
             const int variant = pick_variant(hp.hdr, jb);
+            if (variant) { int rc = encode_job_tmap(hp.hdr, jb); if (rc) return rc; }
             pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, variant ? tile_stages(hp.hdr) : 0, jb, hp.hdr, boff[i][k]});
         }
         std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& c) {
@@ -257,6 +296,7 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
             CK(imp_launch_blur_generic(j, hp.hdr, (uint16_t*)(scratch + boff[k]), ops_smem(hp.hdr), st));
         } else {
             const int variant = pick_variant(hp.hdr, j);
+            if (variant) { int rc = encode_job_tmap(hp.hdr, j); if (rc) return rc; }
             ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, variant ? (hp.hdr.bw + 31) / 32 : pass_tiles(hp.hdr), variant ? tile_smem_bytes(hp.hdr, tile_stages(hp.hdr)) : ops_smem(hp.hdr),
                              variant, variant ? tile_stages(hp.hdr) : 0};
             CK(imp_launch_group(g, nullptr, &j, st));

@@ -179,11 +179,11 @@ cudaError_t launch_kind(const ImpLaunchGroup& g, const ImpJob* d_jobs, const Imp
 
 }  // namespace
 
-template <int SC, int NSTAGE>
+template <int SC, int MODE>
 cudaError_t launch_area_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
     static bool attr_set[16] = {false};
     int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_area_frac_strip_kernel<SC, NSTAGE>;
+    auto kern = imp_tiles::imp_area_strip_kernel<SC, MODE>;
     if (!attr_set[dev & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
@@ -191,26 +191,26 @@ cudaError_t launch_area_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, cons
     }
     dim3 block(imp_tiles::STRIP_THREADS);
     dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);      // max_tiles = strips (tile columns)
-    kern<<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o);
+    kern<<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o, g.tmax);
     g_imp_launches++;
     return cudaGetLastError();
 }
 
 cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st) {
-    if (g.variant == 1 && g.kind == IMP_G_AREA_FRAC) {
+    if (g.variant == 1 && (g.kind == IMP_G_AREA_FRAC || g.kind == IMP_G_AREA_INT)) {
         const ImpJob dummy{};
         const ImpJob& o = one ? *one : dummy;
-        if (g.tmax == 3) {
+        if (g.kind == IMP_G_AREA_FRAC) {
             switch (g.sc) {
-                case 1: return launch_area_tile<1, 3>(g, d_jobs, o, st);
-                case 3: return launch_area_tile<3, 3>(g, d_jobs, o, st);
-                case 4: return launch_area_tile<4, 3>(g, d_jobs, o, st);
+                case 1: return launch_area_tile<1, 0>(g, d_jobs, o, st);
+                case 3: return launch_area_tile<3, 0>(g, d_jobs, o, st);
+                case 4: return launch_area_tile<4, 0>(g, d_jobs, o, st);
             }
         } else {
             switch (g.sc) {
-                case 1: return launch_area_tile<1, 2>(g, d_jobs, o, st);
-                case 3: return launch_area_tile<3, 2>(g, d_jobs, o, st);
-                case 4: return launch_area_tile<4, 2>(g, d_jobs, o, st);
+                case 1: return launch_area_tile<1, 1>(g, d_jobs, o, st);
+                case 3: return launch_area_tile<3, 1>(g, d_jobs, o, st);
+                case 4: return launch_area_tile<4, 1>(g, d_jobs, o, st);
             }
         }
         return cudaErrorInvalidValue;

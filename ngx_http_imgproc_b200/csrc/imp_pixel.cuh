@@ -197,7 +197,12 @@ IMP_HD void imp_op_scanline(ImpPx& p, int y, int period, int freq, int sbyte, in
 // dx*dx+dy*dy is exact in double, sqrt is correctly rounded, narrowing matches the reference; cos and
 // the 4th power are double, then narrowed (libm vs CUDA may differ in the last double ulp, which the
 // float narrowing hides except with probability ~2^-29: tested as <= 1 LSB).
-IMP_HD float imp_vignette_mask(int x, int y, int cx, int cy, float maxr, float intensity) {
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__            // double cos + its slow path: large and rare, keep one copy per kernel
+#else
+inline
+#endif
+float imp_vignette_mask(int x, int y, int cx, int cy, float maxr, float intensity) {
     double dx = (double)(cx - x), dy = (double)(cy - y);
     float distance = (float)sqrt(dx * dx + dy * dy);
     float raw = IMP_FMUL(IMP_FDIV(distance, maxr), intensity);

@@ -90,4 +90,9 @@ struct ImpJob {
     const uint8_t* pass;      // device pointer to the ImpPass blob
     const uint8_t* wm;        // watermark pixels on this device (or null)
     int src_pitch, dst_pitch, wm_pitch, wm_c;
+    int tm_x0;                // strip kernels: byte offset of the source window's first pixel inside the tensor map's row
+    int pad_[15];
+    // strip kernels: CUtensorMap (2-D, 8-byte elements) over the 16-byte aligned source window of this job, so the
+    // TMA engine fetches a whole tile (box = tile_rs bytes x tile_rows rows) with ONE instruction.
+    alignas(64) unsigned char tmap[128];
 };

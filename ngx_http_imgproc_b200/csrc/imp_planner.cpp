@@ -489,13 +489,14 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
             P.xofs_off = L.bb.add(xo.data(), xo.size() * 4);
             P.yofs_off = L.bb.add(yo.data(), yo.size() * 4);
         } else if (mode == 3 && scale_x >= 1 && scale_y >= 1) {
-            if (fast) {
-                P.kind = IMP_G_AREA_INT; P.nx = isx; P.ny = isy; P.area_scale = 1.f / (isx * isy);
-            } else {
+            {
+                // The strip kernel (imp_tiles.cuh) walks the same tap tables for both flavours; with integer scales
+                // every column/row has exactly nx/ny taps and the weights are unused.
                 std::vector<Range> xr, yr; std::vector<AreaTap> xt, yt;
                 area_table(cw, rw, scale_x, xr, xt, P.max_xtaps);
                 area_table(ch, rh, scale_y, yr, yt, P.max_ytaps);
-                P.kind = IMP_G_AREA_FRAC;
+                if (fast) { P.kind = IMP_G_AREA_INT; P.nx = isx; P.ny = isy; P.area_scale = 1.f / (isx * isy); }
+                else P.kind = IMP_G_AREA_FRAC;
                 // footprint of the 32x8 output tiles of the shared-memory kernel (imp_tiles.cuh)
                 int span = 0, rows = 0;
                 std::vector<int> xtile, ytile;
@@ -513,10 +514,13 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
                 }
                 P.xtile_off = L.bb.add(xtile.data(), xtile.size() * 4);
                 P.ytile_off = L.bb.add(ytile.data(), ytile.size() * 4);
-                P.tile_rs = ((span + 2) * c + 15 + 15) & ~15;     // +2 px: zero-weight padded taps of narrower columns
+                // TMA box: tile_rs bytes x rows; +2 px for the zero-weight padded taps of narrower columns, +15 for the
+                // 16-byte alignment of the box origin, +4 for the aligned word loads of packed 3-channel pixels
+                P.tile_rs = ((span + 2) * c + 15 + 4 + 15) & ~15;
                 if ((P.tile_rs / 4) % 32 == 0) P.tile_rs += 16;
                 P.tile_rows = rows;
-                P.tile_smem = (P.max_xtaps <= 12 && (long long)P.tile_rs * rows <= 100 * 1024) ? P.tile_rs * rows : 0;
+                P.tile_smem = (P.max_xtaps <= 12 && P.tile_rs <= 2048 && rows <= 256 && (long long)P.tile_rs * rows <= 100 * 1024 &&
+                               (!fast || isx * isy <= 256)) ? P.tile_rs * rows : 0;
                 P.xofs_off = L.bb.add(xr.data(), xr.size() * sizeof(Range));
                 P.xcoef_off = L.bb.add(xt.data(), xt.size() * sizeof(AreaTap));
                 P.yofs_off = L.bb.add(yr.data(), yr.size() * sizeof(Range));

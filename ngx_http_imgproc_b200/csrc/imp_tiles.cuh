@@ -35,6 +35,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// 2-D tiled TMA load (SASS UTMALDG): box of the job's tensor map at element coordinates (c0, c1).
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
 // u8 -> f32 product without the XU pipe: m = 2^23 + S (PRMT), fma(m, a, -(2^23*a)) == RN(S*a) exactly,
 // because m*a - 2^23*a == S*a in exact arithmetic and FMA rounds once.
 __device__ __forceinline__ float byte_times(uint32_t word, int sel, float a, float neg_a23) {
@@ -43,6 +49,21 @@ __device__ __forceinline__ float byte_times(uint32_t word, int sel, float a, flo
 }
 __device__ __forceinline__ float u8_times(uint32_t byte, float a, float neg_a23) {
     return __fmaf_rn(__uint_as_float(byte | 0x4B000000u), a, neg_a23);
+}
+
+// Loads NB consecutive bytes that start at an arbitrarily aligned shared-memory address into NB/4 (rounded up)
+// registers: aligned 32-bit loads + funnel shifts, so packed 3-channel pixels cost ~1/4 LDS + 1/4 SHF per byte
+// instead of one LDS.U8 each, and every byte then sits at a compile-time position.
+template <int NB>
+__device__ __forceinline__ void load_bytes(const uint8_t* p, uint32_t (&w)[(NB + 3) / 4]) {
+    constexpr int NW = (NB + 3) / 4;
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(3));
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+    uint32_t raw[NW + 1];
+#pragma unroll
+    for (int i = 0; i <= NW; i++) raw[i] = base[i];
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
 }
 
 constexpr int TW = 32, TH = 8;          // output tile
@@ -58,11 +79,14 @@ constexpr int MAX_SMEM = 96 * 1024;     // source-tile budget per CTA
 template <int SC, int NT>
 __device__ __forceinline__ void area_rows(const uint8_t* __restrict__ col0, int rs, int py0, const ImpAreaTap* __restrict__ yt, int yfirst, int ycount,
                                           const float (&a)[NT], const float (&na)[NT], float (&sum)[SC]) {
-    for (int j = 0; j < ycount; j++) {
-        const int2 tyr = __ldg(reinterpret_cast<const int2*>(yt + yfirst + j));
-        const float beta = __int_as_float(tyr.y);
-        const uint8_t* row = col0 + (size_t)(tyr.x - py0) * rs;
+    // the y taps of an output row are consecutive source rows: only the first index is looked up, and the
+    // weight of row j is not needed until that row's horizontal sum is done (its load latency hides there)
+    const uint8_t* row = col0 + (size_t)(__ldg(reinterpret_cast<const int*>(yt + yfirst)) - py0) * rs;
+    for (int j = 0; j < ycount; j++, row += rs) {
+        const float beta = __ldg(reinterpret_cast<const float*>(yt + yfirst + j) + 1);
         float h[SC];
+        uint32_t seg[SC == 4 ? 1 : (NT * SC + 3) / 4];
+        if (SC != 4) load_bytes<(SC == 4 ? 4 : NT * SC)>(row, seg);
 #pragma unroll
         for (int k = 0; k < NT; k++) {
             if (SC == 4) {
@@ -75,7 +99,8 @@ __device__ __forceinline__ void area_rows(const uint8_t* __restrict__ col0, int 
             } else {
 #pragma unroll
                 for (int c = 0; c < SC; c++) {
-                    const float pr = u8_times(row[k * SC + c], a[k], na[k]);
+                    const int pos = k * SC + c;
+                    const float pr = byte_times(seg[pos / 4], pos % 4, a[k], na[k]);
                     h[c] = (k == 0) ? pr : __fadd_rn(h[c], pr);
                 }
             }
@@ -88,23 +113,83 @@ __device__ __forceinline__ void area_rows(const uint8_t* __restrict__ col0, int 
     }
 }
 
+// Integer-scale INTER_AREA: plain byte sums over the NT x ycount block. For 4 channels two
+// PRMTs split a pixel into two packed u16 pairs, so a pixel costs LDS + 2 PRMT + 2 IADD (block <= 256 px).
+template <int SC, int NT>
+__device__ __forceinline__ void area_int_rows(const uint8_t* __restrict__ col0, int rs, int py0, const ImpAreaTap* __restrict__ yt, int yfirst, int ycount,
+                                              int (&isum)[SC]) {
+    unsigned lo = 0, hi = 0;                       // SC == 4: {B,R} and {G,A} as u16 pairs
+#pragma unroll
+    for (int c = 0; c < SC; c++) isum[c] = 0;
+    const uint8_t* row = col0 + (size_t)(__ldg(reinterpret_cast<const int*>(yt + yfirst)) - py0) * rs;
+    for (int j = 0; j < ycount; j++, row += rs) {
+#pragma unroll
+        for (int k = 0; k < NT; k++) {
+            if (SC == 4) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(row + k * 4);
+                lo += __byte_perm(w, 0, 0x4240);   // bytes 0 and 2 -> low halves
+                hi += __byte_perm(w, 0, 0x4341);   // bytes 1 and 3
+            }
+        }
+        if (SC != 4) {
+            uint32_t seg[SC == 4 ? 1 : (NT * SC + 3) / 4];
+            load_bytes<(SC == 4 ? 4 : NT * SC)>(row, seg);
+            // per channel: dp4a of each word with the 0/1 mask of that channel's byte positions (compile-time)
+#pragma unroll
+            for (int c = 0; c < SC; c++) {
+#pragma unroll
+                for (int wi = 0; wi < (NT * SC + 3) / 4; wi++) {
+                    unsigned mask = 0;
+#pragma unroll
+                    for (int bpos = 0; bpos < 4; bpos++) {
+                        const int pos = wi * 4 + bpos;
+                        if (pos < NT * SC && pos % SC == c) mask |= 1u << (8 * bpos);
+                    }
+                    if (mask) isum[c] = __dp4a(seg[wi], mask, (unsigned)isum[c]);
+                }
+            }
+        }
+    }
+    if (SC == 4) { isum[0] = lo & 0xFFFF; isum[2 % SC] = lo >> 16; isum[1 % SC] = hi & 0xFFFF; isum[3 % SC] = hi >> 16; }
+}
+
+// Round-half-even of 0 <= x < 2^22 without F2I (FADD + IADD).
+__device__ __forceinline__ int rint_pos(float x) { return __float_as_int(__fadd_rn(x, 12582912.0f)) - 0x4B400000; }
+
 // Persistent strip kernel. A CTA owns a strip of 32 output columns of one job and walks down its 8-row
 // tiles. Warp 8 is the TMA producer: it stages the source rows of tile t+1 into the other half of a
-// two-stage shared-memory ring while warps 0-7 (one output row each) consume tile t. full[]/empty[]
+// multi-stage shared-memory ring (2..8 stages, as many as fit ~64 KB) while warps 0-7 (one output row each) consume tile t. full[]/empty[]
 // mbarriers carry the hand-off; the per-thread x weights are loaded once per strip.
 //   blob tables (host, imp_planner.cpp): xtile[tx] = {first source px, last source px} of tile column tx,
 //   ytile[ty] = {first source row, number of source rows} of tile row ty.
 constexpr int STRIP_CONSUMERS = TW * TH;          // 256 threads, 8 warps
-constexpr int STRIP_THREADS = STRIP_CONSUMERS + 32;
+constexpr int STRIP_PRODUCER_WARPS = 1;         // UBLKCP issue is serialised per warp: spread the rows over 4 warps
+constexpr int STRIP_THREADS = STRIP_CONSUMERS + 32 * STRIP_PRODUCER_WARPS;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int SC, int NT, int NSTAGE>
+// Shared epilogue of the strip kernels: op list + store of one pixel. Inlined: an out-of-line call (v[] through
+// local memory + call/return) measured 12-20 % slower on cfg1/cfg2 than the larger code.
+template <int SC>
+__device__ __forceinline__ void strip_epilogue(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* s_ops, int nops, int bx, int by, const int* v) {
+    ImpPx p;
+    if (SC == 1) { p.b = p.g = p.r = v[0]; p.a = 255; }
+    else { p.b = v[0]; p.g = v[SC > 1 ? 1 : 0]; p.r = v[SC > 2 ? 2 : 0]; p.a = (SC == 4) ? v[SC - 1] : 255; }
+    const int oc = P->oc;
+    if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+    int X, Y;
+    imp_map_xy(P->out, bx, by, X, Y);
+    uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * oc;
+    if (oc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
+    else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
+}
+
+template <int SC, int NT, int MODE>
 __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* __restrict__ blob,
                                                    const uint8_t* tile0, int stage_bytes, uint64_t* full, uint64_t* empty,
-                                                   const uint8_t* s_ops, int nops, int bx0, int col_off, int tiles_y) {
+                                                   const uint8_t* s_ops, int nops, int bx0, int col_off, int tiles_y, int NSTAGE) {
     const ImpRange* __restrict__ xr = reinterpret_cast<const ImpRange*>(blob + P->xofs_off);
     const ImpAreaTap* __restrict__ xt = reinterpret_cast<const ImpAreaTap*>(blob + P->xcoef_off);
     const ImpRange* __restrict__ yr = reinterpret_cast<const ImpRange*>(blob + P->yofs_off);
@@ -115,14 +200,17 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
     const bool in_x = bx0 + lane < bw;
     const int bx = min(bx0 + lane, bw - 1);
     const int2 rxv = __ldg(reinterpret_cast<const int2*>(xr + bx));
-    float a[NT], na[NT];
+    float a[MODE == 0 ? NT : 1], na[MODE == 0 ? NT : 1];
+    if (MODE == 0) {
 #pragma unroll
-    for (int k = 0; k < NT; k++) {
-        a[k] = (k < rxv.y) ? __int_as_float(__ldg(reinterpret_cast<const int2*>(xt + rxv.x + k)).y) : 0.0f;
-        na[k] = -8388608.0f * a[k];
+        for (int k = 0; k < (MODE == 0 ? NT : 1); k++) {
+            a[k] = (k < rxv.y) ? __int_as_float(__ldg(reinterpret_cast<const int2*>(xt + rxv.x + k)).y) : 0.0f;
+            na[k] = -8388608.0f * a[k];
+        }
     }
+    const int box_2x2 = (P->nx == 2 && P->ny == 2);
+    const float box_scale = P->area_scale;
     const int my_off = col_off + __ldg(reinterpret_cast<const int*>(xt + rxv.x)) * SC;    // byte offset of my first tap in a tile row
-    const ImpFrameMap om = P->out;
 
     int stage = 0, phase = 0;
     for (int t = 0; t < tiles_y; t++) {
@@ -131,35 +219,34 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
         const int2 ryv = __ldg(reinterpret_cast<const int2*>(yr + by));
         const int py0 = __ldg(ytile + t).x;
         mbar_wait(full + stage, phase);
-        float sum[SC];
-        area_rows<SC, NT>(tile0 + stage * stage_bytes + my_off, rs, py0, yt, ryv.x, ryv.y, a, na, sum);
+        int v[SC];
+        if (MODE == 0) {
+            float sum[SC];
+            area_rows<SC, (MODE == 0 ? NT : 1)>(tile0 + stage * stage_bytes + my_off, rs, py0, yt, ryv.x, ryv.y, a, na, sum);
+#pragma unroll
+            for (int c = 0; c < SC; c++) v[c] = min(rint_pos(sum[c]), 255);          // sums are >= 0
+        } else {
+            area_int_rows<SC, NT>(tile0 + stage * stage_bytes + my_off, rs, py0, yt, ryv.x, ryv.y, v);
+#pragma unroll
+            for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
-        if (in_x && in_y) {
-            ImpPx p;
-            if (SC == 1) { p.b = p.g = p.r = imp_sat8(__float2int_rn(sum[0])); p.a = 255; }
-            else {
-                p.b = imp_sat8(__float2int_rn(sum[0])); p.g = imp_sat8(__float2int_rn(sum[SC > 1 ? 1 : 0])); p.r = imp_sat8(__float2int_rn(sum[SC > 2 ? 2 : 0]));
-                p.a = (SC == 4) ? imp_sat8(__float2int_rn(sum[SC - 1])) : 255;
-            }
-            if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
-            int X, Y;
-            imp_map_xy(om, bx, by, X, Y);
-            uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * oc;
-            if (oc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
-            else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
-        }
+        if (in_x && in_y) strip_epilogue<SC>(job, P, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
 
-template <int SC, int NSTAGE>
+template <int SC, int MODE>
 __global__ void __launch_bounds__(STRIP_THREADS, 3)
-imp_area_frac_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const ImpJob one) {
+imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one, const int NSTAGE) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int jn = blockIdx.y + blockIdx.z * 65535;
     if (jn >= count) return;
-    const ImpJob job = jobs ? jobs[first + jn] : one;
+    const ImpJob* __restrict__ jp = jobs ? jobs + first + jn : &one;
+    ImpJob job;                                                        // everything but the tensor map
+    job.src = jp->src; job.dst = jp->dst; job.pass = jp->pass; job.wm = jp->wm;
+    job.src_pitch = jp->src_pitch; job.dst_pitch = jp->dst_pitch; job.wm_pitch = jp->wm_pitch; job.wm_c = jp->wm_c; job.tm_x0 = jp->tm_x0;
     const uint8_t* __restrict__ blob = job.pass;
     const ImpPass* __restrict__ P = reinterpret_cast<const ImpPass*>(blob);
     const int bw = P->bw, bh = P->bh;
@@ -170,10 +257,10 @@ imp_area_frac_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count
     uint64_t* empty = full + NSTAGE;                                  // [NSTAGE]
     const int nops = P->nops;
     const int ops_bytes = (nops * (int)sizeof(ImpOp) + P->lut_bytes + 15) & ~15;
-    uint8_t* s_ops = smem + 64;
-    uint8_t* tile0 = s_ops + ((ops_bytes + 127) & ~127) + 64;         // 128-byte aligned
+    uint8_t* s_ops = smem + 128;                                      // up to 8 stages: 16 mbarriers
+    uint8_t* tile0 = s_ops + ((ops_bytes + 127) & ~127);              // 128-byte aligned
     const int rs = P->tile_rs;
-    const int stage_bytes = (rs * P->tile_rows + 64 + 127) & ~127;
+    const int stage_bytes = (rs * P->tile_rows + 127) & ~127;
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 1); mbar_init(empty + i, TH); }
@@ -183,47 +270,44 @@ imp_area_frac_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count
         uint4* sdst = reinterpret_cast<uint4*>(s_ops);
         for (int i = tid; i < ops_bytes / 16; i += STRIP_THREADS) sdst[i] = __ldg(gsrc + i);
     }
-    const int2 xt_tile = __ldg(reinterpret_cast<const int2*>(blob + P->xtile_off) + blockIdx.x);     // {px0, px1}
-    const uint8_t* w0 = job.src + (size_t)P->sy0 * job.src_pitch + (size_t)P->sx0 * SC;            // window origin
-    const uint8_t* col_first = w0 + (size_t)xt_tile.x * SC;
-    const int shift = (int)((uintptr_t)col_first & 15);
-    const int row_bytes = (shift + (xt_tile.y - xt_tile.x + 1) * SC + 15) & ~15;
+    // x placement of this strip inside the tensor map (8-byte elements)
+    const int px0 = __ldg(reinterpret_cast<const int2*>(blob + P->xtile_off) + blockIdx.x).x;     // first source pixel of the strip
+    const int xbyte = job.tm_x0 + px0 * SC;                           // its byte offset in the map's row
+    const int c0 = (xbyte >> 4) << 1;                                 // element coordinate of the box; TMA wants the box origin 16-byte aligned
     __syncthreads();
 
     if (tid >= STRIP_CONSUMERS) {
-        // ---- TMA producer warp ----
-        const int lane = tid & 31;
-        const int2* __restrict__ ytile = reinterpret_cast<const int2*>(blob + P->ytile_off);
-        int stage = 0, phase = 0;
-        for (int t = 0; t < tiles_y; t++) {
-            const int2 yt_tile = __ldg(ytile + t);                                                  // {py0, rows}
-            mbar_wait(empty + stage, phase ^ 1);
-            if (lane == 0) mbar_expect_tx(full + stage, (uint32_t)(row_bytes * yt_tile.y));
-            __syncwarp();
-            uint8_t* dst = tile0 + stage * stage_bytes;
-            const uint8_t* src = col_first - shift + (size_t)yt_tile.x * job.src_pitch;
-            for (int r = lane; r < yt_tile.y; r += 32)
-                bulk_g2s(dst + (size_t)r * rs, src + (size_t)r * job.src_pitch, (uint32_t)row_bytes, full + stage);
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        // ---- TMA producer: one elected thread, one instruction per tile ----
+        if (tid == STRIP_CONSUMERS) {
+            const int2* __restrict__ ytile = reinterpret_cast<const int2*>(blob + P->ytile_off);
+            const uint32_t box_bytes = (uint32_t)(rs * P->tile_rows);
+            int stage = 0, phase = 0;
+            for (int t = 0; t < tiles_y; t++) {
+                const int py0 = __ldg(ytile + t).x;
+                mbar_wait(empty + stage, phase ^ 1);
+                mbar_expect_tx(full + stage, box_bytes);
+                tma_load_2d(tile0 + stage * stage_bytes, jp->tmap, c0, py0, full + stage);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
         }
         return;
     }
     // ---- consumers ----
-    const int col_off = shift - xt_tile.x * SC;                       // tile byte offset of source pixel 0
+    const int col_off = job.tm_x0 - c0 * 8;                           // tile byte offset of source pixel 0
     const int bx0 = blockIdx.x * TW;
     switch (P->max_xtaps) {                                           // uniform over the pass
-        case 1:  area_strip_consume<SC, 1, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 2:  area_strip_consume<SC, 2, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 3:  area_strip_consume<SC, 3, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 4:  area_strip_consume<SC, 4, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 5:  area_strip_consume<SC, 5, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 6:  area_strip_consume<SC, 6, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 7:  area_strip_consume<SC, 7, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 8:  area_strip_consume<SC, 8, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 9:  area_strip_consume<SC, 9, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 10: area_strip_consume<SC, 10, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        case 11: area_strip_consume<SC, 11, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
-        default: area_strip_consume<SC, 12, NSTAGE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y); break;
+        case 1:  area_strip_consume<SC, 1, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 2:  area_strip_consume<SC, 2, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 3:  area_strip_consume<SC, 3, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 4:  area_strip_consume<SC, 4, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 5:  area_strip_consume<SC, 5, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 6:  area_strip_consume<SC, 6, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 7:  area_strip_consume<SC, 7, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 8:  area_strip_consume<SC, 8, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 9:  area_strip_consume<SC, 9, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 10: area_strip_consume<SC, 10, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 11: area_strip_consume<SC, 11, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        default: area_strip_consume<SC, 12, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
     }
 }
 

@@ -88,3 +88,7 @@ int hostsim_run(const imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst,
     return 0;
 }
 }
+extern "C" void hostsim_plan_tile_info(const imp_gpu_plan* p, int k, int* out) {
+    const ImpPass& h = p->passes[k].hdr;
+    out[0] = h.tile_rs; out[1] = h.tile_rows; out[2] = h.tile_smem; out[3] = h.max_xtaps; out[4] = h.max_ytaps; out[5] = h.kind;
+}
