@@ -259,7 +259,11 @@ def library() -> Library:
     """The process-wide library handle (built on demand when nvcc is present)."""
     global _default
     if _default is None:
-        if _build.stale():
-            _build.build()
-        _default = Library()
+        override = os.environ.get("IMP_GPU_LIB")           # A/B tuning: load another build of the same ABI
+        if override:
+            _default = Library(override)
+        else:
+            if _build.stale():
+                _build.build()
+            _default = Library()
     return _default

@@ -116,12 +116,10 @@ __device__ __forceinline__ void area_rows(const uint8_t* __restrict__ col0, int 
 // Integer-scale INTER_AREA: plain byte sums over the NT x ycount block. For 4 channels two
 // PRMTs split a pixel into two packed u16 pairs, so a pixel costs LDS + 2 PRMT + 2 IADD (block <= 256 px).
 template <int SC, int NT>
-__device__ __forceinline__ void area_int_rows(const uint8_t* __restrict__ col0, int rs, int py0, const ImpAreaTap* __restrict__ yt, int yfirst, int ycount,
-                                              int (&isum)[SC]) {
+__device__ __forceinline__ void area_int_rows(const uint8_t* __restrict__ row, int rs, int ycount, int (&isum)[SC]) {
     unsigned lo = 0, hi = 0;                       // SC == 4: {B,R} and {G,A} as u16 pairs
 #pragma unroll
     for (int c = 0; c < SC; c++) isum[c] = 0;
-    const uint8_t* row = col0 + (size_t)(__ldg(reinterpret_cast<const int*>(yt + yfirst)) - py0) * rs;
     for (int j = 0; j < ycount; j++, row += rs) {
 #pragma unroll
         for (int k = 0; k < NT; k++) {
@@ -226,13 +224,54 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
 #pragma unroll
             for (int c = 0; c < SC; c++) v[c] = min(rint_pos(sum[c]), 255);          // sums are >= 0
         } else {
-            area_int_rows<SC, NT>(tile0 + stage * stage_bytes + my_off, rs, py0, yt, ryv.x, ryv.y, v);
+            // integer-scale mode lives in area_int_strip_consume()
 #pragma unroll
             for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
         if (in_x && in_y) strip_epilogue<SC>(job, P, s_ops, nops, bx, by, v);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+    }
+}
+
+// Integer-scale consumer (INTER_AREA NxM): no tap tables at all — output row y reads source rows y*ny .. y*ny+ny-1 and
+// output column x reads source pixels x*nx .. — and the store map is hoisted (registers are plentiful here).
+// Kept separate from the fractional consumer: sharing one body cost that one 4 % (register allocation).
+template <int SC, int NT>
+__device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* tile0, int stage_bytes,
+                                                       uint64_t* full, uint64_t* empty, const uint8_t* s_ops, int nops, int bx0, int col_off,
+                                                       int tiles_y, int NSTAGE) {
+    const int bw = P->bw, bh = P->bh, rs = P->tile_rs, oc = P->oc, ny = P->ny;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool in_x = bx0 + lane < bw;
+    const int bx = min(bx0 + lane, bw - 1);
+    const int box_2x2 = (P->nx == 2 && ny == 2);
+    const float box_scale = P->area_scale;
+    const int my_off = col_off + bx * NT * SC;                        // byte offset of my first source pixel in a tile row
+    const ImpFrameMap om = P->out;
+    int stage = 0, phase = 0;
+    for (int t = 0; t < tiles_y; t++) {
+        const int by = min(t * TH + warp, bh - 1);
+        const bool in_y = t * TH + warp < bh;
+        mbar_wait(full + stage, phase);
+        int v[SC];
+        area_int_rows<SC, NT>(tile0 + stage * stage_bytes + my_off + (size_t)(by * ny - t * TH * ny) * rs, rs, ny, v);
+#pragma unroll
+        for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
+        if (in_x && in_y) {
+            ImpPx p;
+            if (SC == 1) { p.b = p.g = p.r = v[0]; p.a = 255; }
+            else { p.b = v[0]; p.g = v[SC > 1 ? 1 : 0]; p.r = v[SC > 2 ? 2 : 0]; p.a = (SC == 4) ? v[SC - 1] : 255; }
+            if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+            int X, Y;
+            imp_map_xy(om, bx, by, X, Y);
+            uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * oc;
+            if (oc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
+            else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
+        }
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
@@ -295,19 +334,36 @@ imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
     // ---- consumers ----
     const int col_off = job.tm_x0 - c0 * 8;                           // tile byte offset of source pixel 0
     const int bx0 = blockIdx.x * TW;
-    switch (P->max_xtaps) {                                           // uniform over the pass
-        case 1:  area_strip_consume<SC, 1, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 2:  area_strip_consume<SC, 2, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 3:  area_strip_consume<SC, 3, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 4:  area_strip_consume<SC, 4, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 5:  area_strip_consume<SC, 5, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 6:  area_strip_consume<SC, 6, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 7:  area_strip_consume<SC, 7, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 8:  area_strip_consume<SC, 8, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 9:  area_strip_consume<SC, 9, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 10: area_strip_consume<SC, 10, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 11: area_strip_consume<SC, 11, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        default: area_strip_consume<SC, 12, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+    if (MODE == 0) {
+        switch (P->max_xtaps) {                                       // uniform over the pass
+        case 1: area_strip_consume<SC, 1, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 2: area_strip_consume<SC, 2, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 3: area_strip_consume<SC, 3, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 4: area_strip_consume<SC, 4, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 5: area_strip_consume<SC, 5, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 6: area_strip_consume<SC, 6, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 7: area_strip_consume<SC, 7, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 8: area_strip_consume<SC, 8, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 9: area_strip_consume<SC, 9, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 10: area_strip_consume<SC, 10, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 11: area_strip_consume<SC, 11, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        default: area_strip_consume<SC, 12, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        }
+    } else {
+        switch (P->nx) {
+        case 1: area_int_strip_consume<SC, 1>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 2: area_int_strip_consume<SC, 2>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 3: area_int_strip_consume<SC, 3>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 4: area_int_strip_consume<SC, 4>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 5: area_int_strip_consume<SC, 5>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 6: area_int_strip_consume<SC, 6>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 7: area_int_strip_consume<SC, 7>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 8: area_int_strip_consume<SC, 8>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 9: area_int_strip_consume<SC, 9>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 10: area_int_strip_consume<SC, 10>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 11: area_int_strip_consume<SC, 11>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        default: area_int_strip_consume<SC, 12>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        }
     }
 }
 
