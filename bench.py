@@ -293,6 +293,15 @@ def main():
             dist.barrier(); dist.destroy_process_group()
         return
     peak, peak_src = peaks()
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json), scaled to
+    # this launch's job count; null for workloads that have no capture yet.
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(a.config)
+        if tj:
+            traffic = tj["traffic_bytes_per_job"] * len(jobs)
+    except Exception:
+        traffic = None
     achieved = algo_bytes / (float(np.mean(step_ms)) / 1e3) / 1e9
     line = {
         "metric": metric, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -302,7 +311,7 @@ def main():
                    "e2e_inputs": "32 distinct pinned host frames per shape, cycled; each request copies its crop window H2D and its result D2H"},
         "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "jobs_per_step": len(h_plans), "steps": a.e2e_steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_step": int(algo_bytes), "kernel_launches_per_step": launches_per_step,
                      "ms_per_launch_group": float(np.mean(step_ms)), "ms_min": float(np.min(step_ms))},
         "clocks": clocks_summary(samples),
