@@ -70,10 +70,22 @@ int plan_to_device(imp_gpu_plan* plan) {
     if (pd.ready) return IMP_OK;
     pd.pass_blobs.assign(plan->passes.size(), nullptr);
     for (size_t i = 0; i < plan->passes.size(); i++) {
-        const std::vector<uint8_t>& b = plan->passes[i].blob;
+        std::vector<uint8_t> b = plan->passes[i].blob;            // per-device copy: vignette table pointers are patched in
+        const ImpPass& h = plan->passes[i].hdr;
+        ImpOp* ops = reinterpret_cast<ImpOp*>(b.data() + h.ops_off);
+        for (int k = 0; k < h.nops; k++) {
+            if (ops[k].kind != IMP_OP_VIGNETTE || ops[k].i[2] <= 0) continue;
+            float* tab = nullptr;
+            CK(cudaMalloc((void**)&tab, (size_t)ops[k].i[2] * sizeof(float)));
+            pd.vignette_tabs.push_back(tab);
+            CK(imp_build_vignette_table(tab, ops[k].i[2], ops[k].f[0], ops[k].f[1], g_dev[d].stream));
+            const unsigned long long v = (unsigned long long)(uintptr_t)tab;
+            ops[k].i[4] = (int)(unsigned)(v & 0xffffffffu); ops[k].i[5] = (int)(unsigned)(v >> 32);
+        }
         CK(cudaMalloc((void**)&pd.pass_blobs[i], b.size()));
         CK(cudaMemcpy(pd.pass_blobs[i], b.data(), b.size(), cudaMemcpyHostToDevice));
     }
+    CK(cudaStreamSynchronize(g_dev[d].stream));
     if (!plan->wm_pixels.empty()) {
         pd.wm_pitch = align16(plan->wm_w * plan->wm_c);
         CK(cudaMalloc((void**)&pd.wm, (size_t)pd.wm_pitch * plan->wm_h));
@@ -91,6 +103,8 @@ void plan_free_device(imp_gpu_plan* plan) {
         if (cudaSetDevice(d) != cudaSuccess) continue;
         for (uint8_t* p : pd.pass_blobs) cudaFree(p);
         if (pd.wm) cudaFree(pd.wm);
+        for (float* t : pd.vignette_tabs) cudaFree(t);
+        pd.vignette_tabs.clear(); pd.wm = nullptr;
         pd.ready = false;
     }
 }
@@ -192,8 +206,17 @@ int pick_variant(const ImpPass& h, const ImpJob& j) {
     const uintptr_t img = (uintptr_t)j.src;
     const uintptr_t win = img + (size_t)h.sy0 * j.src_pitch + (size_t)h.sx0 * h.sc;
     if (img % 16 && win % 16) return 0;
-    return 1;
+    if (h.kind == IMP_G_BLUR) return h.blur_r > 0 ? 2 : 0;           // fused blur tile kernel
+    return 1;                                                        // area strip kernels
 }
+int blur_smem_bytes(const ImpPass& h) {
+    const int ops = (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15;
+    const int span = 32 + 2 * h.blur_r;
+    return 128 + ((ops + 127) & ~127) + ((h.tile_rs * span + 127) & ~127) + span * 32 * h.sc * 2 + 32 * (32 * h.sc + 4) + 64;
+}
+int variant_param(const ImpPass& h, int variant);
+int variant_smem(const ImpPass& h, int variant, int param);
+int variant_tiles(const ImpPass& h, int variant);
 int tile_stage_bytes(const ImpPass& h) { return (h.tile_smem + 127) & ~127; }
 // three ring stages while three CTAs still fit an SM's shared memory, else two
 // Ring depth: as many stages as fit ~64 KB (so three CTAs still share an SM), between 2 and 8. Small tiles
@@ -206,6 +229,14 @@ int tile_stages(const ImpPass& h) {
 int tile_smem_bytes(const ImpPass& h, int stages) {
     const int ops = (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15;
     return 128 + ((ops + 127) & ~127) + stages * tile_stage_bytes(h) + 64;      // +64: padded taps past the last row
+}
+
+int variant_param(const ImpPass& h, int variant) { return variant == 1 ? tile_stages(h) : variant == 2 ? h.blur_r : 0; }
+int variant_smem(const ImpPass& h, int variant, int param) {
+    return variant == 1 ? tile_smem_bytes(h, param) : variant == 2 ? blur_smem_bytes(h) : ops_smem(h);
+}
+int variant_tiles(const ImpPass& h, int variant) {
+    return variant == 1 ? (h.bw + 31) / 32 : variant == 2 ? ((h.bw + 31) / 32) * ((h.bh + 31) / 32) : pass_tiles(h);
 }
 
 int batch_compile(imp_gpu_batch* b) {
@@ -239,7 +270,7 @@ int batch_compile(imp_gpu_batch* b) {
             ImpJob jb = make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->d_scratch, off[i]);
             const int variant = pick_variant(hp.hdr, jb);
             if (variant) { int rc = encode_job_tmap(hp.hdr, jb); if (rc) return rc; }
-            pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, variant ? tile_stages(hp.hdr) : 0, jb, hp.hdr, boff[i][k]});
+            pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, variant_param(hp.hdr, variant), jb, hp.hdr, boff[i][k]});
         }
         std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& c) {
             if (a.kind != c.kind) return a.kind < c.kind;
@@ -250,7 +281,7 @@ int batch_compile(imp_gpu_batch* b) {
         while (s < pend.size()) {
             size_t e = s;
             while (e < pend.size() && pend[e].kind == pend[s].kind && pend[e].sc == pend[s].sc && pend[e].variant == pend[s].variant && pend[e].tmax == pend[s].tmax) e++;
-            if (pend[s].kind == IMP_G_BLUR) {
+            if (pend[s].kind == IMP_G_BLUR && pend[s].variant == 0) {
                 for (size_t j = s; j < e; j++) {
                     imp_gpu_batch::Step st{};
                     st.generic_blur = true; st.job = (int)b->h_jobs.size(); st.hdr = pend[j].hdr; st.smem = ops_smem(pend[j].hdr);
@@ -264,8 +295,8 @@ int batch_compile(imp_gpu_batch* b) {
                 st.g.kind = pend[s].kind; st.g.sc = pend[s].sc; st.g.first = (int)b->h_jobs.size(); st.g.count = (int)(e - s);
                 st.g.max_tiles = 0; st.g.smem_bytes = 16; st.g.variant = pend[s].variant; st.g.tmax = pend[s].tmax;
                 for (size_t j = s; j < e; j++) {
-                    st.g.max_tiles = std::max(st.g.max_tiles, pend[s].variant ? (pend[j].hdr.bw + 31) / 32 : pass_tiles(pend[j].hdr));
-                    st.g.smem_bytes = std::max(st.g.smem_bytes, pend[s].variant ? tile_smem_bytes(pend[j].hdr, pend[s].tmax) : ops_smem(pend[j].hdr));
+                    st.g.max_tiles = std::max(st.g.max_tiles, variant_tiles(pend[j].hdr, pend[s].variant));
+                    st.g.smem_bytes = std::max(st.g.smem_bytes, variant_smem(pend[j].hdr, pend[s].variant, pend[s].tmax));
                     b->h_jobs.push_back(pend[j].job);
                 }
                 b->steps.push_back(st); b->launches += 1;
@@ -292,13 +323,13 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
     for (size_t k = 0; k < p->passes.size(); k++) {
         const ImpHostPass& hp = p->passes[k];
         ImpJob j = make_job(p, t_dev, k, src, sp, dst, dp, scratch, off);
-        if (hp.hdr.kind == IMP_G_BLUR) {
+        const int variant = pick_variant(hp.hdr, j);
+        if (variant) { int rc = encode_job_tmap(hp.hdr, j); if (rc) return rc; }
+        if (hp.hdr.kind == IMP_G_BLUR && variant == 0) {
             CK(imp_launch_blur_generic(j, hp.hdr, (uint16_t*)(scratch + boff[k]), ops_smem(hp.hdr), st));
         } else {
-            const int variant = pick_variant(hp.hdr, j);
-            if (variant) { int rc = encode_job_tmap(hp.hdr, j); if (rc) return rc; }
-            ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, variant ? (hp.hdr.bw + 31) / 32 : pass_tiles(hp.hdr), variant ? tile_smem_bytes(hp.hdr, tile_stages(hp.hdr)) : ops_smem(hp.hdr),
-                             variant, variant ? tile_stages(hp.hdr) : 0};
+            const int param = variant_param(hp.hdr, variant);
+            ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, variant_tiles(hp.hdr, variant), variant_smem(hp.hdr, variant, param), variant, param};
             CK(imp_launch_group(g, nullptr, &j, st));
         }
     }

@@ -30,6 +30,7 @@ struct imp_gpu_plan {
     struct Dev {
         std::vector<uint8_t*> pass_blobs;
         uint8_t* wm = nullptr; int wm_pitch = 0;
+        std::vector<float*> vignette_tabs;         // one per vignette op that is tabulated
         bool ready = false;
     };
     Dev dev[16];
@@ -53,4 +54,5 @@ cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, cons
 // Two-kernel Gaussian through a u16 scratch (any sigma). One job, passed by value.
 cudaError_t imp_launch_blur_generic(const ImpJob& job, const ImpPass& hdr, uint16_t* d_scratch, int smem_bytes, cudaStream_t st);
 unsigned long long imp_launches();
-cudaError_t imp_upload_tables();          // per-device constant tables of imp_pixel.cuh
+cudaError_t imp_upload_tables();
+cudaError_t imp_build_vignette_table(float* d_tab, int n, float maxr, float intensity, cudaStream_t st);          // per-device constant tables of imp_pixel.cuh

@@ -24,6 +24,24 @@ cudaError_t imp_upload_tables() {
     return cudaMemcpyToSymbol(g_imp_div30, b, sizeof b);
 }
 
+// mask[d2] for d2 = 0..n-1: the per-pixel code of imp_vignette_mask evaluated at (dx, dy) = (d2's exact sqrt is not
+// needed: the mask only sees sqrt(dx*dx+dy*dy) = sqrt(d2)), i.e. at x = cx - 0 ... expressed through d2 directly.
+__global__ void imp_vignette_table_kernel(float* __restrict__ tab, int n, float maxr, float intensity) {
+    const int d2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d2 >= n) return;
+    const float distance = (float)sqrt((double)d2);
+    const float raw = __fmul_rn(__fdiv_rn(distance, maxr), intensity);
+    const double c = cos((double)raw);
+    const double c2 = c * c;
+    tab[d2] = (float)(c2 * c2);
+}
+
+cudaError_t imp_build_vignette_table(float* d_tab, int n, float maxr, float intensity, cudaStream_t st) {
+    imp_vignette_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_tab, n, maxr, intensity);
+    g_imp_launches++;
+    return cudaGetLastError();
+}
+
 namespace {
 
 constexpr int TILE_W = 32, TILE_H = 8;
@@ -196,7 +214,42 @@ cudaError_t launch_area_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, cons
     return cudaGetLastError();
 }
 
+template <int SC, int R>
+cudaError_t launch_blur_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
+    static bool attr_set[16] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    auto kern = imp_tiles::imp_blur_tile_kernel<SC, R>;
+    if (!attr_set[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 15] = true;
+    }
+    dim3 block(imp_tiles::BLUR_THREADS);
+    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);      // max_tiles = 32x32 tiles
+    kern<<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o);
+    g_imp_launches++;
+    return cudaGetLastError();
+}
+
+template <int SC>
+cudaError_t launch_blur_tile_r(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
+    switch (g.tmax) {
+        case 3:  return launch_blur_tile<SC, 3>(g, d_jobs, o, st);
+        case 6:  return launch_blur_tile<SC, 6>(g, d_jobs, o, st);
+        case 9:  return launch_blur_tile<SC, 9>(g, d_jobs, o, st);
+        case 12: return launch_blur_tile<SC, 12>(g, d_jobs, o, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st) {
+    if (g.variant == 2 && g.kind == IMP_G_BLUR) {
+        const ImpJob dummy{};
+        const ImpJob& o = one ? *one : dummy;
+        if (g.sc == 3) return launch_blur_tile_r<3>(g, d_jobs, o, st);
+        if (g.sc == 4) return launch_blur_tile_r<4>(g, d_jobs, o, st);
+        return cudaErrorInvalidValue;
+    }
     if (g.variant == 1 && (g.kind == IMP_G_AREA_FRAC || g.kind == IMP_G_AREA_INT)) {
         const ImpJob dummy{};
         const ImpJob& o = one ? *one : dummy;

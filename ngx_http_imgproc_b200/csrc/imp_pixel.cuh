@@ -211,6 +211,13 @@ float imp_vignette_mask(int x, int y, int cx, int cy, float maxr, float intensit
     return (float)(c2 * c2);
 }
 
+IMP_HD void imp_op_vignette_masked(ImpPx& p, float mask) {
+    int h, s, v;
+    imp_rgb2hsv(p.b, p.g, p.r, h, s, v);
+    v = imp_f2u(IMP_FMUL(imp_u2f(v), mask)) & 255;          // mask = cos^4 >= 0 (NaN -> low byte 0, as on x86)
+    imp_hsv2rgb(h, s, v, p.b, p.g, p.r);
+}
+
 IMP_HD void imp_op_vignette(ImpPx& p, int x, int y, int cx, int cy, float maxr, float intensity) {
     float mask = imp_vignette_mask(x, y, cx, cy, maxr, intensity);
     int h, s, v;
@@ -283,6 +290,14 @@ IMP_HD void imp_run_ops(ImpPx& p, int oc, int bx, int by, const ImpOp* ops, int 
             } break;
             case IMP_OP_VIGNETTE: {
                 int x, y; imp_map_xy(op.map, bx, by, x, y);
+#if defined(__CUDA_ARCH__)
+                const float* tab = reinterpret_cast<const float*>(((unsigned long long)(unsigned)op.i[5] << 32) | (unsigned)op.i[4]);
+                if (tab) {           // mask[d2], tabulated per plan by imp_vignette_table_kernel with the code of imp_vignette_mask
+                    const int dx = op.i[0] - x, dy = op.i[1] - y;
+                    imp_op_vignette_masked(p, __ldg(tab + (dx * dx + dy * dy)));
+                    break;
+                }
+#endif
                 imp_op_vignette(p, x, y, op.i[0], op.i[1], op.f[0], op.f[1]);
             } break;
             case IMP_OP_LOMO: p.g = imp_lomo1(p.g); p.r = imp_lomo1(p.r); break;

@@ -210,6 +210,21 @@ struct Lower {
         hdr.ksize = (int)k.size();
         hdr.taps_off = bb.add(k.data(), k.size() * sizeof(int));
         sigma = sg;
+        // tile kernel (imp_tiles.cuh): effective radius after trimming zero outer taps, padded up to 3/6/9/12
+        int lo = 0, hi = (int)k.size() - 1;
+        while (lo < hi && k[lo] == 0 && k[hi] == 0) { lo++; hi--; }
+        const int r_eff = (hi - lo) / 2;
+        hdr.blur_r = r_eff <= 3 ? 3 : r_eff <= 6 ? 6 : r_eff <= 9 ? 9 : r_eff <= 12 ? 12 : 0;
+        if (k.size() == 1) hdr.blur_r = 0;                          // n == 1 holds the single tap 256, a plain copy
+        if (hdr.blur_r) {
+            const int R = hdr.blur_r;
+            std::vector<int> kr(2 * R + 1, 0);
+            for (int i = lo; i <= hi; i++) kr[R - r_eff + (i - lo)] = k[i];
+            hdr.tapsr_off = bb.add(kr.data(), kr.size() * sizeof(int));
+            hdr.tile_rows = 32 + 2 * R;
+            hdr.tile_rs = ((32 + 2 * R) * hdr.sc + 15 + 15) & ~15;
+            hdr.tile_smem = hdr.tile_rs * hdr.tile_rows;
+        }
     }
 };
 
@@ -334,6 +349,13 @@ int lower_filter(Lower& L, const char* request, int allow) {
                 if (maxd < d) maxd = d;
             }
             ImpOp o{}; o.kind = IMP_OP_VIGNETTE; o.i[0] = cx; o.i[1] = cy; o.f[0] = radius * maxd; o.f[1] = intensity; o.map = fr.map();
+            // The mask depends on the pixel only through d2 = dx*dx + dy*dy, an integer: the runtime tabulates it once per
+            // plan and device (same double-precision code as the per-pixel path) when the table stays below 64 MB.
+            {
+                long long mx = std::max(cx, w - 1 - cx), my = std::max(cy, h - 1 - cy);
+                long long entries = mx * mx + my * my + 1;
+                o.i[2] = entries <= (16ll << 20) ? (int)entries : 0;
+            }
             L.ops.push_back(o);
             return IMP_OK;
         }

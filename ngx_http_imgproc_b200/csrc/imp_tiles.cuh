@@ -367,4 +367,136 @@ imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
     }
 }
 
+// ---- Gaussian blur (cvSmooth CV_GAUSSIAN) fused with the op list and the oriented store ------------
+// One CTA per 32x32 output tile. The (32+2R)^2 source neighbourhood arrives by ONE TMA box load (zero-filled outside
+// the tensor), border pixels are then replicated in shared memory (BORDER_REPLICATE), a horizontal pass leaves exact
+// u16 sums in shared memory, a vertical pass produces the blurred bytes, the op list runs per pixel, and the tile is
+// written in destination orientation so that a rotate=90/270 still stores 32-pixel contiguous rows.
+// Each thread keeps a sliding window of 8+2R samples in registers (8 outputs per window): ~2.5 shared loads and 2R+1
+// integer MACs per output byte and pass. R is the tap radius padded to {3,6,9,12}; zero taps change nothing.
+constexpr int BT = 32;                              // blur tile edge
+constexpr int BLUR_THREADS = 256;
+
+template <int SC, int R>
+__global__ void __launch_bounds__(BLUR_THREADS)
+imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int jn = blockIdx.y + blockIdx.z * 65535;
+    if (jn >= count) return;
+    const ImpJob* __restrict__ jp = jobs ? jobs + first + jn : &one;
+    ImpJob job;
+    job.src = jp->src; job.dst = jp->dst; job.pass = jp->pass; job.wm = jp->wm;
+    job.src_pitch = jp->src_pitch; job.dst_pitch = jp->dst_pitch; job.wm_pitch = jp->wm_pitch; job.wm_c = jp->wm_c; job.tm_x0 = jp->tm_x0;
+    const uint8_t* __restrict__ blob = job.pass;
+    const ImpPass* __restrict__ P = reinterpret_cast<const ImpPass*>(blob);
+    const int w = P->sw, h = P->sh;                                   // blur: base frame == source window
+    const int tiles_x = (w + BT - 1) / BT, tiles_y = (h + BT - 1) / BT;
+    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
+    constexpr int SPAN = BT + 2 * R;                                   // source rows / columns per tile
+    constexpr int HROW = BT * SC;                                      // u16 per row of the horizontal-pass buffer
+    constexpr int SROW = BT * SC + 4;                                  // staging row stride (bytes), padded against bank conflicts
+    const int rs = P->tile_rs;
+    const int nops = P->nops;
+    const int ops_bytes = (nops * (int)sizeof(ImpOp) + P->lut_bytes + 15) & ~15;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    uint8_t* s_ops = smem + 128;
+    uint8_t* tile = s_ops + ((ops_bytes + 127) & ~127);
+    uint16_t* hbuf = reinterpret_cast<uint16_t*>(tile + ((rs * SPAN + 127) & ~127));
+    uint8_t* stage = reinterpret_cast<uint8_t*>(hbuf + SPAN * HROW);
+    const int tid = threadIdx.x;
+    const int x0 = (blockIdx.x % tiles_x) * BT, y0 = (blockIdx.x / tiles_x) * BT;
+    // box origin: source pixel (x0-R, y0-R); 16-byte aligned in x as TMA requires (coordinates may be negative)
+    const int xbyte = job.tm_x0 + (x0 - R) * SC;
+    const int c0 = (xbyte >> 4) << 1;
+    const int col_off = job.tm_x0 - c0 * 8;                            // tile byte offset of source pixel 0
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)(rs * SPAN));
+        tma_load_2d(tile, jp->tmap, c0, y0 - R, bar);
+    }
+    {
+        const uint4* gsrc = reinterpret_cast<const uint4*>(blob + P->ops_off);
+        uint4* sdst = reinterpret_cast<uint4*>(s_ops);
+        for (int i = tid; i < ops_bytes / 16; i += BLUR_THREADS) sdst[i] = __ldg(gsrc + i);
+    }
+    int k[2 * R + 1];
+    {
+        const int* taps = reinterpret_cast<const int*>(blob + P->tapsr_off);
+#pragma unroll
+        for (int i = 0; i < 2 * R + 1; i++) k[i] = __ldg(taps + i);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    // BORDER_REPLICATE: fill the part of the neighbourhood that lies outside the image from the clamped pixel
+    if (x0 - R < 0 || y0 - R < 0 || x0 + BT + R > w || y0 + BT + R > h) {
+        for (int i = tid; i < SPAN * SPAN; i += BLUR_THREADS) {
+            const int ty = i / SPAN, tx = i - ty * SPAN;
+            const int X = x0 - R + tx, Y = y0 - R + ty;
+            const int cx = min(max(X, 0), w - 1), cy = min(max(Y, 0), h - 1);
+            if (cx != X || cy != Y) {
+                const uint8_t* s = tile + (cy - (y0 - R)) * rs + col_off + cx * SC;
+                uint8_t* d = tile + ty * rs + col_off + X * SC;
+#pragma unroll
+                for (int c = 0; c < SC; c++) d[c] = s[c];
+            }
+        }
+        __syncthreads();
+    }
+
+    // horizontal pass: item = (row, 8-pixel group, channel)
+    for (int item = tid; item < SPAN * 4 * SC; item += BLUR_THREADS) {
+        const int c = item % SC, g = (item / SC) & 3, row = item / (SC * 4);
+        const uint8_t* p = tile + row * rs + col_off + (x0 + g * 8 - R) * SC + c;
+        int sv[8 + 2 * R];
+#pragma unroll
+        for (int j = 0; j < 8 + 2 * R; j++) sv[j] = p[j * SC];
+        uint16_t* hp = hbuf + row * HROW + g * 8 * SC + c;
+#pragma unroll
+        for (int o = 0; o < 8; o++) {
+            int acc = 0;
+#pragma unroll
+            for (int i = 0; i < 2 * R + 1; i++) acc += sv[o + i] * k[i];
+            hp[o * SC] = (uint16_t)acc;
+        }
+    }
+    __syncthreads();
+    // vertical pass: item = (byte column, 8-row group)
+    for (int item = tid; item < HROW * 4; item += BLUR_THREADS) {
+        const int xb = item % HROW, g = item / HROW;
+        const uint16_t* p = hbuf + (g * 8) * HROW + xb;
+        int sv[8 + 2 * R];
+#pragma unroll
+        for (int j = 0; j < 8 + 2 * R; j++) sv[j] = p[j * HROW];
+#pragma unroll
+        for (int o = 0; o < 8; o++) {
+            unsigned acc = 32768u;
+#pragma unroll
+            for (int i = 0; i < 2 * R + 1; i++) acc += (unsigned)(sv[o + i] * k[i]);
+            stage[(g * 8 + o) * SROW + xb] = (uint8_t)(acc >> 16);
+        }
+    }
+    __syncthreads();
+    // op list + store. With a transposing output map the lane runs along the tile's y so that consecutive lanes still
+    // write consecutive destination pixels.
+    const ImpFrameMap om = P->out;
+    const int oc = P->oc;
+    const int lane = tid & 31, wrp = tid >> 5;
+    for (int it = 0; it < BT / 8; it++) {
+        const int u = wrp + it * 8;
+        const int lx = om.swap ? u : lane, ly = om.swap ? lane : u;
+        const int bx = x0 + lx, by = y0 + ly;
+        if (bx >= w || by >= h) continue;
+        const uint8_t* sp = stage + ly * SROW + lx * SC;
+        ImpPx p;
+        p.b = sp[0]; p.g = sp[1]; p.r = sp[2]; p.a = (SC == 4) ? sp[3 % SC] : 255;
+        if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+        int X, Y;
+        imp_map_xy(om, bx, by, X, Y);
+        uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * oc;
+        if (oc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
+        else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
+    }
+}
+
 }  // namespace imp_tiles
