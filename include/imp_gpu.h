@@ -153,6 +153,12 @@ int  imp_gpu_farm_run_host(int n, imp_gpu_plan* const* plans, const unsigned cha
                            const int* src_steps, unsigned char* const* dsts, const int* dst_steps,
                            int n_gpus, int n_streams);
 
+/* ---- first "next" row: CalcPerceivedBrightness (filters.c:707-729) as a device reduction -------- */
+/* What Info() (bridge.c:283-300) prints as round(brightness*100). The reference accumulates float32 in column-major
+ * order; the device sums in double, so values agree to ~1e-5 relative and the JSON integer is compared in the tests. */
+int  imp_gpu_brightness_device(const void* d_img, int pitch, int width, int height, int channels, float* brightness, void* stream);
+int  imp_gpu_brightness_host(const unsigned char* img, int step, int width, int height, int channels, float* brightness);
+
 /* ---- memory helpers so a C host needs no CUDA headers --------------------------------------------- */
 int  imp_gpu_malloc(void** d_ptr, size_t bytes);
 int  imp_gpu_free(void* d_ptr);

@@ -127,6 +127,8 @@ class Library:
         L.imp_gpu_upload_2d.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.imp_gpu_download_2d.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.imp_gpu_sync.argtypes = [C.c_void_p]
+        L.imp_gpu_brightness_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.imp_gpu_brightness_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]
 
     # ---- lifetime ---------------------------------------------------------------------------------
     def last_error(self) -> str:
@@ -150,6 +152,13 @@ class Library:
 
     def launch_count(self) -> int:
         return int(self.lib.imp_gpu_launch_count())
+
+    def brightness(self, img: np.ndarray) -> float:
+        """CalcPerceivedBrightness (filters.c:707-729) of a host frame, reduced on the device."""
+        img = np.ascontiguousarray(img if img.ndim == 3 else img[:, :, None], dtype=np.uint8)
+        out = C.c_float(0)
+        self.check(self.lib.imp_gpu_brightness_host(img.ctypes.data, img.strides[0], img.shape[1], img.shape[0], img.shape[2], C.byref(out)))
+        return float(out.value)
 
     # ---- plans --------------------------------------------------------------------------------------
     def plan(self, w, h, c, cfg: Optional[Config] = None, **req) -> "Plan":

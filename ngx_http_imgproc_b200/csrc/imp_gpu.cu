@@ -627,6 +627,35 @@ int imp_gpu_farm_run_host(int n, imp_gpu_plan* const* plans, const unsigned char
     return IMP_OK;
 }
 
+// ---- "next" row §8f-1: perceived brightness as a device reduction ------------------------------------------
+int imp_gpu_brightness_device(const void* d_img, int pitch, int w, int h, int c, float* brightness, void* stream) {
+    int rc = bind(); if (rc) return rc;
+    if (!d_img || !brightness || w <= 0 || h <= 0 || (c != 1 && c != 3 && c != 4)) return IMP_ERROR_INVALID_ARGS;
+    cudaStream_t st = pick_stream(stream);
+    double* d_acc = nullptr;
+    CK(cudaMallocAsync((void**)&d_acc, sizeof(double), st));
+    CK(imp_launch_brightness((const uint8_t*)d_img, pitch, w, h, c, d_acc, st));
+    double sum = 0;
+    CK(cudaMemcpyAsync(&sum, d_acc, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaFreeAsync(d_acc, st));
+    CK(cudaStreamSynchronize(st));
+    *brightness = (float)(sum / ((double)w * h) / 255.0);          // filters.c:728
+    return IMP_OK;
+}
+
+int imp_gpu_brightness_host(const unsigned char* img, int step, int w, int h, int c, float* brightness) {
+    int rc = bind(); if (rc) return rc;
+    if (!img || !brightness || w <= 0 || h <= 0 || (c != 1 && c != 3 && c != 4)) return IMP_ERROR_INVALID_ARGS;
+    cudaStream_t st = g_dev[t_dev].stream;
+    const int pitch = align16(w * c);
+    uint8_t* d = nullptr;
+    CK(cudaMallocAsync((void**)&d, (size_t)pitch * h, st));
+    CK(cudaMemcpy2DAsync(d, pitch, img, step, (size_t)w * c, h, cudaMemcpyHostToDevice, st));
+    rc = imp_gpu_brightness_device(d, pitch, w, h, c, brightness, st);
+    cudaFreeAsync(d, st);
+    return rc;
+}
+
 // ---- memory helpers ------------------------------------------------------------------------------------
 int imp_gpu_malloc(void** p, size_t bytes) { int rc = bind(); if (rc) return rc; CK(cudaMalloc(p, bytes)); return IMP_OK; }
 int imp_gpu_free(void* p) { int rc = bind(); if (rc) return rc; CK(cudaFree(p)); return IMP_OK; }

@@ -42,6 +42,43 @@ cudaError_t imp_build_vignette_table(float* d_tab, int n, float maxr, float inte
     return cudaGetLastError();
 }
 
+// CalcPerceivedBrightness (filters.c:707-729): sum over pixels of sqrt(r*r*0.241 + g*g*0.691 + b*b*0.068) (or of the gray
+// value), as a device reduction so that `format=json` (Info, bridge.c:283-300) needs 8 bytes back instead of the frame.
+// The reference's running float32 sum in column-major order is not reproducible in parallel; this sums in double and the
+// caller divides by w*h*255. Parity is stated on the JSON integer round(brightness*100) (tests/test_gpu_parity.py).
+__global__ void __launch_bounds__(256) imp_brightness_kernel(const uint8_t* __restrict__ img, int pitch, int w, int h, int c, double* __restrict__ acc) {
+    double s = 0.0;
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+        const uint8_t* row = img + (size_t)y * pitch;
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
+            if (c == 1) s += (double)row[x];
+            else {
+                const uint8_t* p = row + (size_t)x * c;
+                const int b = p[0], g = p[1], r = p[2];
+                s += sqrt(r * r * 0.241 + g * g * 0.691 + b * b * 0.068);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += ws[i];
+        atomicAdd(acc, t);
+    }
+}
+
+cudaError_t imp_launch_brightness(const uint8_t* d_img, int pitch, int w, int h, int c, double* d_acc, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(d_acc, 0, sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    dim3 grid((w + 255) / 256 > 8 ? 8 : (w + 255) / 256, h < 1184 ? h : 1184);
+    imp_brightness_kernel<<<grid, 256, 0, st>>>(d_img, pitch, w, h, c, d_acc);
+    g_imp_launches++;
+    return cudaGetLastError();
+}
+
 namespace {
 
 constexpr int TILE_W = 32, TILE_H = 8;

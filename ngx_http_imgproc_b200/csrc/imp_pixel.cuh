@@ -54,7 +54,12 @@ __device__ __forceinline__ int imp_udiv16(int n, int d) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(imp_u2f(d)));
     return imp_f2u(__fmul_rn(imp_u2f(n), __fmul_rn(r, 1.000003814697265625f)));
 }
+// |x| < 2^22 -> float, exact (IADD + FADD); float |x| < 2^22 -> round-half-even int (FADD + IADD)
+__device__ __forceinline__ float imp_i2f22(int x) { return __fadd_rn(__int_as_float(0x4B400000 + x), -12582912.0f); }
+__device__ __forceinline__ int imp_rint22(float x) { return __float_as_int(__fadd_rn(x, 12582912.0f)) - 0x4B400000; }
 #else
+inline float imp_i2f22(int x) { return (float)x; }
+inline int imp_rint22(float x) { return (int)lrintf(x); }
 inline float imp_u2f(int x) { return (float)x; }
 inline int imp_f2u(float x) { return (x == x) ? (int)x : 0x400000; }
 inline int imp_udiv16(int n, int d) { return n / d; }

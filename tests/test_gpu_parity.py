@@ -271,3 +271,16 @@ def test_properties_full_size(gpu):
     assert np.array_equal(c1, c2)                                             # blur commutes with the dihedral maps
     flat = np.full((1500, 2000, 4), 77, np.uint8)
     assert (gpu.run(flat, resize="333,211") == 77).all() and (gpu.run(flat, filters=["blur=6"]) == 77).all()
+
+
+def test_perceived_brightness_reduction(gpu, orc):
+    """Info()'s brightness. The reference's sequential float32 sum is order-dependent, so parity is the
+    JSON integer round(brightness*100) and a 1e-4 absolute band on the value itself."""
+    o = orc.orc()
+    for (h, w, c) in [(2, 4, 3), (270, 480, 4), (1080, 1920, 3), (33, 47, 1), (1, 1, 3)]:
+        img = smooth_image(h + w, h, w, c) if h > 2 else np.array([[[0,0,0],[255,255,255],[10,128,250],[200,30,180]],[[37,201,99],[128,128,128],[255,0,170],[3,2,1]]], np.uint8)
+        got, ref = gpu.brightness(img), o.perceived_brightness(img)
+        assert abs(got - ref) < 1e-4, (h, w, c, got, ref)
+        if abs(ref * 100 - round(ref * 100)) < 0.49:
+            assert round(got * 100) == round(ref * 100)
+    assert abs(gpu.brightness(np.array([[[0,0,0],[255,255,255],[10,128,250],[200,30,180]],[[37,201,99],[128,128,128],[255,0,170],[3,2,1]]], np.uint8)) - 0.45781034) < 1e-6   # App. B
