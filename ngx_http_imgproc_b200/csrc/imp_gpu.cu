@@ -201,6 +201,7 @@ int encode_job_tmap(const ImpPass& h, ImpJob& j) {
 }
 
 int pick_variant(const ImpPass& h, const ImpJob& j) {
+    if (h.kind == IMP_G_CUBIC) return 3;                             // column-run kernel: no alignment requirements
     if (h.tile_smem <= 0 || !encode_tiled()) return 0;
     if (j.src_pitch % 16) return 0;
     const uintptr_t img = (uintptr_t)j.src;
@@ -236,7 +237,7 @@ int variant_smem(const ImpPass& h, int variant, int param) {
     return variant == 1 ? tile_smem_bytes(h, param) : variant == 2 ? blur_smem_bytes(h) : ops_smem(h);
 }
 int variant_tiles(const ImpPass& h, int variant) {
-    return variant == 1 ? (h.bw + 31) / 32 : variant == 2 ? ((h.bw + 31) / 32) * ((h.bh + 31) / 32) : pass_tiles(h);
+    return variant == 1 ? (h.bw + 31) / 32 : (variant == 2 || variant == 3) ? ((h.bw + 31) / 32) * ((h.bh + 31) / 32) : pass_tiles(h);
 }
 
 int batch_compile(imp_gpu_batch* b) {
@@ -269,7 +270,7 @@ int batch_compile(imp_gpu_batch* b) {
             const ImpHostPass& hp = it.plan->passes[k];
             ImpJob jb = make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->d_scratch, off[i]);
             const int variant = pick_variant(hp.hdr, jb);
-            if (variant) { int rc = encode_job_tmap(hp.hdr, jb); if (rc) return rc; }
+            if (variant == 1 || variant == 2) { int rc = encode_job_tmap(hp.hdr, jb); if (rc) return rc; }
             pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, variant_param(hp.hdr, variant), jb, hp.hdr, boff[i][k]});
         }
         std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& c) {
@@ -324,7 +325,7 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
         const ImpHostPass& hp = p->passes[k];
         ImpJob j = make_job(p, t_dev, k, src, sp, dst, dp, scratch, off);
         const int variant = pick_variant(hp.hdr, j);
-        if (variant) { int rc = encode_job_tmap(hp.hdr, j); if (rc) return rc; }
+        if (variant == 1 || variant == 2) { int rc = encode_job_tmap(hp.hdr, j); if (rc) return rc; }
         if (hp.hdr.kind == IMP_G_BLUR && variant == 0) {
             CK(imp_launch_blur_generic(j, hp.hdr, (uint16_t*)(scratch + boff[k]), ops_smem(hp.hdr), st));
         } else {

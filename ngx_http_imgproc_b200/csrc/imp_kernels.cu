@@ -163,6 +163,97 @@ imp_pass_kernel(const ImpJob* __restrict__ jobs, int first, int count, const Imp
     if (oc == 4) store_px<4>(job, P, bx, by, p); else store_px<3>(job, P, bx, by, p);
 }
 
+// ---- INTER_CUBIC with the horizontal pass shared down a column run ------------------------------------------------
+// A thread produces CUBIC_RUN vertically adjacent output pixels of one column. OpenCV's H[row][dx] (int32, SURVEY
+// App. A.4) depends only on the source row and the output column, so a sliding window of four H rows is carried
+// down the run: at 2x upscale that is ~1.4 horizontal rows per output instead of 4. The window is held as floats
+// (the conversion is exact, |H| < 2^22) because the vertical pass of every byte below simd_end is OpenCV's float
+// form; the last <8 bytes of a row take the integer form through the generic per-pixel gather.
+constexpr int CUBIC_RUN = 4;
+
+template <int SC>
+__device__ __forceinline__ void cubic_hrow(const ImpSrcGlobal<SC>& S, const int (&sx)[4], int sy, int a0, int a1, int a2, int a3, float (&hf)[SC]) {
+    int p0[SC], p1[SC], p2[SC], p3[SC];
+    S.px(sx[0], sy, p0); S.px(sx[1], sy, p1); S.px(sx[2], sy, p2); S.px(sx[3], sy, p3);
+#pragma unroll
+    for (int c = 0; c < SC; c++) hf[c] = imp_i2f22(p0[c] * a0 + p1[c] * a1 + p2[c] * a2 + p3[c] * a3);
+}
+
+template <int SC>
+__global__ void __launch_bounds__(TILE_W * TILE_H)
+imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, const ImpJob one) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int jn = blockIdx.y + blockIdx.z * 65535;
+    if (jn >= count) return;
+    const ImpJob job = jobs ? jobs[first + jn] : one;
+    const uint8_t* blob = job.pass;
+    const ImpPass* __restrict__ P = reinterpret_cast<const ImpPass*>(blob);
+    const int bw = P->bw, bh = P->bh;
+    const int tiles_x = (bw + TILE_W - 1) / TILE_W, tiles_y = (bh + TILE_H * CUBIC_RUN - 1) / (TILE_H * CUBIC_RUN);
+    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
+    OpsSmem os = stage_ops(P, blob, smem);
+    const int bx = (blockIdx.x % tiles_x) * TILE_W + threadIdx.x;
+    const int by0 = ((blockIdx.x / tiles_x) * TILE_H + threadIdx.y) * CUBIC_RUN;
+    if (bx >= bw || by0 >= bh) return;
+    ImpSrcGlobal<SC> S;
+    S.base = job.src + (size_t)P->sy0 * job.src_pitch + (size_t)P->sx0 * SC;
+    S.pitch = job.src_pitch;
+    const int sw = P->sw, sh = P->sh, oc = P->oc, nops = P->nops, simd_end = P->simd_end;
+    const int* __restrict__ xofs = reinterpret_cast<const int*>(blob + P->xofs_off);
+    const short* __restrict__ xa = reinterpret_cast<const short*>(blob + P->xcoef_off);
+    const int* __restrict__ yofs = reinterpret_cast<const int*>(blob + P->yofs_off);
+    const short* __restrict__ yb = reinterpret_cast<const short*>(blob + P->ycoef_off);
+    const bool fast = bx * SC + SC <= simd_end;                        // every byte of this pixel is on the float path
+    int sx[4];
+    const int x0 = __ldg(xofs + bx) - 1;
+#pragma unroll
+    for (int t = 0; t < 4; t++) sx[t] = min(max(x0 + t, 0), sw - 1);
+    const int2 av = __ldg(reinterpret_cast<const int2*>(xa + bx * 4));   // 4 shorts, 8-byte aligned
+    const int a0 = (short)(av.x & 0xffff), a1 = av.x >> 16, a2 = (short)(av.y & 0xffff), a3 = av.y >> 16;
+    float h0[SC], h1[SC], h2[SC], h3[SC];
+    int top = 0;
+    const float sc = 1.0f / 4194304.0f;
+    for (int o = 0; o < CUBIC_RUN; o++) {
+        const int by = by0 + o;
+        if (by >= bh) break;
+        int v[4] = {0, 0, 0, 255};
+        if (fast) {
+            const int want = __ldg(yofs + by) - 1;
+            if (o == 0 || want - top > 3 || want < top) {
+                top = want;
+                cubic_hrow<SC>(S, sx, min(max(top, 0), sh - 1), a0, a1, a2, a3, h0);
+                cubic_hrow<SC>(S, sx, min(max(top + 1, 0), sh - 1), a0, a1, a2, a3, h1);
+                cubic_hrow<SC>(S, sx, min(max(top + 2, 0), sh - 1), a0, a1, a2, a3, h2);
+                cubic_hrow<SC>(S, sx, min(max(top + 3, 0), sh - 1), a0, a1, a2, a3, h3);
+            } else {
+                while (top < want) {
+#pragma unroll
+                    for (int c = 0; c < SC; c++) { h0[c] = h1[c]; h1[c] = h2[c]; h2[c] = h3[c]; }
+                    top++;
+                    cubic_hrow<SC>(S, sx, min(max(top + 3, 0), sh - 1), a0, a1, a2, a3, h3);
+                }
+            }
+            const int2 bv = __ldg(reinterpret_cast<const int2*>(yb + by * 4));
+            const float f0 = __fmul_rn(imp_i2f22((short)(bv.x & 0xffff)), sc), f1 = __fmul_rn(imp_i2f22(bv.x >> 16), sc);
+            const float f2 = __fmul_rn(imp_i2f22((short)(bv.y & 0xffff)), sc), f3 = __fmul_rn(imp_i2f22(bv.y >> 16), sc);
+#pragma unroll
+            for (int c = 0; c < SC; c++) {
+                const float t3 = __fmul_rn(h3[c], f3);
+                const float t2 = __fadd_rn(__fmul_rn(h2[c], f2), t3);
+                const float t1 = __fadd_rn(__fmul_rn(h1[c], f1), t2);
+                const float t0 = __fadd_rn(__fmul_rn(h0[c], f0), t1);
+                v[c] = imp_sat8(imp_rint22(t0));
+            }
+        } else {
+            imp_gather_cubic<SC>(S, sw, sh, xofs, xa, yofs, yb, simd_end, bx, by, v);
+        }
+        ImpPx p;
+        promote<SC>(v, p);
+        if (nops) imp_run_ops(p, oc, bx, by, os.ops, nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
+        if (oc == 4) store_px<4>(job, P, bx, by, p); else store_px<3>(job, P, bx, by, p);
+    }
+}
+
 // ---- generic Gaussian (any sigma): horizontal pass to a u16 scratch, vertical pass + ops + store ----
 template <int SC>
 __global__ void __launch_bounds__(256) imp_blur_h_kernel(const ImpJob job, uint16_t* __restrict__ tmp) {
@@ -279,7 +370,23 @@ cudaError_t launch_blur_tile_r(const ImpLaunchGroup& g, const ImpJob* d_jobs, co
     return cudaErrorInvalidValue;
 }
 
+cudaError_t launch_cubic_run(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st) {
+    const ImpJob dummy{};
+    const ImpJob& o = one ? *one : dummy;
+    dim3 block(TILE_W, TILE_H);
+    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);     // max_tiles = 32 x (8*CUBIC_RUN) tiles
+    switch (g.sc) {
+        case 1: imp_cubic_run_kernel<1><<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o); break;
+        case 3: imp_cubic_run_kernel<3><<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o); break;
+        case 4: imp_cubic_run_kernel<4><<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o); break;
+        default: return cudaErrorInvalidValue;
+    }
+    g_imp_launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st) {
+    if (g.variant == 3 && g.kind == IMP_G_CUBIC) return launch_cubic_run(g, d_jobs, one, st);
     if (g.variant == 2 && g.kind == IMP_G_BLUR) {
         const ImpJob dummy{};
         const ImpJob& o = one ? *one : dummy;
