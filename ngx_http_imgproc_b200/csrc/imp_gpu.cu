@@ -201,6 +201,10 @@ int encode_job_tmap(const ImpPass& h, ImpJob& j) {
 }
 
 int pick_variant(const ImpPass& h, const ImpJob& j) {
+    // IMP_GPU_FORCE_DIRECT=1 routes everything through the general direct-from-global kernels (used by the tests to keep
+    // the fallback paths — unaligned pitches, oversized footprints, large sigma — covered on the GPU).
+    static const bool force_direct = [] { const char* e = getenv("IMP_GPU_FORCE_DIRECT"); return e && *e == '1'; }();
+    if (force_direct) return 0;
     if (h.kind == IMP_G_CUBIC) return 3;                             // column-run kernel: no alignment requirements
     if (h.tile_smem <= 0 || !encode_tiled()) return 0;
     if (j.src_pitch % 16) return 0;

@@ -284,3 +284,39 @@ def test_perceived_brightness_reduction(gpu, orc):
         if abs(ref * 100 - round(ref * 100)) < 0.49:
             assert round(got * 100) == round(ref * 100)
     assert abs(gpu.brightness(np.array([[[0,0,0],[255,255,255],[10,128,250],[200,30,180]],[[37,201,99],[128,128,128],[255,0,170],[3,2,1]]], np.uint8)) - 0.45781034) < 1e-6   # App. B
+
+
+def test_direct_fallback_kernels_subprocess(orc):
+    """The general direct-from-global kernels (taken for unaligned pitches, oversized footprints, sigma > 4) stay
+    parity-green: the same request matrix in a child process with IMP_GPU_FORCE_DIRECT=1."""
+    import os, subprocess, sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import ngx_http_imgproc_b200 as M
+from ngx_http_imgproc_b200 import api
+from oracle import oracle as O
+from conftest import rnd_image, smooth_image
+from test_planner_host import REQS, _oracle
+from test_gpu_parity import _gpu_run, _assert_same, _has_vignette
+L = M.library(); L.init(0)
+wm = rnd_image(7, 12, 20, 4)
+kw = dict(allow_experiments=True, max_filters=8, watermark=wm, wm_gravity_x="r", wm_gravity_y="b", wm_offset_x=3, wm_offset_y=2, wm_opacity=60)
+n = 0
+for (h, w, c) in [(60, 80, 3), (45, 64, 4), (33, 47, 1)]:
+    img = smooth_image(h, h, w, c)
+    for rq in REQS + [dict(resize="20,15"), dict(resize="27,31"), dict(filters=["blur=2.3", "rotate=90"]), dict(filters=["blur=6"])]:
+        code, step, out = _gpu_run(L, img, kw, rq)
+        c2, s2, o2 = _oracle(O, img, rq, kw)
+        assert code == c2, rq
+        if not code:
+            _assert_same(out, o2, rq, _has_vignette(rq))
+        n += 1
+img = rnd_image(1, 540, 960, 3)
+for rq in (dict(resize="320,180"), dict(resize="213,120"), dict(resize="1500,900,up"), dict(filters=["blur=2.3"])):
+    _assert_same(_gpu_run(L, img, dict(max_w=0, max_h=0), rq)[2], _oracle(O, img, rq, dict(max_w=0, max_h=0))[2], rq, False)
+print("DIRECT_OK", n)
+"""
+    env = dict(os.environ, IMP_GPU_FORCE_DIRECT="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert "DIRECT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
