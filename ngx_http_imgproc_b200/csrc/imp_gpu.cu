@@ -222,7 +222,10 @@ int blur_smem_bytes(const ImpPass& h) {
 int variant_param(const ImpPass& h, int variant);
 int variant_smem(const ImpPass& h, int variant, int param);
 int variant_tiles(const ImpPass& h, int variant);
-int tile_stage_bytes(const ImpPass& h) { return (h.tile_smem + 127) & ~127; }
+int tile_stage_bytes(const ImpPass& h) {
+    const int extra = h.kind == IMP_G_AREA_FRAC ? (((h.tile_ytaps * 8 + 15) & ~15) + 64) : 0;     // staged y taps + ranges
+    return (h.tile_smem + extra + 127) & ~127;
+}
 // three ring stages while three CTAs still fit an SM's shared memory, else two
 // Ring depth: as many stages as fit ~64 KB (so three CTAs still share an SM), between 2 and 8. Small tiles
 // (cfg1: 7 KB) need the depth to keep enough bytes in flight; big ones (cfg2: 23 KB) are fine with 2.

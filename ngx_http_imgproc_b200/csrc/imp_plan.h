@@ -76,7 +76,8 @@ struct ImpPass {
     int max_xtaps, max_ytaps; // AREA_FRAC: largest tap count per output column / row
     int tile_rs, tile_rows;   // tile kernels: shared-memory row stride (bytes) and max source rows per 32x8 tile
     int tile_smem;            // tile kernels: source-tile bytes (tile_rs*tile_rows); 0 = no tile variant for this pass
-    int xtile_off, ytile_off; // tile kernels: int2 per tile column {first px, last px}; int2 per tile row {first src row, rows}
+    int xtile_off, ytile_off; // tile kernels: int2 per tile column {first px, last px}; int4 per tile row {first src row, rows, first y tap, y taps}
+    int tile_ytaps;           // strip kernel: y-tap entries staged per tile (max over tiles, incl. alignment slack)
     int nops;
     int ops_off;              // ImpOp[nops]
     int lut_off, lut_bytes;   // LUT area (gamma 256 B each, gradmap 768 B each)

@@ -184,7 +184,7 @@ struct Lower {
         hdr.lut_bytes = (int)luts.size();
         hdr.out = out;
         hdr.dc = hdr.oc;
-        while (bb.b.size() % 16) bb.b.push_back(0);
+        bb.b.resize(((bb.b.size() + 15) & ~size_t(15)) + 64, 0);     // tail slack: the strip kernels' 16/64-byte table copies may over-read
         hdr.blob_bytes = (int)bb.b.size();
         memcpy(bb.b.data(), &hdr, sizeof hdr);
         ImpHostPass hp;
@@ -528,12 +528,16 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
                     xtile.push_back(p0); xtile.push_back(p1);
                     span = std::max(span, p1 - p0 + 1);
                 }
+                int ytaps = 0;
                 for (int y0 = 0; y0 < rh; y0 += 8) {
                     int y1 = std::min(y0 + 8, rh) - 1;
                     int p0 = yt[yr[y0].first].si, p1 = yt[yr[y1].first + yr[y1].count - 1].si;
-                    ytile.push_back(p0); ytile.push_back(p1 - p0 + 1);
+                    int t0 = yr[y0].first, tn = yr[y1].first + yr[y1].count - t0;
+                    ytile.push_back(p0); ytile.push_back(p1 - p0 + 1); ytile.push_back(t0); ytile.push_back(tn);   // int4 per tile row
                     rows = std::max(rows, p1 - p0 + 1);
+                    ytaps = std::max(ytaps, tn + 2);           // +1 for the even alignment of the first tap, +1 for the 16-byte rounding
                 }
+                P.tile_ytaps = ytaps;
                 P.xtile_off = L.bb.add(xtile.data(), xtile.size() * 4);
                 P.ytile_off = L.bb.add(ytile.data(), ytile.size() * 4);
                 // TMA box: tile_rs bytes x rows; +2 px for the zero-weight padded taps of narrower columns, +15 for the

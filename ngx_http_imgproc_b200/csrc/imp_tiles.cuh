@@ -77,13 +77,13 @@ constexpr int MAX_SMEM = 96 * 1024;     // source-tile budget per CTA
 // leaves a running float sum bit-identical, so the result equals OpenCV's ordered accumulation.
 // (A padded tap may read a byte past the staged pixels; any byte converts to a finite float.)
 template <int SC, int NT>
-__device__ __forceinline__ void area_rows(const uint8_t* __restrict__ col0, int rs, int py0, const ImpAreaTap* __restrict__ yt, int yfirst, int ycount,
+__device__ __forceinline__ void area_rows(const uint8_t* __restrict__ col0, int rs, int py0, const ImpAreaTap* yt /* shared memory */, int ycount,
                                           const float (&a)[NT], const float (&na)[NT], float (&sum)[SC]) {
-    // the y taps of an output row are consecutive source rows: only the first index is looked up, and the
-    // weight of row j is not needed until that row's horizontal sum is done (its load latency hides there)
-    const uint8_t* row = col0 + (size_t)(__ldg(reinterpret_cast<const int*>(yt + yfirst)) - py0) * rs;
+    // the y taps of an output row are consecutive source rows: only the first index is looked up; the taps of the
+    // tile were staged next to the pixels by the producer, so this loop touches no global memory at all
+    const uint8_t* row = col0 + (size_t)(yt[0].si - py0) * rs;
     for (int j = 0; j < ycount; j++, row += rs) {
-        const float beta = __ldg(reinterpret_cast<const float*>(yt + yfirst + j) + 1);
+        const float beta = yt[j].a;
         float h[SC];
         uint32_t seg[SC == 4 ? 1 : (NT * SC + 3) / 4];
         if (SC != 4) load_bytes<(SC == 4 ? 4 : NT * SC)>(row, seg);
@@ -190,10 +190,7 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
                                                    const uint8_t* s_ops, int nops, int bx0, int col_off, int tiles_y, int NSTAGE) {
     const ImpRange* __restrict__ xr = reinterpret_cast<const ImpRange*>(blob + P->xofs_off);
     const ImpAreaTap* __restrict__ xt = reinterpret_cast<const ImpAreaTap*>(blob + P->xcoef_off);
-    const ImpRange* __restrict__ yr = reinterpret_cast<const ImpRange*>(blob + P->yofs_off);
-    const ImpAreaTap* __restrict__ yt = reinterpret_cast<const ImpAreaTap*>(blob + P->ycoef_off);
-    const int2* __restrict__ ytile = reinterpret_cast<const int2*>(blob + P->ytile_off);
-    const int bw = P->bw, bh = P->bh, rs = P->tile_rs, oc = P->oc;
+    const int bw = P->bw, bh = P->bh, rs = P->tile_rs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool in_x = bx0 + lane < bw;
     const int bx = min(bx0 + lane, bw - 1);
@@ -210,17 +207,23 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
     const float box_scale = P->area_scale;
     const int my_off = col_off + __ldg(reinterpret_cast<const int*>(xt + rxv.x)) * SC;    // byte offset of my first tap in a tile row
 
+    const int box_bytes = rs * P->tile_rows;
+    const int ytap_bytes = (P->tile_ytaps * 8 + 15) & ~15;
     int stage = 0, phase = 0;
     for (int t = 0; t < tiles_y; t++) {
         const int by = min(t * TH + warp, bh - 1);
         const bool in_y = t * TH + warp < bh;
-        const int2 ryv = __ldg(reinterpret_cast<const int2*>(yr + by));
-        const int py0 = __ldg(ytile + t).x;
         mbar_wait(full + stage, phase);
+        const uint8_t* sbase = tile0 + stage * stage_bytes;
+        const ImpAreaTap* s_yt = reinterpret_cast<const ImpAreaTap*>(sbase + box_bytes);              // taps [tapbase ..) of this tile
+        const int2* s_yr = reinterpret_cast<const int2*>(sbase + box_bytes + ytap_bytes);          // ranges of the tile's 8 output rows
+        const int tap_first = s_yr[0].x, tapbase = tap_first & ~1;
+        const int2 ryv = s_yr[by - t * TH];
+        const int py0 = s_yt[tap_first - tapbase].si;                                              // first source row of the tile
         int v[SC];
         if (MODE == 0) {
             float sum[SC];
-            area_rows<SC, (MODE == 0 ? NT : 1)>(tile0 + stage * stage_bytes + my_off, rs, py0, yt, ryv.x, ryv.y, a, na, sum);
+            area_rows<SC, (MODE == 0 ? NT : 1)>(sbase + my_off, rs, py0, s_yt + (ryv.x - tapbase), ryv.y, a, na, sum);
 #pragma unroll
             for (int c = 0; c < SC; c++) v[c] = min(rint_pos(sum[c]), 255);          // sums are >= 0
         } else {
@@ -299,7 +302,9 @@ imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
     uint8_t* s_ops = smem + 128;                                      // up to 8 stages: 16 mbarriers
     uint8_t* tile0 = s_ops + ((ops_bytes + 127) & ~127);              // 128-byte aligned
     const int rs = P->tile_rs;
-    const int stage_bytes = (rs * P->tile_rows + 127) & ~127;
+    // stage = [pixel box][y taps of the tile][y ranges of its 8 output rows] (the last two only in fractional mode)
+    const int ytap_bytes = (MODE == 0) ? ((P->tile_ytaps * 8 + 15) & ~15) : 0;
+    const int stage_bytes = (rs * P->tile_rows + ytap_bytes + (MODE == 0 ? 64 : 0) + 127) & ~127;
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 1); mbar_init(empty + i, TH); }
@@ -318,14 +323,28 @@ imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
     if (tid >= STRIP_CONSUMERS) {
         // ---- TMA producer: one elected thread, one instruction per tile ----
         if (tid == STRIP_CONSUMERS) {
-            const int2* __restrict__ ytile = reinterpret_cast<const int2*>(blob + P->ytile_off);
+            const int4* __restrict__ ytile = reinterpret_cast<const int4*>(blob + P->ytile_off);
+            const uint8_t* __restrict__ g_yt = blob + P->ycoef_off;
+            const uint8_t* __restrict__ g_yr = blob + P->yofs_off;
             const uint32_t box_bytes = (uint32_t)(rs * P->tile_rows);
             int stage = 0, phase = 0;
             for (int t = 0; t < tiles_y; t++) {
-                const int py0 = __ldg(ytile + t).x;
+                const int4 yt4 = __ldg(ytile + t);                       // {first source row, rows, first y tap, y taps}
                 mbar_wait(empty + stage, phase ^ 1);
-                mbar_expect_tx(full + stage, box_bytes);
-                tma_load_2d(tile0 + stage * stage_bytes, jp->tmap, c0, py0, full + stage);
+                uint8_t* sdst = tile0 + stage * stage_bytes;
+                if (MODE == 0) {
+                    // the tile's y taps and row ranges ride along as two small bulk copies, so the consumers' inner
+                    // loops never leave shared memory
+                    const int tapbase = yt4.z & ~1;
+                    const uint32_t tapbytes = (uint32_t)(((yt4.w + (yt4.z & 1)) * 8 + 15) & ~15);
+                    mbar_expect_tx(full + stage, box_bytes + tapbytes + 64u);
+                    tma_load_2d(sdst, jp->tmap, c0, yt4.x, full + stage);
+                    bulk_g2s(sdst + box_bytes, g_yt + (size_t)tapbase * 8, tapbytes, full + stage);
+                    bulk_g2s(sdst + box_bytes + ytap_bytes, g_yr + (size_t)t * TH * 8, 64u, full + stage);
+                } else {
+                    mbar_expect_tx(full + stage, box_bytes);
+                    tma_load_2d(sdst, jp->tmap, c0, yt4.x, full + stage);
+                }
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
         }
