@@ -60,6 +60,11 @@ extern "C" {
 
 /* The decoded watermark as PrepareWatermark leaves it in the conf pool (RecoverInfo, required.h:101-108,
  * bridge.c:221-234) plus its placement (Position, required.h:86-91) and opacity (module.c directive). */
+/* ---- encoder-side pixel prep folded into the final store (advancedio.c:65-101) ------ */
+#define IMP_PACK_NONE 0          /* rows top-down, channel count of the chain (what cvEncodeImage wants) */
+#define IMP_PACK_FI24 24         /* IplToFI24: rows bottom-up, 3 bytes per pixel (alpha dropped) */
+#define IMP_PACK_FI32 32         /* IplToFI32: rows bottom-up, 4 bytes per pixel (alpha 255 when the frame has none) */
+
 typedef struct imp_gpu_watermark {
     const unsigned char* pixels;   /* RecoverInfo.Pointer: 8-bit B,G,R[,A] interleaved, host memory */
     int  width, height;            /* RecoverInfo.Size */
@@ -90,6 +95,7 @@ typedef struct imp_gpu_request {
     int                simple_resize; /* 1 when the encoder is GIF -> INTER_NN (bridge.c:594) */
     int                flatten;       /* 1 when the encoder has no alpha -> BlendWithPaper (bridge.c:642-656) */
     int                interp;        /* IMP_INTERP_* */
+    int                pack;          /* IMP_PACK_*: encoder-side layout of the result */
 } imp_gpu_request;
 
 typedef struct imp_gpu_plan  imp_gpu_plan;    /* validated, lowered, device-resident job recipe */
@@ -158,6 +164,14 @@ int  imp_gpu_farm_run_host(int n, imp_gpu_plan* const* plans, const unsigned cha
  * order; the device sums in double, so values agree to ~1e-5 relative and the JSON integer is compared in the tests. */
 int  imp_gpu_brightness_device(const void* d_img, int pitch, int width, int height, int channels, float* brightness, void* stream);
 int  imp_gpu_brightness_host(const unsigned char* img, int step, int width, int height, int channels, float* brightness);
+
+/* ---- ASCII (filters.c:486-522, format=text) on the device -------------------------------------------- */
+/* `args` as the reference takes it ("wide" selects the 70-level ramp, anything else the 10-level one). Writes
+ * (width+1)*height-1 bytes: one character per pixel, rows separated by '\n'. The frame itself is not modified (the
+ * reference converts it to HSV in place, filters.c:504, which nothing reads afterwards). */
+long imp_gpu_ascii_length(int width, int height);
+int  imp_gpu_ascii_host(const unsigned char* img, int step, int width, int height, int channels, const char* args,
+                        unsigned char* out, long out_cap);
 
 /* ---- memory helpers so a C host needs no CUDA headers --------------------------------------------- */
 int  imp_gpu_malloc(void** d_ptr, size_t bytes);

@@ -40,7 +40,7 @@ class CConfig(C.Structure):
 class CRequest(C.Structure):
     _fields_ = [("crop", C.c_char_p), ("gravity", C.c_char_p), ("resize", C.c_char_p),
                 ("filters", C.POINTER(C.c_char_p)), ("filter_count", C.c_int),
-                ("simple_resize", C.c_int), ("flatten", C.c_int), ("interp", C.c_int)]
+                ("simple_resize", C.c_int), ("flatten", C.c_int), ("interp", C.c_int), ("pack", C.c_int)]
 
 
 @dataclass
@@ -70,12 +70,12 @@ class Config:
         return c, keep
 
 
-def make_request(crop=None, gravity=None, resize=None, filters: Sequence[str] = (), simple=False, flatten=False, interp=0):
+def make_request(crop=None, gravity=None, resize=None, filters: Sequence[str] = (), simple=False, flatten=False, interp=0, pack=0):
     keep = []
     enc = lambda s: None if s is None else s.encode("latin-1")
     arr = (C.c_char_p * max(1, len(filters)))(*[enc(f) for f in filters])
     keep.append(arr)
-    r = CRequest(enc(crop), enc(gravity), enc(resize), arr, len(filters), 1 if simple else 0, 1 if flatten else 0, interp)
+    r = CRequest(enc(crop), enc(gravity), enc(resize), arr, len(filters), 1 if simple else 0, 1 if flatten else 0, interp, pack)
     keep.append(r)
     return r, keep
 
@@ -152,6 +152,16 @@ class Library:
 
     def launch_count(self) -> int:
         return int(self.lib.imp_gpu_launch_count())
+
+    def ascii(self, img: np.ndarray, args: str = "") -> bytes:
+        """ASCII (filters.c:486-522) of a host frame."""
+        img = np.ascontiguousarray(img if img.ndim == 3 else img[:, :, None], dtype=np.uint8)
+        self.lib.imp_gpu_ascii_length.restype = C.c_long
+        n = self.lib.imp_gpu_ascii_length(img.shape[1], img.shape[0])
+        out = C.create_string_buffer(n + 1)
+        self.lib.imp_gpu_ascii_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_long]
+        self.check(self.lib.imp_gpu_ascii_host(img.ctypes.data, img.strides[0], img.shape[1], img.shape[0], img.shape[2], args.encode(), out, n))
+        return out.raw[:n]
 
     def brightness(self, img: np.ndarray) -> float:
         """CalcPerceivedBrightness (filters.c:707-729) of a host frame, reduced on the device."""

@@ -5,6 +5,7 @@
 #include "imp_internal.h"
 #include <cuda.h>
 #include <stdio.h>
+#include <math.h>
 #include <string.h>
 #include <stdlib.h>
 #include <algorithm>
@@ -662,6 +663,38 @@ int imp_gpu_brightness_host(const unsigned char* img, int step, int w, int h, in
     rc = imp_gpu_brightness_device(d, pitch, w, h, c, brightness, st);
     cudaFreeAsync(d, st);
     return rc;
+}
+
+// ---- "next" row §8f-4: ASCII (format=text) ---------------------------------------------------------------------
+// Density ramps of filters.c:486-487 (the reference's data; the classic 70- and 10-level ASCII-art ramps).
+static const char kAsciiWide[] = "$@B%8&WM#*oahkbdpqwmZO0QLCJUYXzcvunxrjft/\\|()1{}[]?-_+~<>i!lI;:,\"^`'. ";
+static const char kAsciiNarrow[] = "@%8#*+=-:. ";
+
+long imp_gpu_ascii_length(int width, int height) { return (long)(width + 1) * height - 1; }
+
+int imp_gpu_ascii_host(const unsigned char* img, int step, int w, int h, int c, const char* args, unsigned char* out, long out_cap) {
+    int rc = bind(); if (rc) return rc;
+    if (!img || !out || w <= 0 || h <= 0 || (c != 1 && c != 3 && c != 4)) return IMP_ERROR_INVALID_ARGS;
+    const long len = imp_gpu_ascii_length(w, h);
+    if (out_cap < len) return IMP_ERROR_INVALID_ARGS;
+    const char* table = (args && strcmp(args, "wide") == 0) ? kAsciiWide : kAsciiNarrow;     // filters.c:490-494
+    const int tablelen = (int)strlen(table);
+    const float factor = 256.0 / tablelen;                                                   // filters.c:496
+    unsigned char lut[256];
+    for (int v = 0; v < 256; v++) lut[v] = (unsigned char)table[(int)floor((double)((float)v / factor))];   // filters.c:509
+    cudaStream_t st = g_dev[t_dev].stream;
+    const int pitch = align16(w * c);
+    uint8_t *d_img = nullptr, *d_lut = nullptr, *d_out = nullptr;
+    CK(cudaMallocAsync((void**)&d_img, (size_t)pitch * h, st));
+    CK(cudaMallocAsync((void**)&d_lut, 256, st));
+    CK(cudaMallocAsync((void**)&d_out, (size_t)len + 1, st));
+    CK(cudaMemcpy2DAsync(d_img, pitch, img, step, (size_t)w * c, h, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, st));
+    CK(imp_launch_ascii(d_img, pitch, w, h, c, d_lut, d_out, st));
+    CK(cudaMemcpyAsync(out, d_out, (size_t)len, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFreeAsync(d_img, st); cudaFreeAsync(d_lut, st); cudaFreeAsync(d_out, st);
+    return IMP_OK;
 }
 
 // ---- memory helpers ------------------------------------------------------------------------------------

@@ -79,6 +79,26 @@ cudaError_t imp_launch_brightness(const uint8_t* d_img, int pitch, int w, int h,
     return cudaGetLastError();
 }
 
+// ASCII (filters.c:486-522, `format=text`): one character per pixel from the HSV value V = max(B,G,R) through a 256-entry
+// table the host derives with the reference's float maths; rows are separated by '\n' (no trailing newline).
+__global__ void __launch_bounds__(256) imp_ascii_kernel(const uint8_t* __restrict__ img, int pitch, int w, int h, int c,
+                                                        const uint8_t* __restrict__ lut, uint8_t* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x > w || y >= h) return;
+    uint8_t* o = out + (size_t)y * (w + 1) + x;
+    if (x == w) { if (y + 1 < h) *o = '\n'; return; }
+    const uint8_t* p = img + (size_t)y * pitch + (size_t)x * c;
+    const int v = c == 1 ? p[0] : max(p[0], max(p[1], p[2]));
+    *o = __ldg(lut + v);
+}
+
+cudaError_t imp_launch_ascii(const uint8_t* d_img, int pitch, int w, int h, int c, const uint8_t* d_lut, uint8_t* d_out, cudaStream_t st) {
+    dim3 grid((w + 1 + 255) / 256, h);
+    imp_ascii_kernel<<<grid, 256, 0, st>>>(d_img, pitch, w, h, c, d_lut, d_out);
+    g_imp_launches++;
+    return cudaGetLastError();
+}
+
 namespace {
 
 constexpr int TILE_W = 32, TILE_H = 8;
@@ -160,7 +180,7 @@ imp_pass_kernel(const ImpJob* __restrict__ jobs, int first, int count, const Imp
     promote<SC>(v, p);
     const int oc = P->oc;
     imp_run_ops(p, oc, bx, by, os.ops, P->nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
-    if (oc == 4) store_px<4>(job, P, bx, by, p); else store_px<3>(job, P, bx, by, p);
+    if (P->dc == 4) store_px<4>(job, P, bx, by, p); else store_px<3>(job, P, bx, by, p);
 }
 
 // ---- INTER_CUBIC with the horizontal pass shared down a column run ------------------------------------------------
@@ -198,7 +218,7 @@ imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
     ImpSrcGlobal<SC> S;
     S.base = job.src + (size_t)P->sy0 * job.src_pitch + (size_t)P->sx0 * SC;
     S.pitch = job.src_pitch;
-    const int sw = P->sw, sh = P->sh, oc = P->oc, nops = P->nops, simd_end = P->simd_end;
+    const int sw = P->sw, sh = P->sh, oc = P->oc, dc = P->dc, nops = P->nops, simd_end = P->simd_end;
     const int* __restrict__ xofs = reinterpret_cast<const int*>(blob + P->xofs_off);
     const short* __restrict__ xa = reinterpret_cast<const short*>(blob + P->xcoef_off);
     const int* __restrict__ yofs = reinterpret_cast<const int*>(blob + P->yofs_off);
@@ -250,7 +270,7 @@ imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
         ImpPx p;
         promote<SC>(v, p);
         if (nops) imp_run_ops(p, oc, bx, by, os.ops, nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
-        if (oc == 4) store_px<4>(job, P, bx, by, p); else store_px<3>(job, P, bx, by, p);
+        if (P->dc == 4) store_px<4>(job, P, bx, by, p); else store_px<3>(job, P, bx, by, p);
     }
 }
 
@@ -303,7 +323,7 @@ __global__ void __launch_bounds__(256) imp_blur_v_kernel(const ImpJob job, const
     promote<SC>(v, p);
     const int oc = P->oc;
     imp_run_ops(p, oc, x, y, os.ops, P->nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
-    if (oc == 4) store_px<4>(job, P, x, y, p); else store_px<3>(job, P, x, y, p);
+    if (P->dc == 4) store_px<4>(job, P, x, y, p); else store_px<3>(job, P, x, y, p);
 }
 
 template <int KIND>

@@ -63,7 +63,7 @@ void to_request(const Pending& p, Built& b) {
     b.req.resize = p.has_resize ? p.resize.c_str() : nullptr;
     b.req.filters = b.fp.empty() ? nullptr : b.fp.data();
     b.req.filter_count = (int)b.fp.size();
-    b.req.simple_resize = p.simple; b.req.flatten = p.flatten; b.req.interp = IMP_INTERP_REFERENCE;
+    b.req.simple_resize = p.simple; b.req.flatten = p.flatten; b.req.interp = IMP_INTERP_REFERENCE; b.req.pack = IMP_PACK_NONE;
     b.cfg.max_target_w = p.max_w; b.cfg.max_target_h = p.max_h;
     b.cfg.max_filters = 1 << 20;                         // RunJob enforces the count while parsing (bridge.c:361)
     b.cfg.allow_experiments = p.allow;

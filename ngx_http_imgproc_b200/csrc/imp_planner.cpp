@@ -172,6 +172,7 @@ struct Lower {
         hdr.sc = in_c_;
     }
     int add_lut(const uint8_t* p, int n) { int off = (int)luts.size(); luts.insert(luts.end(), p, p + n); return off; }
+    int final_dc = 0;              // destination channels of the LAST pass when the encoder-side packing changes them
     void end_pass(const ImpFrameMap& out, int out_w, int out_h) {
         hdr.nops = (int)ops.size();
         while (luts.size() % 16) luts.push_back(0);
@@ -183,14 +184,14 @@ struct Lower {
         hdr.lut_off = hdr.ops_off + (int)(ops.size() * sizeof(ImpOp));
         hdr.lut_bytes = (int)luts.size();
         hdr.out = out;
-        hdr.dc = hdr.oc;
+        hdr.dc = final_dc ? final_dc : hdr.oc;
         bb.b.resize(((bb.b.size() + 15) & ~size_t(15)) + 64, 0);     // tail slack: the strip kernels' 16/64-byte table copies may over-read
         hdr.blob_bytes = (int)bb.b.size();
         memcpy(bb.b.data(), &hdr, sizeof hdr);
         ImpHostPass hp;
         hp.hdr = hdr; hp.blob = bb.b;
         hp.in_w = in_w; hp.in_h = in_h; hp.in_c = in_c;
-        hp.out_w = out_w; hp.out_h = out_h; hp.out_c = hdr.oc;
+        hp.out_w = out_w; hp.out_h = out_h; hp.out_c = hdr.dc;
         hp.uses_watermark = uses_wm; hp.sigma = sigma;
         plan->passes.push_back(std::move(hp));
     }
@@ -617,8 +618,16 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
     if ((int)L.ops.size() > IMP_MAX_OPS) return IMP_ERROR_TOO_MUCH_FILTERS;
 
     *step = IMP_STEP_ENCODE;
+    // encoder-side pixel prep (advancedio.c:65-101 IplToFI32 / IplToFI24): FreeImage bitmaps are bottom-up, 32-bit ones
+    // get alpha 255 when the frame has none, 24-bit ones drop the alpha. A final vertical flip of the store map plus a
+    // destination channel count; no extra pass.
+    if (req->pack != IMP_PACK_NONE && req->pack != IMP_PACK_FI24 && req->pack != IMP_PACK_FI32) return IMP_ERROR_INVALID_ARGS;
+    if (req->pack != IMP_PACK_NONE) {
+        L.fr.flip_v();
+        L.final_dc = req->pack == IMP_PACK_FI32 ? 4 : 3;
+    }
     L.end_pass(L.fr.map(), L.fr.w, L.fr.h);
-    plan->out_w = L.fr.w; plan->out_h = L.fr.h; plan->out_c = L.fr.c;
+    plan->out_w = L.fr.w; plan->out_h = L.fr.h; plan->out_c = L.final_dc ? L.final_dc : L.fr.c;
     plan->algo_bytes = (unsigned long long)cw * ch * c + (unsigned long long)plan->out_w * plan->out_h * plan->out_c + wm_bytes;
     return IMP_OK;
 }

@@ -179,8 +179,9 @@ __device__ __forceinline__ void strip_epilogue(const ImpJob& job, const ImpPass*
     if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
     int X, Y;
     imp_map_xy(P->out, bx, by, X, Y);
-    uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * oc;
-    if (oc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
+    const int dc = P->dc;
+    uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * dc;
+    if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
     else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
 }
 
@@ -245,7 +246,7 @@ template <int SC, int NT>
 __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* tile0, int stage_bytes,
                                                        uint64_t* full, uint64_t* empty, const uint8_t* s_ops, int nops, int bx0, int col_off,
                                                        int tiles_y, int NSTAGE) {
-    const int bw = P->bw, bh = P->bh, rs = P->tile_rs, oc = P->oc, ny = P->ny;
+    const int bw = P->bw, bh = P->bh, rs = P->tile_rs, oc = P->oc, dc = P->dc, ny = P->ny;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool in_x = bx0 + lane < bw;
     const int bx = min(bx0 + lane, bw - 1);
@@ -271,8 +272,8 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
             if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
             int X, Y;
             imp_map_xy(om, bx, by, X, Y);
-            uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * oc;
-            if (oc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
+            uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * dc;
+            if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
             else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
         }
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -499,7 +500,7 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
     // op list + store. With a transposing output map the lane runs along the tile's y so that consecutive lanes still
     // write consecutive destination pixels.
     const ImpFrameMap om = P->out;
-    const int oc = P->oc;
+    const int oc = P->oc, dc = P->dc;
     const int lane = tid & 31, wrp = tid >> 5;
     for (int it = 0; it < BT / 8; it++) {
         const int u = wrp + it * 8;
@@ -512,8 +513,8 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
         if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
         int X, Y;
         imp_map_xy(om, bx, by, X, Y);
-        uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * oc;
-        if (oc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
+        uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * dc;
+        if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
         else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
     }
 }

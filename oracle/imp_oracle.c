@@ -351,6 +351,27 @@ float orc_perceived_brightness(const orc_img* im) {
     return sum / (im->width * im->height) / 255.0;
 }
 
+/* filters.c:486-522 ASCII: density = floor(V / factor), V = max(B,G,R) (RGB2HSV's value), factor = 256.0/len as float. */
+long orc_ascii(const orc_img* im, int wide, unsigned char* out) {
+    static const char w70[] = "$@B%8&WM#*oahkbdpqwmZO0QLCJUYXzcvunxrjft/\\|()1{}[]?-_+~<>i!lI;:,\"^`'. ";
+    static const char n10[] = "@%8#*+=-:. ";
+    const char* table = wide ? w70 : n10;
+    int tablelen = (int)strlen(table);
+    float factor = 256.0 / tablelen;
+    int width = im->width, height = im->height;
+    for (int y = 0; y < height; y++) {
+        long rowoffset = (long)y * (width + 1);
+        for (int x = 0; x < width; x++) {
+            const unsigned char* p = &PX(im, x, y, 0);
+            int v = im->channels == 1 ? p[0] : (p[0] > p[1] ? (p[0] > p[2] ? p[0] : p[2]) : (p[1] > p[2] ? p[1] : p[2]));
+            int density = (int)floor(v / factor);
+            out[rowoffset + x] = (unsigned char)table[density];
+        }
+        if (rowoffset > 0) out[rowoffset - 1] = '\n';
+    }
+    return (long)(width + 1) * height - 1;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* 2. OpenCV ops the reference calls (pinned against cv2 4.13 IPP-off)        */
 /* ------------------------------------------------------------------------------------------ */

@@ -131,6 +131,15 @@ class _Orc:
         v = _view(np.ascontiguousarray(img))
         return float(self.lib.orc_perceived_brightness(C.byref(v)))
 
+    def ascii(self, img, wide=False) -> bytes:
+        a = np.ascontiguousarray(img)
+        v = _view(a)
+        n = (a.shape[1] + 1) * a.shape[0] - 1
+        out = C.create_string_buffer(n + 1)
+        self.lib.orc_ascii.restype = C.c_long
+        self.lib.orc_ascii(C.byref(v), 1 if wide else 0, out)
+        return out.raw[:n]
+
     def vignette_mask(self, x, y, w, h, power, radius):
         return float(self.lib.orc_vignette_mask(x, y, w, h, C.c_float(power), C.c_float(radius)))
 
@@ -439,10 +448,23 @@ def apply_filter(img: np.ndarray, request: str, allow_experiments: bool):
     return IMP_ERROR_NO_SUCH_FILTER, img
 
 
+def fi_pack(img: np.ndarray, bits: int) -> np.ndarray:
+    """advancedio.c:65-101 IplToFI32 / IplToFI24: bottom-up rows; 32-bit gets alpha 255 when the frame has none,
+    24-bit keeps the first three channels."""
+    img = np.ascontiguousarray(img)[::-1]
+    if bits == 32:
+        if img.shape[2] == 4:
+            return np.ascontiguousarray(img)
+        out = np.full(img.shape[:2] + (4,), 255, np.uint8)
+        out[:, :, :3] = img[:, :, :3]
+        return out
+    return np.ascontiguousarray(img[:, :, :3])
+
+
 def run_chain(img: np.ndarray, crop: Optional[str] = None, gravity: Optional[str] = None,
               resize: Optional[str] = None, filters: Optional[List[str]] = None,
               cfg: Optional[OracleConfig] = None, simple: bool = False, flatten: bool = False,
-              linear: bool = False):
+              linear: bool = False, pack: int = 0):
     """RunJob steps 3-7 (bridge.c:574-656) on one decoded frame. Returns (code, step, image).
     `linear=True` is the shim-level INTER_LINEAR extension (not a reference call site)."""
     o = orc()
@@ -476,6 +498,8 @@ def run_chain(img: np.ndarray, crop: Optional[str] = None, gravity: Optional[str
         img = o.alpha_over(img, org[0], org[1], wm, float(np.float32(cfg.wm_opacity / 100.0)))
     if flatten and img.shape[2] == 4:
         img = o.paper(img)
+    if pack:
+        img = fi_pack(img, pack)
     return IMP_OK, STEP_ENCODE, img
 
 
@@ -750,6 +774,20 @@ class Ref:
         L.AlphaBlendOver(d, s, C.c_float(opacity))
         out = cls.to_numpy(d)
         cls.release(d); cls.release(s)
+        return out
+
+    @classmethod
+    def ascii(cls, img, args: str = "") -> bytes:
+        """The reference's ASCII (filters.c:486-522); it converts its copy of the frame to HSV in place."""
+        class _Memory(C.Structure):
+            _fields_ = [("Buffer", C.c_void_p), ("Length", C.c_long), ("Error", C.c_int)]
+        L = cls.lib()
+        L.ASCII.restype = _Memory
+        L.ASCII.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        p = cls.new_image(img)
+        m = L.ASCII(p, args.encode(), None)
+        out = C.string_at(m.Buffer, m.Length)
+        cls.release(p)
         return out
 
     @classmethod

@@ -320,3 +320,21 @@ print("DIRECT_OK", n)
     env = dict(os.environ, IMP_GPU_FORCE_DIRECT="1")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert "DIRECT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_ascii_and_encoder_packing(gpu, orc):
+    """IplToFI24/32 packing folded into the store, and ASCII on the device."""
+    o = orc.orc()
+    ramp = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(3, 2)
+    for img in (ramp, smooth_image(3, 37, 53, 3), smooth_image(4, 64, 96, 4), rnd_image(5, 1, 1, 3)):
+        for args, wide in (("wide", True), ("", False)):
+            assert gpu.ascii(img, args) == o.ascii(img, wide)
+    kw = dict(allow_experiments=True)
+    for c in (3, 4, 1):
+        img = smooth_image(20 + c, 90, 120, c)
+        for rq in (dict(resize="45,37", pack=24), dict(resize="45,37", pack=32), dict(filters=["rotate=90", "blur=1.2", "vignette=0.6"], pack=32),
+                   dict(crop="1,1", resize="200,200,up", filters=["flip=10"], pack=24, flatten=True)):
+            code, _, out = _gpu_run(gpu, img, kw, rq)
+            c2, _, ref = _oracle(orc, img, rq, kw)
+            assert code == c2 == 0
+            _assert_same(out, ref, rq, _has_vignette(rq))

@@ -219,3 +219,16 @@ def test_alpha_unit_identity():
     """(float)(a/255.0) == a/255.0f for every byte: the device uses one IEEE float division (imp_pixel.cuh)."""
     a = np.arange(256)
     assert np.array_equal((a / 255.0).astype(np.float32), a.astype(np.float32) / np.float32(255.0))
+
+
+def test_ascii_restatement_vs_compiled_reference(orc):
+    """the restated ASCII equals the reference's (both ramps)."""
+    if not _have_ref(orc):
+        pytest.skip("compiled reference not available on this box")
+    o = orc.orc()
+    for (h, w, c) in [(7, 13, 3), (20, 31, 4), (1, 5, 3)]:
+        img = rnd_image(h + w, h, w, c)
+        for args, wide in (("wide", True), ("", False), ("narrow", False)):
+            assert o.ascii(img, wide) == orc.Ref.ascii(img, args), (h, w, c, args)
+    ramp = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(3, 2)
+    assert o.ascii(ramp, True) == orc.Ref.ascii(ramp, "wide") and o.ascii(ramp, False) == orc.Ref.ascii(ramp, "x")
