@@ -173,6 +173,28 @@ long imp_gpu_ascii_length(int width, int height);
 int  imp_gpu_ascii_host(const unsigned char* img, int step, int width, int height, int channels, const char* args,
                         unsigned char* out, long out_cap);
 
+/* ---- GIF canvas expansion (advancedio.c:195-248, LoadGIF's per-pixel loop) on the device ------------- */
+/* A frame exactly as LoadGIF holds it after FreeImage_LockPage (+ConvertTo8Bits): 8-bit palette indices in FreeImage
+ * scanline order (bottom-up), FrameLeft/FrameTop, DisposalMethod, FreeImage_GetTransparentIndex, the RGBQUAD palette. */
+typedef struct imp_gpu_gif_frame {
+    const unsigned char* indices;      /* host memory, height rows of `pitch` bytes, row 0 = bottom scanline */
+    int pitch, width, height;
+    int left, top;
+    int dispose;                       /* advancedio.h:3-6: 0 unspecified, 1 leave, 2 background, 3 previous */
+    int transparency_key;              /* -1 when the frame has none */
+    const unsigned char* palette;      /* 256 x {B,G,R,reserved} */
+} imp_gpu_gif_frame;
+/* Expands n frames into n BGRA canvases of canvas_w x canvas_h laid out back to back on the device
+ * (frame f at d_canvases + f*canvas_pitch*canvas_h), ready to be fed to imp_gpu_batch_add. `destructive` as
+ * LoadGIF's isdestructive (replay disposal through the master index canvas). Uploads 1 byte per pixel.
+ * Two reference accidents are not reproduced: the off-by-one that reads one byte past a frame's row at
+ * x == left+width (advancedio.c:203), and palette[-1] for uncovered pixels of a frame without a transparency key
+ * (written as transparent black here). */
+int  imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
+                               void* d_canvases, int canvas_pitch, void* stream);
+int  imp_gpu_gif_expand_host(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
+                             unsigned char* const* canvases, int canvas_step);
+
 /* ---- memory helpers so a C host needs no CUDA headers --------------------------------------------- */
 int  imp_gpu_malloc(void** d_ptr, size_t bytes);
 int  imp_gpu_free(void* d_ptr);

@@ -32,6 +32,11 @@ class CWatermark(C.Structure):
                 ("offset_x", C.c_int), ("offset_y", C.c_int), ("opacity", C.c_int)]
 
 
+class CGifFrame(C.Structure):
+    _fields_ = [("indices", C.c_void_p), ("pitch", C.c_int), ("width", C.c_int), ("height", C.c_int), ("left", C.c_int), ("top", C.c_int),
+                ("dispose", C.c_int), ("transparency_key", C.c_int), ("palette", C.c_void_p)]
+
+
 class CConfig(C.Structure):
     _fields_ = [("max_target_w", C.c_uint), ("max_target_h", C.c_uint), ("max_filters", C.c_int),
                 ("allow_experiments", C.c_int), ("watermark", C.POINTER(CWatermark))]
@@ -162,6 +167,19 @@ class Library:
         self.lib.imp_gpu_ascii_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_long]
         self.check(self.lib.imp_gpu_ascii_host(img.ctypes.data, img.strides[0], img.shape[1], img.shape[0], img.shape[2], args.encode(), out, n))
         return out.raw[:n]
+
+    def gif_expand(self, frames, cw: int, ch: int, destructive: bool):
+        """LoadGIF's canvas expansion (advancedio.c:195-248) on the device; frames as dicts: indices (HxW uint8, bottom-up), left, top, dispose, key, palette (256x4)."""
+        keep, arr = [], (CGifFrame * len(frames))()
+        for i, f in enumerate(frames):
+            idx = np.ascontiguousarray(f["indices"], np.uint8); pal = np.ascontiguousarray(f["palette"], np.uint8)
+            keep += [idx, pal]
+            arr[i] = CGifFrame(idx.ctypes.data, idx.strides[0], idx.shape[1], idx.shape[0], f["left"], f["top"], f["dispose"], f["key"], pal.ctypes.data)
+        outs = [np.zeros((ch, cw, 4), np.uint8) for _ in frames]
+        ptrs = (C.c_void_p * len(frames))(*[o.ctypes.data for o in outs])
+        self.lib.imp_gpu_gif_expand_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        self.check(self.lib.imp_gpu_gif_expand_host(arr, len(frames), cw, ch, 1 if destructive else 0, ptrs, cw * 4))
+        return outs
 
     def brightness(self, img: np.ndarray) -> float:
         """CalcPerceivedBrightness (filters.c:707-729) of a host frame, reduced on the device."""

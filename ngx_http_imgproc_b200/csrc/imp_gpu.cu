@@ -697,6 +697,61 @@ int imp_gpu_ascii_host(const unsigned char* img, int step, int w, int h, int c, 
     return IMP_OK;
 }
 
+// ---- "next" row §8f-2: GIF canvas expansion ------------------------------------------------------------------
+int imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
+                              void* d_canvases, int canvas_pitch, void* stream) {
+    int rc = bind(); if (rc) return rc;
+    if (!frames || n <= 0 || canvas_w <= 0 || canvas_h <= 0 || !d_canvases || canvas_pitch < canvas_w * 4 || canvas_pitch % 4) return IMP_ERROR_INVALID_ARGS;
+    cudaStream_t st = pick_stream(stream);
+    // one staging buffer: [ImpGifFrame n][palettes n*1024][index planes]
+    size_t idx_bytes = 0;
+    for (int f = 0; f < n; f++) {
+        if (!frames[f].indices || !frames[f].palette || frames[f].width <= 0 || frames[f].height <= 0 || frames[f].pitch < frames[f].width) return IMP_ERROR_INVALID_ARGS;
+        idx_bytes += ((size_t)frames[f].pitch * frames[f].height + 15) & ~size_t(15);
+    }
+    const size_t meta_bytes = (((size_t)n * sizeof(ImpGifFrame)) + 15) & ~size_t(15), pal_bytes = (size_t)n * 1024;
+    const size_t total = meta_bytes + pal_bytes + idx_bytes;
+    uint8_t* h_buf = nullptr; uint8_t* d_buf = nullptr;
+    CK(cudaHostAlloc((void**)&h_buf, total, cudaHostAllocDefault));
+    cudaError_t e = cudaMallocAsync((void**)&d_buf, total, st);
+    if (e != cudaSuccess) { cudaFreeHost(h_buf); return fail(e, "cudaMallocAsync", __LINE__); }
+    ImpGifFrame* meta = reinterpret_cast<ImpGifFrame*>(h_buf);
+    size_t off = meta_bytes + pal_bytes;
+    for (int f = 0; f < n; f++) {
+        const imp_gpu_gif_frame& g = frames[f];
+        memcpy(h_buf + meta_bytes + (size_t)f * 1024, g.palette, 1024);
+        memcpy(h_buf + off, g.indices, (size_t)g.pitch * g.height);
+        meta[f].indices = d_buf + off; meta[f].palette = d_buf + meta_bytes + (size_t)f * 1024;
+        meta[f].pitch = g.pitch; meta[f].w = g.width; meta[f].h = g.height; meta[f].left = g.left; meta[f].top = g.top;
+        meta[f].dispose = g.dispose; meta[f].key = g.transparency_key; meta[f].pad_ = 0;
+        off += ((size_t)g.pitch * g.height + 15) & ~size_t(15);
+    }
+    e = cudaMemcpyAsync(d_buf, h_buf, total, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = imp_launch_gif_expand(reinterpret_cast<const ImpGifFrame*>(d_buf), n, canvas_w, canvas_h, destructive ? 1 : 0, (uint8_t*)d_canvases, canvas_pitch, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // h_buf / d_buf are released below
+    cudaFreeAsync(d_buf, st);
+    cudaFreeHost(h_buf);
+    if (e != cudaSuccess) return fail(e, "gif expand", __LINE__);
+    return IMP_OK;
+}
+
+int imp_gpu_gif_expand_host(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
+                            unsigned char* const* canvases, int canvas_step) {
+    int rc = bind(); if (rc) return rc;
+    if (!canvases || canvas_step < canvas_w * 4) return IMP_ERROR_INVALID_ARGS;
+    cudaStream_t st = g_dev[t_dev].stream;
+    const int pitch = align16(canvas_w * 4);
+    uint8_t* d = nullptr;
+    CK(cudaMalloc((void**)&d, (size_t)pitch * canvas_h * n));
+    rc = imp_gpu_gif_expand_device(frames, n, canvas_w, canvas_h, destructive, d, pitch, st);
+    for (int f = 0; f < n && rc == IMP_OK; f++) {
+        cudaError_t e = cudaMemcpy2D(canvases[f], canvas_step, d + (size_t)f * pitch * canvas_h, pitch, (size_t)canvas_w * 4, canvas_h, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(e, "cudaMemcpy2D", __LINE__);
+    }
+    cudaFree(d);
+    return rc;
+}
+
 // ---- memory helpers ------------------------------------------------------------------------------------
 int imp_gpu_malloc(void** p, size_t bytes) { int rc = bind(); if (rc) return rc; CK(cudaMalloc(p, bytes)); return IMP_OK; }
 int imp_gpu_free(void* p) { int rc = bind(); if (rc) return rc; CK(cudaFree(p)); return IMP_OK; }

@@ -99,3 +99,11 @@ struct ImpJob {
     // TMA engine fetches a whole tile (box = tile_rs bytes x tile_rows rows) with ONE instruction.
     alignas(64) unsigned char tmap[128];
 };
+
+// One GIF frame as the producer of the hot path sees it (advancedio.c:126-186): palette indices in FreeImage scanline
+// order (bottom-up), placement on the canvas, disposal and transparency key, palette as RGBQUAD (B,G,R,x).
+struct ImpGifFrame {
+    const uint8_t* indices;   // device pointer
+    const uint8_t* palette;   // device pointer, 256 * 4 bytes
+    int pitch, w, h, left, top, dispose, key, pad_;
+};

@@ -372,6 +372,37 @@ long orc_ascii(const orc_img* im, int wide, unsigned char* out) {
     return (long)(width + 1) * height - 1;
 }
 
+/* advancedio.c:195-248 LoadGIF's per-pixel loop. PARITY UNPINNED: advancedio.c needs FreeImage, which is not in this image,
+ * so this restatement could not be run against the reference; it follows the source line by line except for the two
+ * accidents named in include/imp_gpu.h (row over-read at x == left+w; palette[-1]). */
+typedef struct { const unsigned char* indices; int pitch, width, height, left, top, dispose, key; const unsigned char* palette; } orc_gif_frame;
+void orc_gif_expand(const orc_gif_frame* frames, int n, int cw, int ch, int destructive, unsigned char* const* canvases, int cstep) {
+    int* master = (int*)calloc((size_t)cw * ch, sizeof(int));
+    for (int f = 0; f < n; f++) {
+        const orc_gif_frame* fr = &frames[f];
+        for (int y = 0; y < ch; y++) {
+            int rowidx = fr->height + fr->top - y - 1;
+            const unsigned char* row = (rowidx >= 0 && rowidx < fr->height) ? fr->indices + (size_t)rowidx * fr->pitch : NULL;
+            for (int x = 0; x < cw; x++) {
+                int coloridx;
+                if (!row || x < fr->left || y < fr->top || x >= fr->left + fr->width || y > fr->top + fr->height) coloridx = fr->key;
+                else coloridx = row[x - fr->left];
+                if (destructive) {
+                    int offset = y * cw + x;
+                    if (fr->dispose == 2) { if (coloridx == fr->key) coloridx = 0; else master[offset] = coloridx; }
+                    else { if (coloridx == fr->key && f > 0) coloridx = master[offset]; else master[offset] = coloridx; }
+                }
+                unsigned char* d = canvases[f] + (size_t)y * cstep + (size_t)x * 4;
+                if (coloridx >= 0 && coloridx < 256) {
+                    const unsigned char* q = fr->palette + coloridx * 4;
+                    d[0] = q[0]; d[1] = q[1]; d[2] = q[2]; d[3] = coloridx == fr->key ? 0 : 255;
+                } else { d[0] = d[1] = d[2] = d[3] = 0; }
+            }
+        }
+    }
+    free(master);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* 2. OpenCV ops the reference calls (pinned against cv2 4.13 IPP-off)        */
 /* ------------------------------------------------------------------------------------------ */

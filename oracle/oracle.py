@@ -131,6 +131,21 @@ class _Orc:
         v = _view(np.ascontiguousarray(img))
         return float(self.lib.orc_perceived_brightness(C.byref(v)))
 
+    def gif_expand(self, frames, cw, ch, destructive):
+        """frames: list of dicts(indices HxW uint8 bottom-up, left, top, dispose, key, palette 256x4). Returns n BGRA canvases."""
+        class F(C.Structure):
+            _fields_ = [("indices", C.c_void_p), ("pitch", C.c_int), ("width", C.c_int), ("height", C.c_int), ("left", C.c_int),
+                        ("top", C.c_int), ("dispose", C.c_int), ("key", C.c_int), ("palette", C.c_void_p)]
+        keep, arr = [], (F * len(frames))()
+        for i, f in enumerate(frames):
+            idx = np.ascontiguousarray(f["indices"], np.uint8); pal = np.ascontiguousarray(f["palette"], np.uint8)
+            keep += [idx, pal]
+            arr[i] = F(idx.ctypes.data, idx.strides[0], idx.shape[1], idx.shape[0], f["left"], f["top"], f["dispose"], f["key"], pal.ctypes.data)
+        outs = [np.zeros((ch, cw, 4), np.uint8) for _ in frames]
+        ptrs = (C.c_void_p * len(frames))(*[o.ctypes.data for o in outs])
+        self.lib.orc_gif_expand(arr, len(frames), cw, ch, 1 if destructive else 0, ptrs, cw * 4)
+        return outs
+
     def ascii(self, img, wide=False) -> bytes:
         a = np.ascontiguousarray(img)
         v = _view(a)

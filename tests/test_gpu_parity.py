@@ -338,3 +338,26 @@ def test_ascii_and_encoder_packing(gpu, orc):
             c2, _, ref = _oracle(orc, img, rq, kw)
             assert code == c2 == 0
             _assert_same(out, ref, rq, _has_vignette(rq))
+
+
+def test_gif_canvas_expansion(gpu, orc):
+    """SURVEY 8f-2: palette-index frames + disposal replay -> BGRA canvases (restatement of advancedio.c:195-248;
+    parity unpinned against the reference itself, which needs FreeImage)."""
+    rng = np.random.default_rng(11)
+    o = orc.orc()
+    for destructive in (False, True):
+        for (cw, ch, n) in [(48, 27, 6), (131, 77, 9), (1, 1, 2)]:
+            frames = []
+            for f in range(n):
+                w = cw if f == 0 else int(rng.integers(1, cw + 1)); h = ch if f == 0 else int(rng.integers(1, ch + 1))
+                pitch = (w + 3) & ~3
+                idx = rng.integers(0, 16, (h, pitch), dtype=np.uint8)
+                frames.append(dict(indices=idx[:, :w] if pitch == w else np.ascontiguousarray(idx)[:, :w], left=0 if f == 0 else int(rng.integers(0, cw - w + 1)),
+                                   top=0 if f == 0 else int(rng.integers(0, ch - h + 1)), dispose=int(rng.integers(0, 4)),
+                                   key=int(rng.choice([-1, 0, 3, 7])), palette=rng.integers(0, 256, (256, 4), dtype=np.uint8)))
+            for fr in frames:
+                fr["indices"] = np.ascontiguousarray(fr["indices"])
+            got = gpu.gif_expand(frames, cw, ch, destructive)
+            ref = o.gif_expand(frames, cw, ch, destructive)
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b)
