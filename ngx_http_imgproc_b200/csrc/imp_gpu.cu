@@ -136,14 +136,24 @@ int pass_pitch(const ImpHostPass& hp) { return align16(hp.out_w * hp.out_c); }
 
 // Scratch a plan needs on the device: intermediates between passes + the u16 plane of each generic blur.
 // off[k] = offset of pass k's output (non-final passes); blur_off[k] = offset of pass k's u16 plane.
-size_t plan_scratch_layout(const imp_gpu_plan* p, size_t base, std::vector<size_t>& off, std::vector<size_t>& blur_off) {
+int pick_variant(const ImpPass& h, const ImpJob& j);
+
+// `src`/`sp`: the job's source (null = one of the library's own aligned buffers). The u16 plane is only reserved for a
+// blur that cannot take the fused tile kernel (radius > 12, or a pass-0 source whose rows are not 16-byte addressable).
+size_t plan_scratch_layout(const imp_gpu_plan* p, size_t base, std::vector<size_t>& off, std::vector<size_t>& blur_off,
+                           const uint8_t* src = nullptr, int sp = 0) {
     size_t cur = base;
     auto take = [&](size_t bytes) { size_t o = cur; cur += (bytes + 255) & ~size_t(255); return o; };
     off.assign(p->passes.size(), 0); blur_off.assign(p->passes.size(), 0);
     for (size_t k = 0; k < p->passes.size(); k++) {
         const ImpHostPass& hp = p->passes[k];
         if (k + 1 < p->passes.size()) off[k] = take((size_t)pass_pitch(hp) * hp.out_h);
-        if (hp.hdr.kind == IMP_G_BLUR) blur_off[k] = take((size_t)hp.hdr.sw * hp.hdr.sh * hp.hdr.sc * 2);
+        if (hp.hdr.kind == IMP_G_BLUR) {
+            ImpJob probe{};
+            probe.src = (k == 0 && src) ? src : reinterpret_cast<const uint8_t*>(uintptr_t(256));
+            probe.src_pitch = (k == 0 && src) ? sp : 16;
+            if (pick_variant(hp.hdr, probe) == 0) blur_off[k] = take((size_t)hp.hdr.sw * hp.hdr.sh * hp.hdr.sc * 2);
+        }
     }
     return cur;
 }
@@ -261,7 +271,7 @@ int batch_compile(imp_gpu_batch* b) {
         if (rc) return rc;
         max_passes = std::max(max_passes, (int)p->passes.size());
         b->algo_bytes += p->algo_bytes;
-        scratch = plan_scratch_layout(p, scratch, off[i], boff[i]);
+        scratch = plan_scratch_layout(p, scratch, off[i], boff[i], b->items[i].src, b->items[i].sp);
     }
     if (scratch > b->scratch_cap) {
         if (b->d_scratch) CK(cudaFree(b->d_scratch));
@@ -328,7 +338,7 @@ int batch_compile(imp_gpu_batch* b) {
 // `scratch` must hold plan_scratch_layout(plan) bytes (or be null when the plan needs none).
 int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int dp, uint8_t* scratch, cudaStream_t st) {
     std::vector<size_t> off, boff;
-    plan_scratch_layout(p, 0, off, boff);
+    plan_scratch_layout(p, 0, off, boff, src, sp);
     for (size_t k = 0; k < p->passes.size(); k++) {
         const ImpHostPass& hp = p->passes[k];
         ImpJob j = make_job(p, t_dev, k, src, sp, dst, dp, scratch, off);
@@ -345,7 +355,7 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
     return IMP_OK;
 }
 
-size_t plan_scratch_bytes(const imp_gpu_plan* p) { std::vector<size_t> a, b; return plan_scratch_layout(p, 0, a, b); }
+size_t plan_scratch_bytes(const imp_gpu_plan* p, const uint8_t* src = nullptr, int sp = 0) { std::vector<size_t> a, b; return plan_scratch_layout(p, 0, a, b, src, sp); }
 
 }  // namespace
 
@@ -511,7 +521,7 @@ int imp_gpu_run_device(imp_gpu_plan* plan, const void* d_src, int sp, void* d_ds
     if (plan->src_c == 4 && (sp % 4 || ((uintptr_t)d_src) % 4)) return IMP_ERROR_INVALID_ARGS;
     if ((rc = plan_to_device(plan))) return rc;
     cudaStream_t st = pick_stream(stream);
-    const size_t need = plan_scratch_bytes(plan);
+    const size_t need = plan_scratch_bytes(plan, (const uint8_t*)d_src, sp);
     uint8_t* scratch = nullptr;
     if (need) CK(cudaMallocAsync((void**)&scratch, need, st));        // stream-ordered: stays asynchronous
     rc = launch_single(plan, (const uint8_t*)d_src, sp, (uint8_t*)d_dst, dp, scratch, st);
