@@ -49,6 +49,11 @@ def watermark(seed, h, w):
 def workload(name: str, scale: int = 1):
     if name == "cfg1":
         return dict(desc="1920x1080x3 -> resize=640,360 (AREA 3x3), batch 256", jobs=[((1080, 1920, 3), dict(resize="640,360"), 256 // scale)], cfg=dict())
+    if name == "cfg1l":   # cfg1 "as worded": bilinear (shim-level extension, not a reference call site)
+        return dict(desc="1920x1080x3 -> resize=640,360 INTER_LINEAR (extension), batch 256", jobs=[((1080, 1920, 3), dict(resize="640,360", interp=1), 256 // scale)], cfg=dict())
+    if name == "cfg3nn":  # cfg3 reference-faithful: GIF output forces INTER_NN (bridge.c:594)
+        return dict(desc="200 frames 480x270x4 -> resize=960,540,up (NN, GIF output) + modulate=0,0,100 + colorize=704214,0.6",
+                    jobs=[((270, 480, 4), dict(resize="960,540,up", simple=True, filters=["modulate=0,0,100", "colorize=704214,0.6"]), 200 // scale)], cfg=dict())
     if name == "cfg2":
         return dict(desc="256 x [3840x2160x4 -> crop=3600px,2025px,c,c -> resize=800,450 (AREA 4.5x) -> 256x64 watermark r,b,10,10 opacity 60]",
                     jobs=[((2160, 3840, 4), dict(crop="3600px,2025px,c,c", resize="800,450"), 256 // scale)],

@@ -187,9 +187,11 @@ typedef struct imp_gpu_gif_frame {
 /* Expands n frames into n BGRA canvases of canvas_w x canvas_h laid out back to back on the device
  * (frame f at d_canvases + f*canvas_pitch*canvas_h), ready to be fed to imp_gpu_batch_add. `destructive` as
  * LoadGIF's isdestructive (replay disposal through the master index canvas). Uploads 1 byte per pixel.
- * Two reference accidents are not reproduced: the off-by-one that reads one byte past a frame's row at
- * x == left+width (advancedio.c:203), and palette[-1] for uncovered pixels of a frame without a transparency key
- * (written as transparent black here). */
+ * The loop's accidents are kept: the off-by-one at x == left+width (advancedio.c:203) reads row[width] — the pad
+ * byte or the next scanline's first index — as long as it lies inside the page's pitch*height block (so pass the
+ * page bits as FreeImage holds them), and uncovered pixels of a page without a transparent colour read palette[-1],
+ * FreeImage's biClrImportant == 256, i.e. {B,G,R} = {0,1,0} with alpha 0. `master` starts at 0 (uninitialised pool
+ * memory in the reference, only observable when frame 0 has DISPOSAL_BACKGROUND and transparent pixels). */
 int  imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
                                void* d_canvases, int canvas_pitch, void* stream);
 int  imp_gpu_gif_expand_host(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,

@@ -169,12 +169,12 @@ class Library:
         return out.raw[:n]
 
     def gif_expand(self, frames, cw: int, ch: int, destructive: bool):
-        """LoadGIF's canvas expansion (advancedio.c:195-248) on the device; frames as dicts: indices (HxW uint8, bottom-up), left, top, dispose, key, palette (256x4)."""
+        """LoadGIF's canvas expansion (advancedio.c:195-248) on the device; frames as dicts: indices (HxW uint8, bottom-up; or H x pitch with `width`: the page as FreeImage pads it), left, top, dispose, key, palette (256x4)."""
         keep, arr = [], (CGifFrame * len(frames))()
         for i, f in enumerate(frames):
             idx = np.ascontiguousarray(f["indices"], np.uint8); pal = np.ascontiguousarray(f["palette"], np.uint8)
             keep += [idx, pal]
-            arr[i] = CGifFrame(idx.ctypes.data, idx.strides[0], idx.shape[1], idx.shape[0], f["left"], f["top"], f["dispose"], f["key"], pal.ctypes.data)
+            arr[i] = CGifFrame(idx.ctypes.data, idx.strides[0], f.get("width") or idx.shape[1], idx.shape[0], f["left"], f["top"], f["dispose"], f["key"], pal.ctypes.data)
         outs = [np.zeros((ch, cw, 4), np.uint8) for _ in frames]
         ptrs = (C.c_void_p * len(frames))(*[o.ctypes.data for o in outs])
         self.lib.imp_gpu_gif_expand_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]

@@ -171,7 +171,7 @@ ImpJob make_job(const imp_gpu_plan* p, int d, size_t k, const uint8_t* src, int 
     return j;
 }
 
-int pass_tiles(const ImpPass& h) { return ((h.bw + 31) / 32) * ((h.bh + 7) / 8); }
+int pass_tiles(const ImpPass& h) { return ((h.bw + 31) / 32) * ((h.bh + 31) / 32); }      // imp_pass_kernel: 32 x (8 x PASS_PPT) pixels per CTA
 
 // Tile (shared-memory, TMA-staged) variant: needs 16-byte addressable source rows — pitch % 16 == 0 and
 // either the image rows or the window rows start 16-byte aligned (imp_tiles.cuh) — and a footprint that fits.

@@ -111,8 +111,11 @@ __global__ void __launch_bounds__(256) imp_gif_expand_kernel(const ImpGifFrame* 
         const ImpGifFrame fr = frames[f];
         const int rowidx = fr.h + fr.top - y - 1;
         int idx;
-        if (rowidx < 0 || rowidx >= fr.h || x < fr.left || y < fr.top || x >= fr.left + fr.w) idx = fr.key;
-        else idx = __ldg(fr.indices + (size_t)rowidx * fr.pitch + (x - fr.left));
+        // advancedio.c:203 tests `x > left + w`, so the column right of the frame reads row[w]: a pad byte of the
+        // scanline or the first index of the next one. Reproduced while that byte is inside the page's pixel block.
+        const int col = x - fr.left;
+        if (rowidx < 0 || rowidx >= fr.h || col < 0 || col > fr.w || rowidx * fr.pitch + col >= fr.h * fr.pitch) idx = fr.key;
+        else idx = __ldg(fr.indices + (size_t)rowidx * fr.pitch + col);
         if (destructive) {
             if (fr.dispose == 2) {                       // GIF_DISPOSAL_BACKGROUND
                 if (idx == fr.key) idx = 0; else master = idx;
@@ -120,11 +123,11 @@ __global__ void __launch_bounds__(256) imp_gif_expand_kernel(const ImpGifFrame* 
                 if (idx == fr.key && f > 0) idx = master; else master = idx;
             }
         }
-        uchar4 px = make_uchar4(0, 0, 0, 0);
-        if (idx >= 0 && idx < 256) {
-            const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(fr.palette) + idx);
-            px = make_uchar4(q.x, q.y, q.z, idx == fr.key ? 0 : 255);
-        }
+        // idx is 0..255 or -1 (a page without a transparent colour). palette[-1] aliases FreeImage's biClrImportant == 256,
+        // i.e. the bytes {0,1,0,0} (advancedio.c:232 with FreeImage_GetTransparentIndex == -1).
+        uchar4 q = make_uchar4(0, 1, 0, 0);
+        if (idx >= 0 && idx < 256) q = __ldg(reinterpret_cast<const uchar4*>(fr.palette) + idx);
+        const uchar4 px = make_uchar4(q.x, q.y, q.z, idx == fr.key ? 0 : 255);
         *reinterpret_cast<uchar4*>(canvases + ((size_t)f * ch + y) * cpitch + (size_t)x * 4) = px;
     }
 }
@@ -176,48 +179,102 @@ __device__ __forceinline__ void promote(const int* v, ImpPx& p) {
     else { p.b = v[0]; p.g = v[1]; p.r = v[2]; p.a = (SC == 4) ? v[3] : 255; }
 }
 
+// The general pass kernel: one thread owns PASS_PPT output pixels of a column (rows TILE_H apart inside a
+// 32 x 32 tile). The job and pass headers are staged in shared memory together with the ops, so the per-thread
+// set-up (about 130 instructions when it was paid per pixel) and every op's parameter fetch + dispatch are
+// shared by PASS_PPT pixels, and the PASS_PPT gathers are independent loads in flight together.
+constexpr int PASS_PPT = 4;
+
+struct PassHdrSmem {
+    ImpPass P;
+    const uint8_t* src; uint8_t* dst; const uint8_t* wm;
+    int src_pitch, dst_pitch, wm_pitch, wm_c;
+};
+
 template <int KIND, int SC>
 __global__ void __launch_bounds__(TILE_W * TILE_H)
 imp_pass_kernel(const ImpJob* __restrict__ jobs, int first, int count, const ImpJob one) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(16) PassHdrSmem H;
     const int j = blockIdx.y + blockIdx.z * 65535;
     if (j >= count) return;
-    const ImpJob job = jobs ? jobs[first + j] : one;
-    const uint8_t* blob = job.pass;
-    const ImpPass* __restrict__ P = reinterpret_cast<const ImpPass*>(blob);
-    const int bw = P->bw, bh = P->bh;
-    const int tiles_x = (bw + TILE_W - 1) / TILE_W, tiles_y = (bh + TILE_H - 1) / TILE_H;
+    const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    const ImpJob* jp = jobs ? jobs + first + j : nullptr;
+    const uint8_t* blob = jp ? jp->pass : one.pass;
+    {
+        static_assert(sizeof(ImpPass) % 4 == 0, "ImpPass is copied by words");
+        const int* g = reinterpret_cast<const int*>(blob);
+        int* sP = reinterpret_cast<int*>(&H.P);
+        if (tid < (int)(sizeof(ImpPass) / 4)) sP[tid] = __ldg(g + tid);
+        if (tid == 64) {
+            H.src = jp ? jp->src : one.src; H.dst = jp ? jp->dst : one.dst; H.wm = jp ? jp->wm : one.wm;
+            H.src_pitch = jp ? jp->src_pitch : one.src_pitch; H.dst_pitch = jp ? jp->dst_pitch : one.dst_pitch;
+            H.wm_pitch = jp ? jp->wm_pitch : one.wm_pitch; H.wm_c = jp ? jp->wm_c : one.wm_c;
+        }
+        const ImpPass* gP = reinterpret_cast<const ImpPass*>(blob);
+        const int bytes = __ldg(&gP->nops) * (int)sizeof(ImpOp) + __ldg(&gP->lut_bytes);
+        const uint4* go = reinterpret_cast<const uint4*>(blob + __ldg(&gP->ops_off));
+        uint4* so = reinterpret_cast<uint4*>(smem);
+        for (int i = tid; i < (bytes + 15) / 16; i += TILE_W * TILE_H) so[i] = __ldg(go + i);
+    }
+    __syncthreads();
+    const ImpPass& P = H.P;
+    const int bw = P.bw, bh = P.bh;
+    const int tiles_x = (bw + TILE_W - 1) / TILE_W, tiles_y = (bh + TILE_H * PASS_PPT - 1) / (TILE_H * PASS_PPT);
     if ((int)blockIdx.x >= tiles_x * tiles_y) return;
-    OpsSmem os = stage_ops(P, blob, smem);
-    const int bx = (blockIdx.x % tiles_x) * TILE_W + threadIdx.x;
-    const int by = (blockIdx.x / tiles_x) * TILE_H + threadIdx.y;
-    if (bx >= bw || by >= bh) return;
+    const int x = (blockIdx.x % tiles_x) * TILE_W + threadIdx.x;
+    const int y0 = (blockIdx.x / tiles_x) * (TILE_H * PASS_PPT) + threadIdx.y;
+    if (x >= bw || y0 >= bh) return;
+    const int nops = P.nops;
+    const ImpOp* ops = reinterpret_cast<const ImpOp*>(smem);
+    const uint8_t* lut = smem + nops * sizeof(ImpOp);
 
     ImpSrcGlobal<SC> S;
-    S.base = job.src + (size_t)P->sy0 * job.src_pitch + (size_t)P->sx0 * SC;
-    S.pitch = job.src_pitch;
-    int v[4] = {0, 0, 0, 255};
-    if (KIND == IMP_G_COPY) {
-        imp_gather_copy<SC>(S, bx, by, v);
-    } else if (KIND == IMP_G_NN) {
-        imp_gather_nn<SC>(S, reinterpret_cast<const int*>(blob + P->xofs_off), reinterpret_cast<const int*>(blob + P->yofs_off), bx, by, v);
-    } else if (KIND == IMP_G_AREA_INT) {
-        imp_gather_area_int<SC>(S, P->nx, P->ny, P->area_scale, bx, by, v);
-    } else if (KIND == IMP_G_AREA_FRAC) {
-        imp_gather_area_frac<SC>(S, reinterpret_cast<const ImpRange*>(blob + P->xofs_off), reinterpret_cast<const ImpAreaTap*>(blob + P->xcoef_off),
-                                 reinterpret_cast<const ImpRange*>(blob + P->yofs_off), reinterpret_cast<const ImpAreaTap*>(blob + P->ycoef_off), bx, by, v);
-    } else if (KIND == IMP_G_CUBIC) {
-        imp_gather_cubic<SC>(S, P->sw, P->sh, reinterpret_cast<const int*>(blob + P->xofs_off), reinterpret_cast<const short*>(blob + P->xcoef_off),
-                             reinterpret_cast<const int*>(blob + P->yofs_off), reinterpret_cast<const short*>(blob + P->ycoef_off), P->simd_end, bx, by, v);
-    } else if (KIND == IMP_G_LINEAR) {
-        imp_gather_linear<SC>(S, P->sw, P->sh, reinterpret_cast<const int*>(blob + P->xofs_off), reinterpret_cast<const short*>(blob + P->xcoef_off),
-                              reinterpret_cast<const int*>(blob + P->yofs_off), reinterpret_cast<const short*>(blob + P->ycoef_off), bx, by, v);
+    S.pitch = H.src_pitch;
+    S.base = H.src + (size_t)P.sy0 * S.pitch + (size_t)P.sx0 * SC;
+    // rows past the bottom edge repeat the last row (computed, never stored)
+    int bx[PASS_PPT], by[PASS_PPT];
+#pragma unroll
+    for (int n = 0; n < PASS_PPT; n++) { bx[n] = x; by[n] = min(y0 + n * TILE_H, bh - 1); }
+    ImpPx px[PASS_PPT];
+#pragma unroll
+    for (int n = 0; n < PASS_PPT; n++) {
+        int v[4] = {0, 0, 0, 255};
+        if (KIND == IMP_G_COPY) {
+            imp_gather_copy<SC>(S, x, by[n], v);
+        } else if (KIND == IMP_G_NN) {
+            imp_gather_nn<SC>(S, reinterpret_cast<const int*>(blob + P.xofs_off), reinterpret_cast<const int*>(blob + P.yofs_off), x, by[n], v);
+        } else if (KIND == IMP_G_AREA_INT) {
+            imp_gather_area_int<SC>(S, P.nx, P.ny, P.area_scale, x, by[n], v);
+        } else if (KIND == IMP_G_AREA_FRAC) {
+            imp_gather_area_frac<SC>(S, reinterpret_cast<const ImpRange*>(blob + P.xofs_off), reinterpret_cast<const ImpAreaTap*>(blob + P.xcoef_off),
+                                     reinterpret_cast<const ImpRange*>(blob + P.yofs_off), reinterpret_cast<const ImpAreaTap*>(blob + P.ycoef_off), x, by[n], v);
+        } else if (KIND == IMP_G_CUBIC) {
+            imp_gather_cubic<SC>(S, P.sw, P.sh, reinterpret_cast<const int*>(blob + P.xofs_off), reinterpret_cast<const short*>(blob + P.xcoef_off),
+                                 reinterpret_cast<const int*>(blob + P.yofs_off), reinterpret_cast<const short*>(blob + P.ycoef_off), P.simd_end, x, by[n], v);
+        } else if (KIND == IMP_G_LINEAR) {
+            imp_gather_linear<SC>(S, P.sw, P.sh, reinterpret_cast<const int*>(blob + P.xofs_off), reinterpret_cast<const short*>(blob + P.xcoef_off),
+                                  reinterpret_cast<const int*>(blob + P.yofs_off), reinterpret_cast<const short*>(blob + P.ycoef_off), x, by[n], v);
+        }
+        promote<SC>(v, px[n]);
     }
-    ImpPx p;
-    promote<SC>(v, p);
-    const int oc = P->oc;
-    imp_run_ops(p, oc, bx, by, os.ops, P->nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
-    if (P->dc == 4) store_px<4>(job, P, bx, by, p); else store_px<3>(job, P, bx, by, p);
+    if (nops) imp_run_ops_n<PASS_PPT>(px, P.oc, bx, by, ops, nops, lut, H.wm, H.wm_pitch, H.wm_c);
+    const ImpFrameMap out = P.out;
+    const int dc = P.dc, dpitch = H.dst_pitch;
+    uint8_t* dst = H.dst;
+#pragma unroll
+    for (int n = 0; n < PASS_PPT; n++) {
+        if (y0 + n * TILE_H >= bh) break;
+        int X, Y;
+        imp_map_xy(out, x, by[n], X, Y);
+        uint8_t* d = dst + (size_t)Y * dpitch + (size_t)X * dc;
+        const ImpPx& p = px[n];
+        if (dc == 4) {
+            *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
+        } else {
+            d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r;
+        }
+    }
 }
 
 // ---- INTER_CUBIC with the horizontal pass shared down a column run ------------------------------------------------
@@ -237,7 +294,7 @@ __device__ __forceinline__ void cubic_hrow(const ImpSrcGlobal<SC>& S, const int 
 }
 
 template <int SC>
-__global__ void __launch_bounds__(TILE_W * TILE_H)
+__global__ void __launch_bounds__(TILE_W * TILE_H, 3)
 imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, const ImpJob one) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int jn = blockIdx.y + blockIdx.z * 65535;
@@ -270,9 +327,11 @@ imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
     float h0[SC], h1[SC], h2[SC], h3[SC];
     int top = 0;
     const float sc = 1.0f / 4194304.0f;
+    unsigned q[CUBIC_RUN];                      // gathered pixels, packed B|G<<8|R<<16|A<<24 while the H window is live
+#pragma unroll
     for (int o = 0; o < CUBIC_RUN; o++) {
         const int by = by0 + o;
-        if (by >= bh) break;
+        if (by >= bh) { q[o] = q[o > 0 ? o - 1 : 0]; continue; }      // past the bottom edge: a copy, never stored
         int v[4] = {0, 0, 0, 255};
         if (fast) {
             const int want = __ldg(yofs + by) - 1;
@@ -306,8 +365,20 @@ imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
         }
         ImpPx p;
         promote<SC>(v, p);
-        if (nops) imp_run_ops(p, oc, bx, by, os.ops, nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
-        if (P->dc == 4) store_px<4>(job, P, bx, by, p); else store_px<3>(job, P, bx, by, p);
+        q[o] = (unsigned)p.b | ((unsigned)p.g << 8) | ((unsigned)p.r << 16) | ((unsigned)p.a << 24);
+    }
+    ImpPx px[CUBIC_RUN];
+    int bxs[CUBIC_RUN], bys[CUBIC_RUN];
+#pragma unroll
+    for (int o = 0; o < CUBIC_RUN; o++) {
+        bxs[o] = bx; bys[o] = min(by0 + o, bh - 1);
+        px[o].b = q[o] & 255; px[o].g = (q[o] >> 8) & 255; px[o].r = (q[o] >> 16) & 255; px[o].a = q[o] >> 24;
+    }
+    if (nops) imp_run_ops_n<CUBIC_RUN>(px, oc, bxs, bys, os.ops, nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
+#pragma unroll
+    for (int o = 0; o < CUBIC_RUN; o++) {
+        if (by0 + o >= bh) break;
+        if (dc == 4) store_px<4>(job, P, bx, by0 + o, px[o]); else store_px<3>(job, P, bx, by0 + o, px[o]);
     }
 }
 

@@ -270,57 +270,116 @@ IMP_HD void imp_op_paper(ImpPx& p) {
     p.a = 255;
 }
 
-// Runs the op list of a pass on one pixel at base coordinates (bx,by).
+// Runs the op list of a pass on N pixels at base coordinates (bx[n],by[n]): the op loop is the outer one, so an op's
+// parameters and its dispatch are paid once per N pixels and the N bodies are independent instruction streams.
 // lut: the pass's LUT area; wm*: this job's watermark.
-IMP_HD void imp_run_ops(ImpPx& p, int oc, int bx, int by, const ImpOp* ops, int nops, const uint8_t* lut,
-                        const uint8_t* wm, int wm_pitch, int wm_c) {
+template <int N>
+IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int (&by)[N], const ImpOp* ops, int nops, const uint8_t* lut,
+                          const uint8_t* wm, int wm_pitch, int wm_c) {
     for (int k = 0; k < nops; k++) {
         const ImpOp& op = ops[k];
         switch (op.kind) {
-            case IMP_OP_MODULATE: imp_op_modulate(p, op.i[0], op.i[1], op.i[2]); break;
-            case IMP_OP_ADDCOLOR: imp_op_addcolor(p, op.f[0], op.f[1], op.f[2], op.f[3], op.i[0] != 0); break;
+            case IMP_OP_MODULATE: {
+                const int a = op.i[0], b = op.i[1], c = op.i[2];
+#pragma unroll
+                for (int n = 0; n < N; n++) imp_op_modulate(px[n], a, b, c);
+            } break;
+            case IMP_OP_ADDCOLOR: {
+                const float f0 = op.f[0], f1 = op.f[1], f2 = op.f[2], f3 = op.f[3];
+                const bool nonneg = op.i[0] != 0;
+#pragma unroll
+                for (int n = 0; n < N; n++) imp_op_addcolor(px[n], f0, f1, f2, f3, nonneg);
+            } break;
             case IMP_OP_LUT_ALL: {
                 const uint8_t* t = lut + op.i[0];
-                p.b = t[p.b]; p.g = t[p.g]; p.r = t[p.r];
-                if (oc == 4) p.a = t[p.a];
+#pragma unroll
+                for (int n = 0; n < N; n++) {
+                    ImpPx& p = px[n];
+                    p.b = t[p.b]; p.g = t[p.g]; p.r = t[p.r];
+                    if (oc == 4) p.a = t[p.a];
+                }
             } break;
-            case IMP_OP_CONTRAST:
-                p.b = imp_contrast1(p.b, op.f[0], op.f[1]);
-                p.g = imp_contrast1(p.g, op.f[0], op.f[1]);
-                p.r = imp_contrast1(p.r, op.f[0], op.f[1]);
-                break;
+            case IMP_OP_CONTRAST: {
+                const float f0 = op.f[0], f1 = op.f[1];
+#pragma unroll
+                for (int n = 0; n < N; n++) {
+                    ImpPx& p = px[n];
+                    p.b = imp_contrast1(p.b, f0, f1);
+                    p.g = imp_contrast1(p.g, f0, f1);
+                    p.r = imp_contrast1(p.r, f0, f1);
+                }
+            } break;
             case IMP_OP_GRADMAP: {
-                const uint8_t* t = lut + op.i[0] + ((p.r + p.g + p.b) / 3) * 3;
-                p.r = t[0]; p.g = t[1]; p.b = t[2];
+                const uint8_t* t0 = lut + op.i[0];
+#pragma unroll
+                for (int n = 0; n < N; n++) {
+                    ImpPx& p = px[n];
+                    const uint8_t* t = t0 + ((p.r + p.g + p.b) / 3) * 3;
+                    p.r = t[0]; p.g = t[1]; p.b = t[2];
+                }
             } break;
             case IMP_OP_VIGNETTE: {
-                int x, y; imp_map_xy(op.map, bx, by, x, y);
 #if defined(__CUDA_ARCH__)
                 const float* tab = reinterpret_cast<const float*>(((unsigned long long)(unsigned)op.i[5] << 32) | (unsigned)op.i[4]);
                 if (tab) {           // mask[d2], tabulated per plan by imp_vignette_table_kernel with the code of imp_vignette_mask
-                    const int dx = op.i[0] - x, dy = op.i[1] - y;
-                    imp_op_vignette_masked(p, __ldg(tab + (dx * dx + dy * dy)));
+                    const int cx = op.i[0], cy = op.i[1];
+#pragma unroll
+                    for (int n = 0; n < N; n++) {
+                        int x, y; imp_map_xy(op.map, bx[n], by[n], x, y);
+                        const int dx = cx - x, dy = cy - y;
+                        imp_op_vignette_masked(px[n], __ldg(tab + (dx * dx + dy * dy)));
+                    }
                     break;
                 }
 #endif
-                imp_op_vignette(p, x, y, op.i[0], op.i[1], op.f[0], op.f[1]);
-            } break;
-            case IMP_OP_LOMO: p.g = imp_lomo1(p.g); p.r = imp_lomo1(p.r); break;
-            case IMP_OP_RAINBOW: imp_op_rainbow(p, op.i[0]); break;
-            case IMP_OP_SCANLINE: {
-                int x, y; imp_map_xy(op.map, bx, by, x, y);
-                imp_op_scanline(p, y, op.i[0], op.i[1], op.i[3], op.i[4]);
-            } break;
-            case IMP_OP_WATERMARK: {
-                int x, y; imp_map_xy(op.map, bx, by, x, y);
-                int wx = x - op.i[0], wy = y - op.i[1];
-                if (wx >= 0 && wy >= 0 && wx < op.i[2] && wy < op.i[3]) {
-                    const uint8_t* s = wm + (size_t)wy * wm_pitch + (size_t)wx * wm_c;
-                    imp_op_over(p, oc == 4, s[0], s[1], s[2], wm_c == 4 ? s[3] : 255, wm_c == 4, op.f[0]);
+                for (int n = 0; n < N; n++) {
+                    int x, y; imp_map_xy(op.map, bx[n], by[n], x, y);
+                    imp_op_vignette(px[n], x, y, op.i[0], op.i[1], op.f[0], op.f[1]);
                 }
             } break;
-            case IMP_OP_PAPER: if (oc == 4) imp_op_paper(p); break;
+            case IMP_OP_LOMO:
+#pragma unroll
+                for (int n = 0; n < N; n++) { px[n].g = imp_lomo1(px[n].g); px[n].r = imp_lomo1(px[n].r); }
+                break;
+            case IMP_OP_RAINBOW: {
+                const int a = op.i[0];
+#pragma unroll
+                for (int n = 0; n < N; n++) imp_op_rainbow(px[n], a);
+            } break;
+            case IMP_OP_SCANLINE:
+#pragma unroll
+                for (int n = 0; n < N; n++) {
+                    int x, y; imp_map_xy(op.map, bx[n], by[n], x, y);
+                    imp_op_scanline(px[n], y, op.i[0], op.i[1], op.i[3], op.i[4]);
+                }
+                break;
+            case IMP_OP_WATERMARK:
+#pragma unroll
+                for (int n = 0; n < N; n++) {
+                    int x, y; imp_map_xy(op.map, bx[n], by[n], x, y);
+                    int wx = x - op.i[0], wy = y - op.i[1];
+                    if (wx >= 0 && wy >= 0 && wx < op.i[2] && wy < op.i[3]) {
+                        const uint8_t* s = wm + (size_t)wy * wm_pitch + (size_t)wx * wm_c;
+                        imp_op_over(px[n], oc == 4, s[0], s[1], s[2], wm_c == 4 ? s[3] : 255, wm_c == 4, op.f[0]);
+                    }
+                }
+                break;
+            case IMP_OP_PAPER:
+                if (oc == 4) {
+#pragma unroll
+                    for (int n = 0; n < N; n++) imp_op_paper(px[n]);
+                }
+                break;
             default: break;
         }
     }
+}
+
+// One pixel.
+IMP_HD void imp_run_ops(ImpPx& p, int oc, int bx, int by, const ImpOp* ops, int nops, const uint8_t* lut,
+                        const uint8_t* wm, int wm_pitch, int wm_c) {
+    ImpPx px[1] = {p};
+    const int xs[1] = {bx}, ys[1] = {by};
+    imp_run_ops_n<1>(px, oc, xs, ys, ops, nops, lut, wm, wm_pitch, wm_c);
+    p = px[0];
 }

@@ -372,9 +372,14 @@ long orc_ascii(const orc_img* im, int wide, unsigned char* out) {
     return (long)(width + 1) * height - 1;
 }
 
-/* advancedio.c:195-248 LoadGIF's per-pixel loop. PARITY UNPINNED: advancedio.c needs FreeImage, which is not in this image,
- * so this restatement could not be run against the reference; it follows the source line by line except for the two
- * accidents named in include/imp_gpu.h (row over-read at x == left+w; palette[-1]). */
+/* advancedio.c:195-248 LoadGIF's per-pixel loop. Pinned against the reference's own LoadGIF (advancedio.c compiled
+ * unmodified over oracle/fake_freeimage.c, tests/test_oracle.py). Three accidents of that loop, as restated here:
+ *  - `x > left + w` (advancedio.c:203) lets x == left+w read row[w]: the scanline's pad byte or the first index of
+ *    the next scanline. Restated while the byte lies inside the page's pitch*height block; past it -> the key.
+ *  - a page without a transparent colour has key == -1 and uncovered pixels index palette[-1], which aliases the
+ *    BITMAPINFOHEADER's biClrImportant (256 for 8-bit pages): bytes {0,1,0,0}.
+ *  - `master` is uninitialised pool memory in the reference; it is only read before being written when frame 0 has
+ *    DISPOSAL_BACKGROUND and transparent pixels. Zero here. */
 typedef struct { const unsigned char* indices; int pitch, width, height, left, top, dispose, key; const unsigned char* palette; } orc_gif_frame;
 void orc_gif_expand(const orc_gif_frame* frames, int n, int cw, int ch, int destructive, unsigned char* const* canvases, int cstep) {
     int* master = (int*)calloc((size_t)cw * ch, sizeof(int));
@@ -385,7 +390,8 @@ void orc_gif_expand(const orc_gif_frame* frames, int n, int cw, int ch, int dest
             const unsigned char* row = (rowidx >= 0 && rowidx < fr->height) ? fr->indices + (size_t)rowidx * fr->pitch : NULL;
             for (int x = 0; x < cw; x++) {
                 int coloridx;
-                if (!row || x < fr->left || y < fr->top || x >= fr->left + fr->width || y > fr->top + fr->height) coloridx = fr->key;
+                if (!row || x < fr->left || y < fr->top || x > fr->left + fr->width || y > fr->top + fr->height) coloridx = fr->key;
+                else if (rowidx * fr->pitch + (x - fr->left) >= fr->height * fr->pitch) coloridx = fr->key;   /* past the block */
                 else coloridx = row[x - fr->left];
                 if (destructive) {
                     int offset = y * cw + x;
@@ -393,10 +399,9 @@ void orc_gif_expand(const orc_gif_frame* frames, int n, int cw, int ch, int dest
                     else { if (coloridx == fr->key && f > 0) coloridx = master[offset]; else master[offset] = coloridx; }
                 }
                 unsigned char* d = canvases[f] + (size_t)y * cstep + (size_t)x * 4;
-                if (coloridx >= 0 && coloridx < 256) {
-                    const unsigned char* q = fr->palette + coloridx * 4;
-                    d[0] = q[0]; d[1] = q[1]; d[2] = q[2]; d[3] = coloridx == fr->key ? 0 : 255;
-                } else { d[0] = d[1] = d[2] = d[3] = 0; }
+                static const unsigned char clr_important[4] = {0, 1, 0, 0};
+                const unsigned char* q = (coloridx >= 0 && coloridx < 256) ? fr->palette + coloridx * 4 : clr_important;
+                d[0] = q[0]; d[1] = q[1]; d[2] = q[2]; d[3] = coloridx == fr->key ? 0 : 255;
             }
         }
     }

@@ -132,7 +132,8 @@ class _Orc:
         return float(self.lib.orc_perceived_brightness(C.byref(v)))
 
     def gif_expand(self, frames, cw, ch, destructive):
-        """frames: list of dicts(indices HxW uint8 bottom-up, left, top, dispose, key, palette 256x4). Returns n BGRA canvases."""
+        """frames: list of dicts(indices HxW uint8 bottom-up (or H x pitch with `width` given: the page block as FreeImage
+        pads it), left, top, dispose, key, palette 256x4). Returns n BGRA canvases."""
         class F(C.Structure):
             _fields_ = [("indices", C.c_void_p), ("pitch", C.c_int), ("width", C.c_int), ("height", C.c_int), ("left", C.c_int),
                         ("top", C.c_int), ("dispose", C.c_int), ("key", C.c_int), ("palette", C.c_void_p)]
@@ -140,7 +141,7 @@ class _Orc:
         for i, f in enumerate(frames):
             idx = np.ascontiguousarray(f["indices"], np.uint8); pal = np.ascontiguousarray(f["palette"], np.uint8)
             keep += [idx, pal]
-            arr[i] = F(idx.ctypes.data, idx.strides[0], idx.shape[1], idx.shape[0], f["left"], f["top"], f["dispose"], f["key"], pal.ctypes.data)
+            arr[i] = F(idx.ctypes.data, idx.strides[0], f.get("width") or idx.shape[1], idx.shape[0], f["left"], f["top"], f["dispose"], f["key"], pal.ctypes.data)
         outs = [np.zeros((ch, cw, 4), np.uint8) for _ in frames]
         ptrs = (C.c_void_p * len(frames))(*[o.ctypes.data for o in outs])
         self.lib.orc_gif_expand(arr, len(frames), cw, ch, 1 if destructive else 0, ptrs, cw * 4)
@@ -635,6 +636,7 @@ class Ref:
         (IPP off, 1 thread): the real OpenCV CPU path. Returns False if cv2 is missing."""
         L = cls.lib()
         if not enable:
+            L.ref_set_callbacks.argtypes = [C.c_void_p] * 4
             L.ref_set_callbacks(None, None, None, None)
             cls._cbs = None
             return True
@@ -832,3 +834,100 @@ class Ref:
         if code == 0 and ow.value:
             res = out[:ow.value * oh.value * oc.value].reshape(oh.value, ow.value, oc.value).copy()
         return code, step.value, res
+
+    # -- advancedio.c (compiled unmodified over oracle/fake_freeimage.c) ------------------------------------
+    FIF_BMP, FIF_JPEG, FIF_TARGA, FIF_GIF = 0, 2, 17, 25
+
+    @staticmethod
+    def gif_container(frames) -> bytes:
+        """The fake multi-page container fake_freeimage.c decodes. frames: dicts with `indices` (h x w uint8, TOP-DOWN),
+        `palette` (256x4 B,G,R,x), left, top, dispose, key (-1 = none), time."""
+        import struct
+        out = [b"IMPGIF1\0", struct.pack("<i", len(frames))]
+        for f in frames:
+            idx = np.ascontiguousarray(f["indices"], np.uint8)
+            h, w = idx.shape
+            out.append(struct.pack("<7i", w, h, f.get("left", 0), f.get("top", 0), f.get("dispose", 0), f.get("key", -1), f.get("time", 0)))
+            out.append(np.ascontiguousarray(f["palette"], np.uint8).tobytes())
+            out.append(idx.tobytes())
+        return b"".join(out)
+
+    @staticmethod
+    def fi_page_bits(indices_top_down: np.ndarray) -> np.ndarray:
+        """The page's pixel block as FreeImage holds it (and as LoadGIF reads it): bottom-up scanlines, rows padded to
+        4 bytes with zeros. Returns an (h, pitch) array; row 0 = bottom scanline."""
+        idx = np.ascontiguousarray(indices_top_down, np.uint8)
+        h, w = idx.shape
+        bits = np.zeros((h, (w + 3) & ~3), np.uint8)
+        bits[:, :w] = idx[::-1]
+        return bits
+
+    @classmethod
+    def fi_load(cls, blob: bytes, fmt: int, destructive: bool = False, page: int = -1):
+        """FiLoadFrames (advancedio.c:311-339). Returns (error, [dict(image, time, dispose, key)])."""
+        L = cls.lib()
+        L.ref_fi_load.restype = C.c_void_p
+        L.ref_fi_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ref_album_frame.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 6 + [C.c_void_p]
+        L.ref_album_free.argtypes = [C.c_void_p]
+        count, err = C.c_int(0), C.c_int(0)
+        album = L.ref_fi_load(blob, len(blob), fmt, 1 if destructive else 0, page, C.byref(count), C.byref(err))
+        frames = []
+        if not err.value:
+            for i in range(count.value):
+                w, h, c, t, d, k = (C.c_int(0) for _ in range(6))
+                if L.ref_album_frame(album, i, C.byref(w), C.byref(h), C.byref(c), C.byref(t), C.byref(d), C.byref(k), None):
+                    break
+                img = np.empty((h.value, w.value, c.value), np.uint8)
+                L.ref_album_frame(album, i, C.byref(w), C.byref(h), C.byref(c), C.byref(t), C.byref(d), C.byref(k), C.c_void_p(img.ctypes.data))
+                frames.append(dict(image=img, time=t.value, dispose=d.value, key=k.value))
+        L.ref_album_free(album)
+        return err.value, frames
+
+    @classmethod
+    def fi_save(cls, img: np.ndarray, fmt: int):
+        """FiSaveFrames -> SaveSingle -> IplToFI32 / IplToFI24 (advancedio.c:65-101, 421-446) through the fake encoder.
+        Returns (error, bpp, bits) with bits = the FIBITMAP's rows as they lie in memory (row 0 = bottom), pad removed."""
+        import struct
+        L = cls.lib()
+        L.ref_fi_save.restype = C.c_long
+        L.ref_fi_save.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.POINTER(C.c_int)]
+        a = np.ascontiguousarray(img)
+        h, w, c = a.shape
+        cap = 64 + ((w * 4 + 3) & ~3) * h
+        out = np.empty(cap, np.uint8)
+        err = C.c_int(0)
+        n = L.ref_fi_save(C.c_void_p(a.ctypes.data), w, h, c, a.strides[0], fmt, C.c_void_p(out.ctypes.data), cap, C.byref(err))
+        if err.value or n < 24:
+            return err.value, 0, None
+        assert out[:8].tobytes() == b"IMPFI01\0"
+        fw, fh, bpp, pitch = struct.unpack("<4i", out[8:24].tobytes())
+        bits = out[24:24 + pitch * fh].reshape(fh, pitch)[:, :fw * bpp // 8].reshape(fh, fw, bpp // 8).copy()
+        return 0, bpp, bits
+
+    @classmethod
+    def run_job_blob(cls, query: str, blob: bytes, cfg: Optional[OracleConfig] = None, exten: str = "gif"):
+        """RunJob (bridge.c:302-724) on an arbitrary blob — the fake GIF container goes through the reference's own
+        FiLoadFrames. Returns (code, step, image or None): the image decoded from cvEncodeImage's RAW container
+        (format=png/jpg) or from SaveSingle's FIBITMAP dump (format=bmp...: rows bottom-up, as IplToFI32/24 wrote them)."""
+        import struct
+        L = cls.lib()
+        cfg = cfg or OracleConfig()
+        c, keep = cls.make_config(cfg)
+        cap = max(cfg.max_w * cfg.max_h * 4, len(blob) * 8, 1 << 22)
+        out = np.empty(cap, np.uint8)
+        n, step, mime = C.c_long(0), C.c_int(0), C.c_int(0)
+        uri = ("/img." + exten + "?" + query).encode()
+        L.ref_run_job_blob.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_long, C.c_void_p, C.c_void_p, C.c_long,
+                                       C.POINTER(C.c_long), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        code = L.ref_run_job_blob(uri, exten.encode(), blob, len(blob), C.byref(c), C.c_void_p(out.ctypes.data), cap,
+                                  C.byref(n), C.byref(step), C.byref(mime))
+        img = None
+        raw = out[:n.value].tobytes()
+        if code == 0 and raw[8:12] == b"IMPR":
+            w, h, ch = struct.unpack("<3i", raw[12:24])
+            img = np.frombuffer(raw, np.uint8, w * h * ch, 24).reshape(h, w, ch).copy()
+        elif code == 0 and raw[:8] == b"IMPFI01\0":
+            w, h, bpp, pitch = struct.unpack("<4i", raw[8:24])
+            img = np.frombuffer(raw, np.uint8, pitch * h, 24).reshape(h, pitch)[:, :w * bpp // 8].reshape(h, w, bpp // 8).copy()
+        return code, step.value, img

@@ -12,9 +12,12 @@
  *    driven end to end without a JPEG/PNG codec: blob = 8-byte PNG signature, "IMPR", int32 w,h,c,
  *    then w*h*c tightly packed bytes. Encode writes the same container. Decode/encode are out of
  *    scope for the hot path; only the steps between them are under test.
+ *  - FreeImage: oracle/fake_freeimage.c (layout-faithful bitmaps over two trivial containers), so that the
+ *    reference's advancedio.c (LoadGIF, LoadSingle, IplToFI32/24) is compiled and driven unmodified too.
  *  - nginx pool functions: malloc/free.
  */
 #include "required.h"
+#include "advancedio.h"
 #include <stdint.h>
 
 typedef struct { unsigned char* data; int width, height, channels, step; } orc_img;
@@ -156,15 +159,7 @@ int cvKMeans2(const CvArr* s, int k, CvArr* l, CvTermCriteria tc, int at, void* 
 }
 void cvConvertScale(const CvArr* s, CvArr* d, double sc, double sh) { (void)s; (void)d; (void)sc; (void)sh; abort(); }
 
-/* ---- FreeImage / advancedio: not reachable with PNG-signed RAW blobs and png/jpg/json output -- */
-FIMEMORY* FreeImage_OpenMemory(BYTE* d, DWORD s) { (void)d; (void)s; return NULL; }
-void FreeImage_CloseMemory(FIMEMORY* s) { (void)s; }
-FREE_IMAGE_FORMAT FreeImage_GetFileTypeFromMemory(FIMEMORY* s, int n) { (void)s; (void)n; return FIF_UNKNOWN; }
-FREE_IMAGE_FORMAT FreeImage_GetFIFFromFilename(const char* f) { (void)f; return FIF_UNKNOWN; }
-int FiNotImplemented(FREE_IMAGE_FORMAT f) { (void)f; return 1; }
-int FiSupports32bit(FREE_IMAGE_FORMAT f) { (void)f; return 0; }
-Album FiLoadFrames(DecodeRequest r) { Album a; (void)r; a.Frames = NULL; a.Count = 0; a.Error = IMP_ERROR_UNSUPPORTED; return a; }
-Memory FiSaveFrames(EncodeRequest r) { Memory m; (void)r; m.Buffer = NULL; m.Length = 0; m.Error = IMP_ERROR_UNSUPPORTED; return m; }
+/* ---- FreeImage: oracle/fake_freeimage.c; advancedio.c itself is the reference's, compiled unmodified ---- */
 
 /* ---- nginx ------------------------------------------------------------------------------------ */
 void* ngx_palloc(ngx_pool_t* pool, size_t size) { (void)pool; return malloc(size ? size : 1); }
@@ -205,3 +200,68 @@ int ref_run_job(const char* uri, const char* exten, const unsigned char* pixels,
 }
 size_t ref_sizeof_iplimage(void) { return sizeof(IplImage); }
 size_t ref_sizeof_config(void) { return sizeof(Config); }
+
+/* ---- advancedio.c entry points -------------------------------------------------------------------- */
+/* FiLoadFrames (advancedio.c:311-339) on a container built by the test (IMPGIF1 / IMPFI01, fake_freeimage.c).
+ * Returns a heap Album*; *count / *error mirror Album.Count / Album.Error. */
+void* ref_fi_load(const unsigned char* buf, int len, int format, int destructive, int page, int* count, int* error) {
+    DecodeRequest r;
+    r.Buffer = (unsigned char*)buf; r.Length = len; r.Pool = NULL; r.Format = format; r.IsDestructive = destructive; r.Page = page;
+    Album* a = (Album*)malloc(sizeof(Album));
+    *a = FiLoadFrames(r);
+    *count = a->Count; *error = a->Error;
+    return a;
+}
+/* Frame i of an album: geometry + metadata; pixels copied tightly packed into out when out != NULL. */
+int ref_album_frame(void* album, int i, int* w, int* h, int* c, int* time, int* dispose, int* key, unsigned char* out) {
+    Album* a = (Album*)album;
+    if (i < 0 || i >= a->Count || !a->Frames) return -1;
+    IplImage* im = a->Frames[i].Image;
+    *w = im->width; *h = im->height; *c = im->nChannels;
+    *time = a->Frames[i].Time; *dispose = a->Frames[i].Dispose; *key = a->Frames[i].TransparencyKey;
+    if (out) for (int y = 0; y < im->height; y++) memcpy(out + (size_t)y * im->width * im->nChannels, im->imageData + (size_t)y * im->widthStep, (size_t)im->width * im->nChannels);
+    return 0;
+}
+void ref_album_free(void* album) {
+    Album* a = (Album*)album;
+    if (a->Frames) { for (int i = 0; i < a->Count; i++) cvReleaseImage(&a->Frames[i].Image); free(a->Frames); }
+    free(a);
+}
+/* FiSaveFrames (advancedio.c:448-461) of one frame in a non-GIF format: SaveSingle -> IplToFI32 / IplToFI24 -> the fake
+ * encoder's dump "IMPFI01\0", int32 w,h,bpp,pitch, then the FIBITMAP's bits as they lie in memory. Returns bytes written. */
+long ref_fi_save(const unsigned char* pixels, int w, int h, int c, int step, int format, unsigned char* out, long out_cap, int* error) {
+    IplImage* im = cvCreateImageHeader(cvSize(w, h), IPL_DEPTH_8U, c);
+    cvSetData(im, (void*)pixels, step);
+    Frame fr; fr.Image = im; fr.Time = 0; fr.Dispose = 0; fr.TransparencyKey = 0;
+    Album a; a.Frames = &fr; a.Count = 1; a.Error = 0;
+    EncodeRequest r; r.Album = &a; r.Pool = NULL; r.Format = format; r.Flags = 0;
+    Memory m = FiSaveFrames(r);
+    *error = m.Error;
+    long n = 0;
+    if (!m.Error && m.Length <= out_cap) { memcpy(out, m.Buffer, (size_t)m.Length); n = m.Length; }
+    if (!m.Error) free(m.Buffer);
+    cvReleaseImageHeader(&im);
+    return n;
+}
+/* RunJob on an arbitrary blob (e.g. the fake GIF container, so that decode goes through the reference's FiLoadFrames and
+ * encode through cvEncodeImage's RAW container or FiSaveFrames' dump). The encoded bytes are copied to out. */
+int ref_run_job_blob(const char* uri, const char* exten, const unsigned char* blob, long len, Config* cfg,
+                     unsigned char* out, long out_cap, long* out_len, int* step, int* mime) {
+    unsigned char* copy = (unsigned char*)malloc((size_t)len);
+    memcpy(copy, blob, (size_t)len);
+    ngx_connection_t conn; conn.log = NULL;
+    ngx_http_request_t req; memset(&req, 0, sizeof req);
+    req.connection = &conn;
+    req.unparsed_uri.data = (u_char*)uri; req.unparsed_uri.len = strlen(uri);
+    req.exten.data = (u_char*)exten; req.exten.len = strlen(exten);
+    JobResult* res = RunJob(copy, (size_t)len, &req, cfg);
+    int code = res->Code;
+    *step = res->Step; *mime = res->MIME; *out_len = 0;
+    if (code == IMP_OK && res->EncodedBytes && (long)res->Length <= out_cap) {
+        memcpy(out, res->EncodedBytes, res->Length);
+        *out_len = (long)res->Length;
+        free(res->EncodedBytes);
+    }
+    free(res); free(copy);
+    return code;
+}

@@ -34,3 +34,32 @@ def split_query(query):
 
 # gradmap LUT tails the reference leaves uninitialised: no golden case uses 4/6/7/8 colours.
 VIGNETTE_TOL = 1   # <= 1 LSB where libm's and CUDA's double cos may differ
+
+
+IO_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_io_v1.npz")
+
+
+def load_io():
+    """tests/golden/golden_io_v1.npz (made by tests/golden/make_golden_io.py from the reference's advancedio.c).
+    Returns dict(gifs=[dict(cw, ch, frames=[dict(indices top-down, palette, left, top, dispose, key)], out={0: [...], 1: [...]})],
+                 packs=[dict(img, fi24, fi32)], jobs=[dict(gif, query, out)])."""
+    z = np.load(IO_PATH)
+    meta = json.loads(bytes(z["meta"]).decode())
+    gifs = []
+    for gi, m in enumerate(meta["gifs"]):
+        frames = [dict(f, indices=z[f"g{gi}_idx{fi}"], palette=z[f"g{gi}_pal{fi}"]) for fi, f in enumerate(m["frames"])]
+        out = {d: [z[f"g{gi}_d{d}_out{fi}"] for fi in range(len(frames))] for d in (0, 1)}
+        gifs.append(dict(cw=m["cw"], ch=m["ch"], frames=frames, out=out))
+    packs = [dict(img=z[f"p{pi}_in"], fi24=z[f"p{pi}_fi24"], fi32=z[f"p{pi}_fi32"]) for pi in range(len(meta["packs"]))]
+    jobs = [dict(j, out=z[f"j{ji}_out"]) for ji, j in enumerate(meta["jobs"])]
+    return dict(gifs=gifs, packs=packs, jobs=jobs)
+
+
+def fi_page(frame):
+    """A golden GIF frame as FreeImage holds the locked page (what LoadGIF reads and the C ABI takes): bottom-up scanlines
+    padded to 4 bytes with zeros, plus the true width."""
+    idx = np.ascontiguousarray(frame["indices"], np.uint8)
+    h, w = idx.shape
+    bits = np.zeros((h, (w + 3) & ~3), np.uint8)
+    bits[:, :w] = idx[::-1]
+    return dict(indices=bits, width=w, palette=frame["palette"], left=frame["left"], top=frame["top"], dispose=frame["dispose"], key=frame["key"])

@@ -341,8 +341,8 @@ def test_ascii_and_encoder_packing(gpu, orc):
 
 
 def test_gif_canvas_expansion(gpu, orc):
-    """SURVEY 8f-2: palette-index frames + disposal replay -> BGRA canvases (restatement of advancedio.c:195-248;
-    parity unpinned against the reference itself, which needs FreeImage)."""
+    """palette-index frames + disposal replay -> BGRA canvases, against the restatement of
+    advancedio.c:195-248 (itself pinned to the reference's LoadGIF in tests/test_oracle.py)."""
     rng = np.random.default_rng(11)
     o = orc.orc()
     for destructive in (False, True):
@@ -361,3 +361,30 @@ def test_gif_canvas_expansion(gpu, orc):
             ref = o.gif_expand(frames, cw, ch, destructive)
             for a, b in zip(got, ref):
                 assert np.array_equal(a, b)
+
+
+def test_gif_expand_and_pack_golden_from_reference(gpu, orc):
+    """tests/golden/golden_io_v1.npz — outputs of the reference's own advancedio.c (LoadGIF, IplToFI24/32, RunJob on GIF
+    pages): sub-frames with the row[w] over-read, pages without a transparent colour (palette[-1]), every disposal."""
+    io = G.load_io()
+    for gif in io["gifs"]:
+        frames = [G.fi_page(f) for f in gif["frames"]]
+        for d in (0, 1):
+            got = gpu.gif_expand(frames, gif["cw"], gif["ch"], bool(d))
+            for k, (a, b) in enumerate(zip(got, gif["out"][d])):
+                assert np.array_equal(a, b), (gif["cw"], gif["ch"], d, k)
+    for pk in io["packs"]:
+        for bits in (24, 32):
+            code, _, out = _gpu_run(gpu, pk["img"], {}, dict(pack=bits))
+            assert code == 0 and np.array_equal(out, pk[f"fi{bits}"])
+    for job in io["jobs"]:
+        gif = io["gifs"][job["gif"]]
+        page = int([t for t in job["query"].split("&") if t.startswith("page")][0].split("=")[1])
+        frames = [G.fi_page(f) for f in gif["frames"]]
+        canvas = gpu.gif_expand(frames[:page + 1], gif["cw"], gif["ch"], True)[page]
+        rq = G.split_query(job["query"])
+        fmt = [t for t in job["query"].split("&") if t.startswith("format")][0].split("=")[1]
+        rq["flatten"] = fmt in ("jpg", "ppm")                      # bridge.c:641-645
+        rq["pack"] = {"tga": 32, "ppm": 24}.get(fmt, 0)            # bridge.c:680: FIF_BMP == 0 leaves through cvEncodeImage
+        code, _, out = _gpu_run(gpu, canvas, {}, rq)
+        assert code == 0 and np.array_equal(out, job["out"]), job["query"]

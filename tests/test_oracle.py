@@ -232,3 +232,111 @@ def test_ascii_restatement_vs_compiled_reference(orc):
             assert o.ascii(img, wide) == orc.Ref.ascii(img, args), (h, w, c, args)
     ramp = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(3, 2)
     assert o.ascii(ramp, True) == orc.Ref.ascii(ramp, "wide") and o.ascii(ramp, False) == orc.Ref.ascii(ramp, "x")
+
+
+# ---- advancedio.c: LoadGIF's canvas loop and IplToFI24/32, pinned against the reference's own code -------------------
+def _gif_job_restated(orc, gif, query):
+    """RunJob on a GIF with page=N, restated: destructive expansion up to the page, then steps 3-7, then the encoder's
+    packing (cvEncodeImage RAW for png/jpg, IplToFI32 for bmp/tga, IplToFI24 for ppm)."""
+    pc, p = orc.parse_query(query, orc.OracleConfig())
+    assert pc == 0
+    page = int([t for t in query.split("&") if t.startswith("page")][0].split("=")[1])
+    frames = [G.fi_page(f) for f in gif["frames"]]
+    canvas = orc.orc().gif_expand(frames[:page + 1], gif["cw"], gif["ch"], True)[page]
+    # bridge.c:443-447,680: FIF_BMP == 0 reads as "no advanced encoder", so format=bmp leaves through cvEncodeImage;
+    # bridge.c:641-645: formats without 32-bit support (ppm) are flattened like jpg.
+    pack = {"tga": 32, "ppm": 24}.get(p["format"], 0)
+    return orc.run_chain(canvas, p["crop"], p["gravity"], p["resize"], p["filters"], orc.OracleConfig(), False,
+                         flatten=(p["format"] in ("jpg", "ppm")), pack=pack)
+
+
+def test_gif_expand_and_pack_restatement_vs_golden(orc):
+    """The committed vectors made from the reference's advancedio.c (tests/golden/make_golden_io.py)."""
+    io = G.load_io()
+    o = orc.orc()
+    for gif in io["gifs"]:
+        frames = [G.fi_page(f) for f in gif["frames"]]
+        for d in (0, 1):
+            got = o.gif_expand(frames, gif["cw"], gif["ch"], bool(d))
+            for a, b in zip(got, gif["out"][d]):
+                assert np.array_equal(a, b)
+    for pk in io["packs"]:
+        assert np.array_equal(orc.fi_pack(pk["img"], 24), pk["fi24"])
+        assert np.array_equal(orc.fi_pack(pk["img"], 32), pk["fi32"])
+    for job in io["jobs"]:
+        code, _, out = _gif_job_restated(orc, io["gifs"][job["gif"]], job["query"])
+        assert code == job["code"] == 0
+        assert np.array_equal(out, job["out"]), job["query"]
+
+
+def test_gif_expand_restatement_vs_reference_loadgif(orc):
+    """Random multi-page GIFs through the reference's LoadGIF (advancedio.c compiled unmodified over the stand-in
+    FreeImage): sub-frames, all disposal methods, pages with and without a transparent colour, destructive or not.
+    The only pixel left out is the one the reference reads from beyond the page block (row[w] of the top scanline
+    when w % 4 == 0), and whatever it feeds through `master` afterwards."""
+    if not _have_ref(orc):
+        pytest.skip("compiled reference not available on this box")
+    rng = np.random.default_rng(1)
+    o = orc.orc()
+    compared = 0
+    for trial in range(250):
+        cw, ch, n = int(rng.integers(1, 24)), int(rng.integers(1, 20)), int(rng.integers(1, 6))
+        fr = []
+        for f in range(n):
+            w, h = (cw, ch) if f == 0 else (int(rng.integers(1, cw + 1)), int(rng.integers(1, ch + 1)))
+            left, top = (0, 0) if f == 0 else (int(rng.integers(0, cw - w + 1)), int(rng.integers(0, ch - h + 1)))
+            dispose = int(rng.integers(0, 4))
+            if f == 0 and dispose == 2:
+                dispose = 1
+            fr.append(dict(indices=rng.integers(0, 256 if rng.random() < .5 else 5, (h, w), dtype=np.uint8),
+                           palette=rng.integers(0, 256, (256, 4), dtype=np.uint8), left=left, top=top, dispose=dispose,
+                           key=int(rng.choice([-1, 0, 3, 255])), time=f))
+        blob = orc.Ref.gif_container(fr)
+        pages = [G.fi_page(f) for f in fr]
+        for destructive in (False, True):
+            err, ref = orc.Ref.fi_load(blob, orc.Ref.FIF_GIF, destructive)
+            assert err == 0 and len(ref) == n
+            got = o.gif_expand(pages, cw, ch, destructive)
+            mask = np.ones((ch, cw), bool)
+            for k in range(n):
+                h, w = fr[k]["indices"].shape
+                if not destructive:
+                    mask[:] = True
+                if w % 4 == 0 and fr[k]["left"] + w < cw:
+                    mask[fr[k]["top"], fr[k]["left"] + w] = False
+                assert not ((got[k] != ref[k]["image"]).any(axis=2) & mask).any(), (trial, destructive, k)
+                assert (ref[k]["dispose"], ref[k]["key"]) == (fr[k]["dispose"], fr[k]["key"])
+                compared += int(mask.sum())
+    assert compared > 100000
+
+
+def test_fi_pack_restatement_vs_reference_ipltofi(orc):
+    """IplToFI32 / IplToFI24 (advancedio.c:65-101) through FiSaveFrames -> SaveSingle, 3- and 4-channel frames."""
+    if not _have_ref(orc):
+        pytest.skip("compiled reference not available on this box")
+    for seed, (h, w, c) in enumerate([(5, 7, 3), (5, 7, 4), (1, 1, 3), (33, 18, 4), (16, 32, 3), (9, 13, 4)]):
+        img = rnd_image(seed, h, w, c)
+        for fmt, bits in ((orc.Ref.FIF_BMP, 32), (orc.Ref.FIF_TARGA, 32), (orc.Ref.FIF_JPEG, 24)):
+            err, bpp, ref = orc.Ref.fi_save(img, fmt)
+            assert err == 0 and bpp == bits
+            assert np.array_equal(orc.fi_pack(img, bits), ref)
+
+
+def test_runjob_on_gif_pages_vs_reference(orc):
+    """Whole RunJob on GIF containers: the reference's FiLoadFrames + steps 3-7 + encoder against the restatement."""
+    if not _have_ref(orc) or not _have_cv2():
+        pytest.skip("needs the compiled reference and cv2")
+    orc.Ref.use_cv2(True)
+    io = G.load_io()
+    try:
+        for gi, q in [(1, "page=5&resize=33,21&filter-modulate=0,0,100&filter-colorize=704214,0.6&format=png"),
+                      (4, "page=3&crop=16,9&gravity=r,b&resize=40&format=bmp"), (0, "page=2&filter-flip=10&filter-gamma=0.8&format=ppm"),
+                      (1, "page=6&resize=200,150,up&format=jpg"), (3, "page=1&resize=9,9&format=tga"), (2, "page=1&format=png")]:
+            gif = io["gifs"][gi]
+            blob = orc.Ref.gif_container(gif["frames"])
+            code, step, out = orc.Ref.run_job_blob(q, blob)
+            c2, s2, o2 = _gif_job_restated(orc, gif, q)
+            assert code == c2 == 0, (q, code, step)
+            assert np.array_equal(out, o2), q
+    finally:
+        orc.Ref.use_cv2(False)
