@@ -82,6 +82,9 @@ __device__ __forceinline__ void area_rows(const uint8_t* __restrict__ col0, int 
     // the y taps of an output row are consecutive source rows: only the first index is looked up; the taps of the
     // tile were staged next to the pixels by the producer, so this loop touches no global memory at all
     const uint8_t* row = col0 + (size_t)(yt[0].si - py0) * rs;
+    // OpenCV assigns the first row's product and adds the rest; 0 + p == p exactly (p >= +0), so the sum starts at 0
+#pragma unroll
+    for (int c = 0; c < SC; c++) sum[c] = 0.0f;
     for (int j = 0; j < ycount; j++, row += rs) {
         const float beta = yt[j].a;
         float h[SC];
@@ -107,8 +110,7 @@ __device__ __forceinline__ void area_rows(const uint8_t* __restrict__ col0, int 
         }
 #pragma unroll
         for (int c = 0; c < SC; c++) {
-            const float pr = __fmul_rn(beta, h[c]);
-            sum[c] = (j == 0) ? pr : __fadd_rn(sum[c], pr);
+            sum[c] = __fadd_rn(sum[c], __fmul_rn(beta, h[c]));
         }
     }
 }
@@ -170,17 +172,29 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // Shared epilogue of the strip kernels: op list + store of one pixel. Inlined: an out-of-line call (v[] through
 // local memory + call/return) measured 12-20 % slower on cfg1/cfg2 than the larger code.
+// The destination address of base pixel (bx, by) is affine in by for a fixed bx under all eight output orientations
+// (dst + Y*pitch + X*dc with (X,Y) = imp_map_xy): a thread of a strip owns one bx, so it keeps {address of (bx,0), step
+// per by} instead of re-evaluating the frame map from the pass header for every pixel.
+struct StripStore { uint8_t* base; int step; };
+__device__ __forceinline__ StripStore strip_store_line(const ImpFrameMap& om, uint8_t* dst, int pitch, int dc, int bx) {
+    int X0, Y0, X1, Y1;
+    imp_map_xy(om, bx, 0, X0, Y0);
+    imp_map_xy(om, bx, 1, X1, Y1);
+    StripStore s;
+    s.base = dst + (ptrdiff_t)Y0 * pitch + (ptrdiff_t)X0 * dc;
+    s.step = (Y1 - Y0) * pitch + (X1 - X0) * dc;
+    return s;
+}
+
+// Shared epilogue of the strip kernels: op list + store of one pixel. Inlined: an out-of-line call (v[] through
+// local memory + call/return) measured 12-20 % slower on cfg1/cfg2 than the larger code.
 template <int SC>
-__device__ __forceinline__ void strip_epilogue(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* s_ops, int nops, int bx, int by, const int* v) {
+__device__ __forceinline__ void strip_epilogue(const ImpJob& job, int oc, int dc, const StripStore& st, const uint8_t* s_ops, int nops, int bx, int by, const int* v) {
     ImpPx p;
     if (SC == 1) { p.b = p.g = p.r = v[0]; p.a = 255; }
     else { p.b = v[0]; p.g = v[SC > 1 ? 1 : 0]; p.r = v[SC > 2 ? 2 : 0]; p.a = (SC == 4) ? v[SC - 1] : 255; }
-    const int oc = P->oc;
     if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
-    int X, Y;
-    imp_map_xy(P->out, bx, by, X, Y);
-    const int dc = P->dc;
-    uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * dc;
+    uint8_t* d = st.base + (ptrdiff_t)by * st.step;
     if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
     else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
 }
@@ -210,6 +224,8 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
 
     const int box_bytes = rs * P->tile_rows;
     const int ytap_bytes = (P->tile_ytaps * 8 + 15) & ~15;
+    const int oc = P->oc, dc = P->dc;
+    const StripStore st = strip_store_line(P->out, job.dst, job.dst_pitch, dc, bx);
     int stage = 0, phase = 0;
     for (int t = 0; t < tiles_y; t++) {
         const int by = min(t * TH + warp, bh - 1);
@@ -234,7 +250,7 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
-        if (in_x && in_y) strip_epilogue<SC>(job, P, s_ops, nops, bx, by, v);
+        if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
@@ -253,7 +269,7 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
     const int box_2x2 = (P->nx == 2 && ny == 2);
     const float box_scale = P->area_scale;
     const int my_off = col_off + bx * NT * SC;                        // byte offset of my first source pixel in a tile row
-    const ImpFrameMap om = P->out;
+    const StripStore st = strip_store_line(P->out, job.dst, job.dst_pitch, dc, bx);
     int stage = 0, phase = 0;
     for (int t = 0; t < tiles_y; t++) {
         const int by = min(t * TH + warp, bh - 1);
@@ -265,17 +281,7 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
         for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
-        if (in_x && in_y) {
-            ImpPx p;
-            if (SC == 1) { p.b = p.g = p.r = v[0]; p.a = 255; }
-            else { p.b = v[0]; p.g = v[SC > 1 ? 1 : 0]; p.r = v[SC > 2 ? 2 : 0]; p.a = (SC == 4) ? v[SC - 1] : 255; }
-            if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
-            int X, Y;
-            imp_map_xy(om, bx, by, X, Y);
-            uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * dc;
-            if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
-            else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
-        }
+        if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
@@ -502,17 +508,27 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
     const ImpFrameMap om = P->out;
     const int oc = P->oc, dc = P->dc;
     const int lane = tid & 31, wrp = tid >> 5;
-    for (int it = 0; it < BT / 8; it++) {
+    constexpr int NPX = BT / 8;                                        // pixels per thread: the op loop runs once over all of them
+    ImpPx px[NPX];
+    int bxs[NPX], bys[NPX];
+    bool live[NPX];
+#pragma unroll
+    for (int it = 0; it < NPX; it++) {
         const int u = wrp + it * 8;
         const int lx = om.swap ? u : lane, ly = om.swap ? lane : u;
         const int bx = x0 + lx, by = y0 + ly;
-        if (bx >= w || by >= h) continue;
-        const uint8_t* sp = stage + ly * SROW + lx * SC;
-        ImpPx p;
-        p.b = sp[0]; p.g = sp[1]; p.r = sp[2]; p.a = (SC == 4) ? sp[3 % SC] : 255;
-        if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+        live[it] = bx < w && by < h;
+        bxs[it] = min(bx, w - 1); bys[it] = min(by, h - 1);            // out-of-frame slots compute on a valid pixel, never stored
+        const uint8_t* sp = stage + (bys[it] - y0) * SROW + (bxs[it] - x0) * SC;
+        px[it].b = sp[0]; px[it].g = sp[1]; px[it].r = sp[2]; px[it].a = (SC == 4) ? sp[3 % SC] : 255;
+    }
+    if (nops) imp_run_ops_n<NPX>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+#pragma unroll
+    for (int it = 0; it < NPX; it++) {
+        if (!live[it]) continue;
+        const ImpPx& p = px[it];
         int X, Y;
-        imp_map_xy(om, bx, by, X, Y);
+        imp_map_xy(om, bxs[it], bys[it], X, Y);
         uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * dc;
         if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
         else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
