@@ -170,8 +170,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Shared epilogue of the strip kernels: op list + store of one pixel. Inlined: an out-of-line call (v[] through
-// local memory + call/return) measured 12-20 % slower on cfg1/cfg2 than the larger code.
 // The destination address of base pixel (bx, by) is affine in by for a fixed bx under all eight output orientations
 // (dst + Y*pitch + X*dc with (X,Y) = imp_map_xy): a thread of a strip owns one bx, so it keeps {address of (bx,0), step
 // per by} instead of re-evaluating the frame map from the pass header for every pixel.
@@ -186,14 +184,34 @@ __device__ __forceinline__ StripStore strip_store_line(const ImpFrameMap& om, ui
     return s;
 }
 
+// Rows of column bx on which the op list can change a pixel. A list made only of watermarks (the common request:
+// resize + watermark) touches nothing outside the watermark rectangles, so a thread asks once per strip for the
+// by-interval its column shares with them and skips the op loop elsewhere. Any other op -> every row.
+struct StripOpsRows { int y0, y1; };
+__device__ __forceinline__ StripOpsRows strip_ops_rows(const uint8_t* s_ops, int nops, int bx) {
+    StripOpsRows r; r.y0 = 0x7fffffff; r.y1 = -1;
+    const ImpOp* ops = reinterpret_cast<const ImpOp*>(s_ops);
+    for (int k = 0; k < nops; k++) {
+        const ImpOp& op = ops[k];
+        if (op.kind != IMP_OP_WATERMARK) { r.y0 = 0; r.y1 = 0x7fffffff; return r; }
+        // watermark rectangle [i0, i0+i2) x [i1, i1+i3) of the op's frame, pulled back through imp_map_xy
+        const ImpFrameMap m = op.map;
+        const int ulo = m.flipx ? m.w - op.i[0] - op.i[2] : op.i[0], uhi = ulo + op.i[2] - 1;
+        const int vlo = m.flipy ? m.h - op.i[1] - op.i[3] : op.i[1], vhi = vlo + op.i[3] - 1;
+        const int xlo = m.swap ? vlo : ulo, xhi = m.swap ? vhi : uhi, ylo = m.swap ? ulo : vlo, yhi = m.swap ? uhi : vhi;
+        if (bx >= xlo && bx <= xhi) { r.y0 = min(r.y0, ylo); r.y1 = max(r.y1, yhi); }
+    }
+    return r;
+}
+
 // Shared epilogue of the strip kernels: op list + store of one pixel. Inlined: an out-of-line call (v[] through
 // local memory + call/return) measured 12-20 % slower on cfg1/cfg2 than the larger code.
 template <int SC>
-__device__ __forceinline__ void strip_epilogue(const ImpJob& job, int oc, int dc, const StripStore& st, const uint8_t* s_ops, int nops, int bx, int by, const int* v) {
+__device__ __forceinline__ void strip_epilogue(const ImpJob& job, int oc, int dc, const StripStore& st, const StripOpsRows& orows, const uint8_t* s_ops, int nops, int bx, int by, const int* v) {
     ImpPx p;
     if (SC == 1) { p.b = p.g = p.r = v[0]; p.a = 255; }
     else { p.b = v[0]; p.g = v[SC > 1 ? 1 : 0]; p.r = v[SC > 2 ? 2 : 0]; p.a = (SC == 4) ? v[SC - 1] : 255; }
-    if (nops) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+    if (by >= orows.y0 && by <= orows.y1) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
     uint8_t* d = st.base + (ptrdiff_t)by * st.step;
     if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
     else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
@@ -226,6 +244,7 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
     const int ytap_bytes = (P->tile_ytaps * 8 + 15) & ~15;
     const int oc = P->oc, dc = P->dc;
     const StripStore st = strip_store_line(P->out, job.dst, job.dst_pitch, dc, bx);
+    const StripOpsRows orows = strip_ops_rows(s_ops, nops, bx);
     int stage = 0, phase = 0;
     for (int t = 0; t < tiles_y; t++) {
         const int by = min(t * TH + warp, bh - 1);
@@ -250,7 +269,7 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
-        if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, s_ops, nops, bx, by, v);
+        if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
@@ -270,6 +289,7 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
     const float box_scale = P->area_scale;
     const int my_off = col_off + bx * NT * SC;                        // byte offset of my first source pixel in a tile row
     const StripStore st = strip_store_line(P->out, job.dst, job.dst_pitch, dc, bx);
+    const StripOpsRows orows = strip_ops_rows(s_ops, nops, bx);
     int stage = 0, phase = 0;
     for (int t = 0; t < tiles_y; t++) {
         const int by = min(t * TH + warp, bh - 1);
@@ -281,7 +301,7 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
         for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
-        if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, s_ops, nops, bx, by, v);
+        if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }

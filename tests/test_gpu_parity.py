@@ -388,3 +388,25 @@ def test_gif_expand_and_pack_golden_from_reference(gpu, orc):
         rq["pack"] = {"tga": 32, "ppm": 24}.get(fmt, 0)            # bridge.c:680: FIF_BMP == 0 leaves through cvEncodeImage
         code, _, out = _gpu_run(gpu, canvas, {}, rq)
         assert code == 0 and np.array_equal(out, job["out"]), job["query"]
+
+
+def test_strip_kernels_watermark_under_all_orientations(gpu, orc):
+    """INTER_AREA (fractional and integer: the strip kernels) + each of the eight output orientations + a watermark at
+    several gravities: the strip epilogue pulls the watermark rectangle back into the base frame to skip untouched rows
+    and keeps an affine store line per column, both of which depend on the orientation."""
+    wm = rnd_image(5, 9, 13, 4)
+    orient = [[], ["flip=10"], ["flip=01"], ["flip=11"], ["rotate=90"], ["rotate=180"], ["rotate=270"], ["rotate=90", "flip=10"], ["flip=01", "rotate=270"]]
+    for (h, w, c) in [(96, 160, 4), (90, 150, 3)]:
+        img = smooth_image(h + c, h, w, c)
+        for resize in ("50,31", "53,30", None):                    # fractional, integer 3x3 (150x90 -> 50x30 only for the 3-ch frame), none
+            for gx, gy, ox, oy in [("r", "b", 3, 2), ("l", "t", 0, 0), ("c", "c", -4, 5), ("r", "t", 40, 1)]:
+                kw = dict(watermark=wm, wm_gravity_x=gx, wm_gravity_y=gy, wm_offset_x=ox, wm_offset_y=oy, wm_opacity=70)
+                for fl in orient:
+                    rq = dict(resize=resize, filters=fl) if resize else dict(filters=fl)
+                    if resize == "53,30":
+                        rq["resize"] = "50,30" if (w, h) == (150, 90) else "40,24"
+                    code, _, out = _gpu_run(gpu, img, kw, rq)
+                    c2, _, ref = _oracle(orc, img, rq, kw)
+                    assert code == c2, (rq, kw, code, c2)
+                    if code == 0:
+                        _assert_same(out, ref, (rq, gx, gy, ox, oy), False)
