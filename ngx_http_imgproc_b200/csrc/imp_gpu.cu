@@ -234,7 +234,7 @@ int variant_param(const ImpPass& h, int variant);
 int variant_smem(const ImpPass& h, int variant, int param);
 int variant_tiles(const ImpPass& h, int variant);
 int tile_stage_bytes(const ImpPass& h) {
-    const int extra = h.kind == IMP_G_AREA_FRAC ? (((h.tile_ytaps * 8 + 15) & ~15) + 64) : 0;     // staged y taps + ranges
+    const int extra = h.kind == IMP_G_AREA_FRAC ? (((h.tile_ytaps * 8 + 15) & ~15) + 128) : 0;    // staged y taps + the 8 rows' int4 descriptors
     return (h.tile_smem + extra + 127) & ~127;
 }
 // three ring stages while three CTAs still fit an SM's shared memory, else two

@@ -78,6 +78,7 @@ struct ImpPass {
     int tile_smem;            // tile kernels: source-tile bytes (tile_rs*tile_rows); 0 = no tile variant for this pass
     int xtile_off, ytile_off; // tile kernels: int2 per tile column {first px, last px}; int4 per tile row {first src row, rows, first y tap, y taps}
     int tile_ytaps;           // strip kernel: y-tap entries staged per tile (max over tiles, incl. alignment slack)
+    int yrow4_off;            // strip kernel: int4 per output row {byte offset of its first source row inside the tile, y taps, index of its first tap in the tile's staged taps, 0}
     int nops;
     int ops_off;              // ImpOp[nops]
     int lut_off, lut_bytes;   // LUT area (gamma 256 B each, gradmap 768 B each)

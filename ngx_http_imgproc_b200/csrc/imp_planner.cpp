@@ -548,6 +548,18 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
                 P.tile_rows = rows;
                 P.tile_smem = (P.max_xtaps <= 12 && P.tile_rs <= 2048 && rows <= 256 && (long long)P.tile_rs * rows <= 100 * 1024 &&
                                (!fast || isx * isy <= 256)) ? P.tile_rs * rows : 0;
+                {
+                    // what a consumer warp needs to start an output row, relative to the tile it is staged with
+                    std::vector<int> yrow4;
+                    const int padded = (rh + 7) & ~7;              // the producer always copies 8 entries
+                    for (int y = 0; y < padded; y++) {
+                        const int yy = std::min(y, rh - 1), t = yy / 8;
+                        const int p0 = ytile[t * 4], tapbase = ytile[t * 4 + 2] & ~1;
+                        yrow4.push_back((yt[yr[yy].first].si - p0) * P.tile_rs); yrow4.push_back(yr[yy].count);
+                        yrow4.push_back(yr[yy].first - tapbase); yrow4.push_back(0);
+                    }
+                    P.yrow4_off = L.bb.add(yrow4.data(), yrow4.size() * 4);
+                }
                 P.xofs_off = L.bb.add(xr.data(), xr.size() * sizeof(Range));
                 P.xcoef_off = L.bb.add(xt.data(), xt.size() * sizeof(AreaTap));
                 P.yofs_off = L.bb.add(yr.data(), yr.size() * sizeof(Range));

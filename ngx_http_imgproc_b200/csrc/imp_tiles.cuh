@@ -77,11 +77,10 @@ constexpr int MAX_SMEM = 96 * 1024;     // source-tile budget per CTA
 // leaves a running float sum bit-identical, so the result equals OpenCV's ordered accumulation.
 // (A padded tap may read a byte past the staged pixels; any byte converts to a finite float.)
 template <int SC, int NT>
-__device__ __forceinline__ void area_rows(const uint8_t* __restrict__ col0, int rs, int py0, const ImpAreaTap* yt /* shared memory */, int ycount,
+__device__ __forceinline__ void area_rows(const uint8_t* __restrict__ row /* first source row, my first tap */, int rs, const ImpAreaTap* yt /* shared memory */, int ycount,
                                           const float (&a)[NT], const float (&na)[NT], float (&sum)[SC]) {
-    // the y taps of an output row are consecutive source rows: only the first index is looked up; the taps of the
-    // tile were staged next to the pixels by the producer, so this loop touches no global memory at all
-    const uint8_t* row = col0 + (size_t)(yt[0].si - py0) * rs;
+    // the y taps of an output row are consecutive source rows and were staged next to the pixels by the producer, so
+    // this loop touches no global memory at all
     // OpenCV assigns the first row's product and adds the rest; 0 + p == p exactly (p >= +0), so the sum starts at 0
 #pragma unroll
     for (int c = 0; c < SC; c++) sum[c] = 0.0f;
@@ -251,15 +250,13 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
         const bool in_y = t * TH + warp < bh;
         mbar_wait(full + stage, phase);
         const uint8_t* sbase = tile0 + stage * stage_bytes;
-        const ImpAreaTap* s_yt = reinterpret_cast<const ImpAreaTap*>(sbase + box_bytes);              // taps [tapbase ..) of this tile
-        const int2* s_yr = reinterpret_cast<const int2*>(sbase + box_bytes + ytap_bytes);          // ranges of the tile's 8 output rows
-        const int tap_first = s_yr[0].x, tapbase = tap_first & ~1;
-        const int2 ryv = s_yr[by - t * TH];
-        const int py0 = s_yt[tap_first - tapbase].si;                                              // first source row of the tile
+        const ImpAreaTap* s_yt = reinterpret_cast<const ImpAreaTap*>(sbase + box_bytes);              // the tile's y taps
+        // {byte offset of my first source row in the tile, taps, first tap}: one 16-byte load starts the row
+        const int4 yrow = reinterpret_cast<const int4*>(sbase + box_bytes + ytap_bytes)[by - t * TH];
         int v[SC];
         if (MODE == 0) {
             float sum[SC];
-            area_rows<SC, (MODE == 0 ? NT : 1)>(sbase + my_off, rs, py0, s_yt + (ryv.x - tapbase), ryv.y, a, na, sum);
+            area_rows<SC, (MODE == 0 ? NT : 1)>(sbase + my_off + yrow.x, rs, s_yt + yrow.z, yrow.y, a, na, sum);
 #pragma unroll
             for (int c = 0; c < SC; c++) v[c] = min(rint_pos(sum[c]), 255);          // sums are >= 0
         } else {
@@ -331,7 +328,7 @@ imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
     const int rs = P->tile_rs;
     // stage = [pixel box][y taps of the tile][y ranges of its 8 output rows] (the last two only in fractional mode)
     const int ytap_bytes = (MODE == 0) ? ((P->tile_ytaps * 8 + 15) & ~15) : 0;
-    const int stage_bytes = (rs * P->tile_rows + ytap_bytes + (MODE == 0 ? 64 : 0) + 127) & ~127;
+    const int stage_bytes = (rs * P->tile_rows + ytap_bytes + (MODE == 0 ? 128 : 0) + 127) & ~127;
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 1); mbar_init(empty + i, TH); }
@@ -352,7 +349,7 @@ imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
         if (tid == STRIP_CONSUMERS) {
             const int4* __restrict__ ytile = reinterpret_cast<const int4*>(blob + P->ytile_off);
             const uint8_t* __restrict__ g_yt = blob + P->ycoef_off;
-            const uint8_t* __restrict__ g_yr = blob + P->yofs_off;
+            const uint8_t* __restrict__ g_yr = blob + P->yrow4_off;
             const uint32_t box_bytes = (uint32_t)(rs * P->tile_rows);
             int stage = 0, phase = 0;
             for (int t = 0; t < tiles_y; t++) {
@@ -364,10 +361,10 @@ imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
                     // loops never leave shared memory
                     const int tapbase = yt4.z & ~1;
                     const uint32_t tapbytes = (uint32_t)(((yt4.w + (yt4.z & 1)) * 8 + 15) & ~15);
-                    mbar_expect_tx(full + stage, box_bytes + tapbytes + 64u);
+                    mbar_expect_tx(full + stage, box_bytes + tapbytes + 128u);
                     tma_load_2d(sdst, jp->tmap, c0, yt4.x, full + stage);
                     bulk_g2s(sdst + box_bytes, g_yt + (size_t)tapbase * 8, tapbytes, full + stage);
-                    bulk_g2s(sdst + box_bytes + ytap_bytes, g_yr + (size_t)t * TH * 8, 64u, full + stage);
+                    bulk_g2s(sdst + box_bytes + ytap_bytes, g_yr + (size_t)t * TH * 16, 128u, full + stage);
                 } else {
                     mbar_expect_tx(full + stage, box_bytes);
                     tma_load_2d(sdst, jp->tmap, c0, yt4.x, full + stage);
