@@ -237,13 +237,12 @@ int tile_stage_bytes(const ImpPass& h) {
     const int extra = h.kind == IMP_G_AREA_FRAC ? (((h.tile_ytaps * 8 + 15) & ~15) + 128) : 0;    // staged y taps + the 8 rows' int4 descriptors
     return (h.tile_smem + extra + 127) & ~127;
 }
-// three ring stages while three CTAs still fit an SM's shared memory, else two
-// Ring depth: as many stages as fit ~64 KB (so three CTAs still share an SM), between 2 and 8. Small tiles
-// (cfg1: 7 KB) need the depth to keep enough bytes in flight; big ones (cfg2: 23 KB) are fine with 2.
+// Ring depth: as many stages as fit 72 KB (three CTAs of 72 KB + ops still share an SM's 227 KB), between 2 and 8.
+// Small tiles (cfg1: 7 KB) need the depth to keep enough bytes in flight; cfg2's 23.7 KB stage gets 3 (1.5 % over 2).
 int tile_stages(const ImpPass& h) {
     static const int forced = [] { const char* e = getenv("IMP_GPU_STAGES"); return e ? atoi(e) : 0; }();     // tuning knob
     if (forced >= 2 && forced <= 8) return forced;
-    return std::max(2, std::min(8, (64 * 1024) / tile_stage_bytes(h)));
+    return std::max(2, std::min(8, (72 * 1024) / tile_stage_bytes(h)));
 }
 int tile_smem_bytes(const ImpPass& h, int stages) {
     const int ops = (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15;
