@@ -57,8 +57,11 @@ __device__ __forceinline__ float u8_times(uint32_t byte, float a, float neg_a23)
 template <int NB>
 __device__ __forceinline__ void load_bytes(const uint8_t* p, uint32_t (&w)[(NB + 3) / 4]) {
     constexpr int NW = (NB + 3) / 4;
-    const uint32_t* base = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(3));
-    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+    // plain pointer arithmetic (no integer round trip), so the compiler still knows these are shared-memory loads (LDS,
+    // 32-bit addresses) — through uintptr_t they became generic LD.E with 64-bit address maths
+    const unsigned mis = smem_u32(p) & 3u;
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(p - mis);
+    const unsigned sh = mis * 8;
     uint32_t raw[NW + 1];
 #pragma unroll
     for (int i = 0; i <= NW; i++) raw[i] = base[i];
@@ -293,7 +296,7 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
         const bool in_y = t * TH + warp < bh;
         mbar_wait(full + stage, phase);
         int v[SC];
-        area_int_rows<SC, NT>(tile0 + stage * stage_bytes + my_off + (size_t)(by * ny - t * TH * ny) * rs, rs, ny, v);
+        area_int_rows<SC, NT>(tile0 + (stage * stage_bytes + my_off + (by * ny - t * TH * ny) * rs), rs, ny, v);
 #pragma unroll
         for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
         __syncwarp();
