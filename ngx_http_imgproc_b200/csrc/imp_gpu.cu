@@ -254,7 +254,10 @@ int variant_smem(const ImpPass& h, int variant, int param) {
     return variant == 1 ? tile_smem_bytes(h, param) : variant == 2 ? blur_smem_bytes(h) : ops_smem(h);
 }
 int variant_tiles(const ImpPass& h, int variant) {
-    return variant == 1 ? (h.bw + 31) / 32 : (variant == 2 || variant == 3) ? ((h.bw + 31) / 32) * ((h.bh + 31) / 32) : pass_tiles(h);
+    if (variant == 1) return (h.bw + 31) / 32;
+    if (variant == 2) return ((h.bw + 31) / 32) * ((h.bh + 31) / 32);
+    if (variant == 3) return ((h.bw + 31) / 32) * ((h.bh + 8 * IMP_CUBIC_RUN - 1) / (8 * IMP_CUBIC_RUN));
+    return pass_tiles(h);
 }
 
 int batch_compile(imp_gpu_batch* b) {

@@ -41,6 +41,7 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
                    imp_gpu_plan* plan, int* step);
 
 // imp_kernels.cu
+#define IMP_CUBIC_RUN 8           // imp_cubic_run_kernel: output rows per thread; a CTA covers 32 x (8 * IMP_CUBIC_RUN) pixels
 struct ImpLaunchGroup {
     int kind, sc;                // kernel variant
     int first, count;            // jobs [first, first+count) of the device job table

@@ -283,7 +283,7 @@ imp_pass_kernel(const ImpJob* __restrict__ jobs, int first, int count, const Imp
 // down the run: at 2x upscale that is ~1.4 horizontal rows per output instead of 4. The window is held as floats
 // (the conversion is exact, |H| < 2^22) because the vertical pass of every byte below simd_end is OpenCV's float
 // form; the last <8 bytes of a row take the integer form through the generic per-pixel gather.
-constexpr int CUBIC_RUN = 4;
+constexpr int CUBIC_RUN = IMP_CUBIC_RUN;      // imp_internal.h (the host sizes the grid with it)
 
 template <int SC>
 __device__ __forceinline__ void cubic_hrow(const ImpSrcGlobal<SC>& S, const int (&sx)[4], int sy, int a0, int a1, int a2, int a3, float (&hf)[SC]) {
@@ -367,18 +367,24 @@ imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
         promote<SC>(v, p);
         q[o] = (unsigned)p.b | ((unsigned)p.g << 8) | ((unsigned)p.r << 16) | ((unsigned)p.a << 24);
     }
-    ImpPx px[CUBIC_RUN];
-    int bxs[CUBIC_RUN], bys[CUBIC_RUN];
+    // op list + store, four pixels at a time (the op loop is the outer loop inside imp_run_ops_n)
 #pragma unroll
-    for (int o = 0; o < CUBIC_RUN; o++) {
-        bxs[o] = bx; bys[o] = min(by0 + o, bh - 1);
-        px[o].b = q[o] & 255; px[o].g = (q[o] >> 8) & 255; px[o].r = (q[o] >> 16) & 255; px[o].a = q[o] >> 24;
-    }
-    if (nops) imp_run_ops_n<CUBIC_RUN>(px, oc, bxs, bys, os.ops, nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
+    for (int g = 0; g < CUBIC_RUN; g += 4) {
+        if (by0 + g >= bh) break;
+        ImpPx px[4];
+        int bxs[4], bys[4];
 #pragma unroll
-    for (int o = 0; o < CUBIC_RUN; o++) {
-        if (by0 + o >= bh) break;
-        if (dc == 4) store_px<4>(job, P, bx, by0 + o, px[o]); else store_px<3>(job, P, bx, by0 + o, px[o]);
+        for (int o = 0; o < 4; o++) {
+            const unsigned w = q[g + o];
+            bxs[o] = bx; bys[o] = min(by0 + g + o, bh - 1);
+            px[o].b = w & 255; px[o].g = (w >> 8) & 255; px[o].r = (w >> 16) & 255; px[o].a = w >> 24;
+        }
+        if (nops) imp_run_ops_n<4>(px, oc, bxs, bys, os.ops, nops, os.lut, job.wm, job.wm_pitch, job.wm_c);
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            if (by0 + g + o >= bh) break;
+            if (dc == 4) store_px<4>(job, P, bx, by0 + g + o, px[o]); else store_px<3>(job, P, bx, by0 + g + o, px[o]);
+        }
     }
 }
 

@@ -135,6 +135,12 @@ IMP_HD int imp_modulate_scale(int c, int k) {
 }
 
 IMP_HD void imp_op_modulate(ImpPx& p, int dh, int ks, int kv) {
+    if (ks == 0) {
+        // saturation factor 0 ("sepia" = modulate=..,0,.. + colorize): S becomes 0 whatever it was, and HSV2RGB's S == 0
+        // branch (helpers.c:117) returns (V,V,V) whatever the hue, with V = max(B,G,R) scaled. Same bytes, no divisions.
+        p.b = p.g = p.r = imp_modulate_scale(imp_max(p.b, imp_max(p.g, p.r)), kv);
+        return;
+    }
     int h, s, v;
     imp_rgb2hsv(p.b, p.g, p.r, h, s, v);
     if (dh != 0) { h += dh; if (h > 180) h -= 180; h &= 255; }

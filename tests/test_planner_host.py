@@ -48,7 +48,8 @@ REQS = [dict(resize="30,20"), dict(crop="1,1"), dict(crop="16,9,l,t"), dict(crop
         dict(resize="31,17", filters=["rotate=270", "vignette=0.9,0.8"]), dict(resize="40,20"), dict(resize="20,15"), dict(resize="40,60"),
         dict(resize="16,12", interp=1), dict(resize="100,77,up", interp=1), dict(resize="32,24", interp=1),
         dict(filters=["blur=0"]), dict(filters=["scanline=,"]), dict(filters=["gradmap=306090"]), dict(filters=["vignette=,"]),
-        dict(filters=["contrast=1e30"]), dict(filters=["modulate=0,-50,100"]), dict(filters=["gamma=0"]), dict(filters=["gamma=-1"]),
+        dict(filters=["contrast=1e30"]), dict(filters=["modulate=0,-50,100"]), dict(filters=["modulate=77,0,250"]), dict(filters=["modulate=10,0,-30"]),
+        dict(filters=["modulate=180,0,0"]), dict(filters=["modulate=0,0,99", "modulate=5,100,100"]), dict(filters=["gamma=0"]), dict(filters=["gamma=-1"]),
         # encoder-side packing (advancedio.c:65-101): bottom-up 24/32-bit
         dict(resize="40,30", pack=24), dict(resize="40,30", pack=32), dict(filters=["rotate=90", "blur=1.2"], pack=32),
         dict(crop="1,1", filters=["flip=10"], pack=24, flatten=True)]
