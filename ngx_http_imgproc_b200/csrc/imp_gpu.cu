@@ -281,7 +281,14 @@ int batch_compile(imp_gpu_batch* b) {
         CK(cudaMalloc((void**)&b->d_scratch, scratch));
         b->scratch_cap = scratch;
     }
-    struct Pending { int kind, sc, variant, tmax; ImpJob job; ImpPass hdr; size_t boff; };
+    // `occ`: how many CTAs of the job's shared-memory footprint fit an SM (capped at the 3 the register budget allows).
+    // A launch takes the largest footprint of its group, so strip jobs are grouped by this class as well: a few big
+    // tiles must not drag thousands of small ones down to two CTAs per SM.
+    struct Pending { int kind, sc, variant, tmax, occ; ImpJob job; ImpPass hdr; size_t boff; };
+    auto occ_class = [](const ImpPass& h, int variant, int param) {
+        if (variant != 1) return 0;
+        return std::max(1, std::min(3, (227 * 1024) / (variant_smem(h, variant, param) + 1024)));
+    };
     for (int k = 0; k < max_passes; k++) {
         std::vector<Pending> pend;
         for (size_t i = 0; i < b->items.size(); i++) {
@@ -291,17 +298,19 @@ int batch_compile(imp_gpu_batch* b) {
             ImpJob jb = make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->d_scratch, off[i]);
             const int variant = pick_variant(hp.hdr, jb);
             if (variant == 1 || variant == 2) { int rc = encode_job_tmap(hp.hdr, jb); if (rc) return rc; }
-            pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, variant_param(hp.hdr, variant), jb, hp.hdr, boff[i][k]});
+            const int param = variant_param(hp.hdr, variant);
+            pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, param, occ_class(hp.hdr, variant, param), jb, hp.hdr, boff[i][k]});
         }
         std::stable_sort(pend.begin(), pend.end(), [](const Pending& a, const Pending& c) {
             if (a.kind != c.kind) return a.kind < c.kind;
             if (a.sc != c.sc) return a.sc < c.sc;
             if (a.variant != c.variant) return a.variant < c.variant;
-            return a.tmax < c.tmax; });
+            if (a.tmax != c.tmax) return a.tmax < c.tmax;
+            return a.occ < c.occ; });
         size_t s = 0;
         while (s < pend.size()) {
             size_t e = s;
-            while (e < pend.size() && pend[e].kind == pend[s].kind && pend[e].sc == pend[s].sc && pend[e].variant == pend[s].variant && pend[e].tmax == pend[s].tmax) e++;
+            while (e < pend.size() && pend[e].kind == pend[s].kind && pend[e].sc == pend[s].sc && pend[e].variant == pend[s].variant && pend[e].tmax == pend[s].tmax && pend[e].occ == pend[s].occ) e++;
             if (pend[s].kind == IMP_G_BLUR && pend[s].variant == 0) {
                 for (size_t j = s; j < e; j++) {
                     imp_gpu_batch::Step st{};
