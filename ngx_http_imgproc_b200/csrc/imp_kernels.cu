@@ -6,6 +6,7 @@
 // flip/rotate map. A whole batch (GIF frames, concurrent requests) is one launch per kernel variant:
 // grid = (tiles, jobs). See DESIGN.md §Kernels for the roofline of each variant.
 #include "imp_internal.h"
+#include <algorithm>
 #include "imp_gather.cuh"
 #include "imp_tiles.cuh"
 
@@ -461,7 +462,7 @@ cudaError_t launch_kind(const ImpLaunchGroup& g, const ImpJob* d_jobs, const Imp
 
 template <int SC, int MODE>
 cudaError_t launch_area_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
-    static bool attr_set[16] = {false};
+    static std::atomic<bool> attr_set[16];                 // per device; setting the attribute twice is harmless
     int dev = 0; cudaGetDevice(&dev);
     auto kern = imp_tiles::imp_area_strip_kernel<SC, MODE>;
     if (!attr_set[dev & 15]) {
@@ -478,7 +479,7 @@ cudaError_t launch_area_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, cons
 
 template <int SC, int R>
 cudaError_t launch_blur_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
-    static bool attr_set[16] = {false};
+    static std::atomic<bool> attr_set[16];                 // per device; setting the attribute twice is harmless
     int dev = 0; cudaGetDevice(&dev);
     auto kern = imp_tiles::imp_blur_tile_kernel<SC, R>;
     if (!attr_set[dev & 15]) {
