@@ -15,7 +15,7 @@
  *   int Filter(IplImage**, char*, int)       filters.c:43  imp_Filter
  *   int Watermark(IplImage*, Config*)        bridge.c:239  imp_Watermark
  *   void BlendWithPaper(IplImage*)           filters.c:666 imp_BlendWithPaper
- *   gray->BGR block                          bridge.c:613-618  implicit (a 1-channel frame leaves the chain as BGR)
+ *   gray->BGR block                          bridge.c:613-618  implicit (a 1-channel frame leaves imp_Flush as BGR, also when nothing was recorded)
  *   (none)                                   before bridge.c:659   imp_Flush / imp_FlushAll
  *   cvReleaseImage on an error path          bridge.c:714-722  imp_Discard first
  *

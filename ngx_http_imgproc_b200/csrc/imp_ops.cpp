@@ -191,8 +191,11 @@ int imp_FlushAll(IplImage** frames, int count) {
         for (int i = 0; i < count && rc == IMP_OK; i++) {
             if (!frames[i]) continue;
             auto it = g_pending.find(frames[i]);
-            if (it == g_pending.end() || it->second.n_ops == 0) { if (it != g_pending.end()) g_pending.erase(it); continue; }
-            Pending& p = it->second;
+            const bool idle = it == g_pending.end() || it->second.n_ops == 0;
+            // bridge.c:613-618 turns EVERY 1-channel frame into BGR at the filter step, even when no operator was asked for:
+            // such a frame still takes the (empty) plan, whose store promotes gray to B,G,R
+            if (idle && frames[i]->nChannels != 1) { if (it != g_pending.end()) g_pending.erase(it); continue; }
+            Pending& p = idle ? entry(frames[i]) : it->second;
             imp_gpu_plan* plan = nullptr; IplImage* out = nullptr;
             rc = run_one(&frames[i], p, &plan, &out);
             if (rc) break;

@@ -924,6 +924,7 @@ class Ref:
                                   C.byref(n), C.byref(step), C.byref(mime))
         img = None
         raw = out[:n.value].tobytes()
+        cls.last_raw = raw                      # the encoded bytes as RunJob returned them (e.g. the multi-page container)
         if code == 0 and raw[8:12] == b"IMPR":
             w, h, ch = struct.unpack("<3i", raw[12:24])
             img = np.frombuffer(raw, np.uint8, w * h * ch, 24).reshape(h, w, ch).copy()
@@ -931,3 +932,28 @@ class Ref:
             w, h, bpp, pitch = struct.unpack("<4i", raw[8:24])
             img = np.frombuffer(raw, np.uint8, pitch * h, 24).reshape(h, pitch)[:, :w * bpp // 8].reshape(h, w, bpp // 8).copy()
         return code, step.value, img
+
+
+class RefGpu(Ref):
+    """The reference with INTEGRATION.md's edits applied (oracle/make_gpu_bridge.py): its own RunJob, FiLoadFrames and
+    encoders, but steps 3-7 call imp_Crop / imp_Resize / imp_Filter / imp_Watermark / imp_BlendWithPaper + imp_FlushAll of
+    libimp_gpu.so. Needs a GPU at run time; `available()` only says the prebuilt library travels with the repo."""
+    _lib = None
+    _cbs = None
+    _started = False
+
+    @classmethod
+    def path(cls):
+        return os.path.join(HERE, "_ref", "libimp_ref_gpu.so")
+
+    @classmethod
+    def available(cls) -> bool:
+        return os.path.exists(cls.path())
+
+    @classmethod
+    def lib(cls):
+        L = super().lib()
+        if not cls._started:
+            L.OnEnvStart()                # bridge.c:10 with the edit: imp_gpu_init(0) + the frame allocator
+            cls._started = True
+        return L

@@ -410,3 +410,48 @@ def test_strip_kernels_watermark_under_all_orientations(gpu, orc):
                     assert code == c2, (rq, kw, code, c2)
                     if code == 0:
                         _assert_same(out, ref, (rq, gx, gy, ox, oy), False)
+
+
+def test_reference_runjob_with_the_gpu_path_dropped_in(gpu, orc):
+    """The drop-in claim, executed: the reference's OWN RunJob (bridge.c:302-724), decode and encode included, compiled
+    with INTEGRATION.md's call-site edits and linked against libimp_gpu.so (oracle/make_gpu_bridge.py ->
+    oracle/_ref/libimp_ref_gpu.so), against the unmodified CPU build of the same sources (libimp_ref.so): same code,
+    same failing step, same bytes, for single frames and for multi-frame GIF containers."""
+    if not (orc.RefGpu.available() and orc.Ref.available()):
+        pytest.skip("prebuilt oracle/_ref libraries not present on this box")
+    from test_oracle import QUERIES
+    wm = rnd_image(7, 12, 20, 4)
+    cfgs = [orc.OracleConfig(), orc.OracleConfig(allow_experiments=True, max_filters=8),
+            orc.OracleConfig(allow_experiments=True, max_filters=8, watermark=wm, wm_gravity_x="r", wm_gravity_y="b", wm_offset_x=3, wm_offset_y=2, wm_opacity=60)]
+    checked = 0
+    for (h, w, c) in [(60, 80, 3), (45, 64, 4), (33, 47, 1)]:
+        img = smooth_image(h, h, w, c)
+        for cfg in cfgs:
+            for q in QUERIES:
+                pc, p = orc.parse_query(q, cfg)
+                # the CPU reference double-frees a frame when a filter fails after gray->BGR / flip / rotate (bridge.c:609-627)
+                if not pc:
+                    c2, s2, _ = orc.run_chain(img, p["crop"], p["gravity"], p["resize"], p["filters"], cfg, False, flatten=(p["format"] == "jpg"))
+                    if c2 and s2 == orc.STEP_FILTERING and (c == 1 or any(f and (f.startswith("flip") or f.startswith("rotate")) for f in p["filters"])):
+                        continue
+                code, step, ref = orc.Ref.run_job(q, img, cfg)
+                gcode, gstep, out = orc.RefGpu.run_job(q, img, cfg)
+                assert (gcode, gstep) == (code, step), (q, (h, w, c), gcode, gstep, code, step)
+                if code == 0 and ref is not None:
+                    _assert_same(out, ref, (q, (h, w, c)), "vignette" in q)
+                    checked += 1
+    io = G.load_io()
+    for gi, q in [(1, "page=5&resize=33,21&filter-modulate=0,0,100&filter-colorize=704214,0.6&format=png"), (4, "page=3&crop=16,9&gravity=r,b&resize=40&format=bmp"),
+                  (0, "page=2&filter-flip=10&filter-gamma=0.8&format=ppm"), (1, "page=6&resize=200,150,up&format=jpg"), (3, "page=1&resize=9,9&format=tga"),
+                  (2, "page=1&format=png"), (0, "resize=24,14&format=gif"), (4, "filter-rotate=90&format=gif")]:
+        blob = orc.Ref.gif_container(io["gifs"][gi]["frames"])
+        code, step, ref = orc.Ref.run_job_blob(q, blob)
+        raw = orc.Ref.last_raw
+        gcode, gstep, out = orc.RefGpu.run_job_blob(q, blob)
+        assert (gcode, gstep) == (code, step) and code == 0, (q, gcode, gstep, code, step)
+        if ref is not None:
+            _assert_same(out, ref, q, False)
+        else:                                   # format=gif: every frame, through SaveGIF's (stand-in) quantiser
+            assert len(raw) > 12 and orc.RefGpu.last_raw == raw, q
+        checked += 1
+    assert checked > 150

@@ -130,3 +130,23 @@ def test_flush_all_frames_of_an_album(gpu, orc):
     for i, f in enumerate(frames):
         code, step, ref = orc.run_chain(f, None, None, "192,108,up", ["gamma=1.3"], orc.OracleConfig(max_w=0, max_h=0))
         assert np.array_equal(_to_np(arr[i]), ref)
+
+
+@pytest.mark.gpu
+def test_gray_frame_with_no_operator_still_leaves_as_bgr(gpu, orc):
+    """bridge.c:613-618 converts every 1-channel frame at the filter step even when no operator was requested; the flush
+    does the same (found by running the reference's RunJob over the GPU path, test_reference_runjob_with_the_gpu_path_dropped_in)."""
+    L = _lib()
+    img = rnd_image(9, 21, 34, 1)
+    im, keep = _ipl(img)
+    p = C.pointer(im)
+    assert L.imp_ops_pending(p) == 0
+    assert L.imp_Flush(C.byref(p)) == 0
+    out = _to_np(p)
+    assert out.shape == (21, 34, 3) and np.array_equal(out, np.repeat(img, 3, axis=2))
+    img3 = rnd_image(10, 21, 34, 3)
+    im3, keep3 = _ipl(img3)
+    p3 = C.pointer(im3)
+    before = gpu.launch_count()
+    assert L.imp_Flush(C.byref(p3)) == 0 and gpu.launch_count() == before          # nothing recorded, nothing launched
+    assert np.array_equal(_to_np(p3), img3)
