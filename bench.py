@@ -149,6 +149,25 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _bind_to_gpu_cpus(index: int) -> bool:
+    """Multi-GPU runs: pin this rank to the CPUs NVML reports as local to its GPU before any pinned host memory is
+    allocated, so the e2e leg's staging buffers are first-touched on the GPU's own NUMA node (the H2D copies of 8 ranks
+    otherwise cross the socket interconnect). Best effort: silently skipped where NVML or the cpuset says no."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -194,6 +213,7 @@ def main():
     from ngx_http_imgproc_b200 import api
 
     torch.cuda.set_device(local)
+    numa_bound = _bind_to_gpu_cpus(local) if world > 1 else False
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -313,7 +333,8 @@ def main():
         "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 pixels, f32/i32 arithmetic", "data": "synthetic",
         "config": {"workload": a.config + ": " + wl["desc"], "jobs_per_gpu": len(jobs), "l2": "every job has its own source frame; inputs per step >> 126 MB L2" if a.config != "cfg5" else "512 sources (1.7 GB) cycled, > L2",
-                   "e2e_inputs": "32 distinct pinned host frames per shape, cycled; each request copies its crop window H2D and its result D2H"},
+                   "e2e_inputs": "32 distinct pinned host frames per shape, cycled; each request copies its crop window H2D and its result D2H",
+                   "rank_cpu_binding": "NVML cpu affinity of the rank's GPU" if numa_bound else "none"},
         "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "jobs_per_step": len(h_plans), "steps": a.e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
