@@ -318,6 +318,7 @@ imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
     const short* __restrict__ xa = reinterpret_cast<const short*>(blob + P->xcoef_off);
     const int* __restrict__ yofs = reinterpret_cast<const int*>(blob + P->yofs_off);
     const short* __restrict__ yb = reinterpret_cast<const short*>(blob + P->ycoef_off);
+    const float* __restrict__ ybf = reinterpret_cast<const float*>(blob + P->taps_off);
     const bool fast = bx * SC + SC <= simd_end;                        // every byte of this pixel is on the float path
     int sx[4];
     const int x0 = __ldg(xofs + bx) - 1;
@@ -327,7 +328,6 @@ imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
     const int a0 = (short)(av.x & 0xffff), a1 = av.x >> 16, a2 = (short)(av.y & 0xffff), a3 = av.y >> 16;
     float h0[SC], h1[SC], h2[SC], h3[SC];
     int top = 0;
-    const float sc = 1.0f / 4194304.0f;
     unsigned q[CUBIC_RUN];                      // gathered pixels, packed B|G<<8|R<<16|A<<24 while the H window is live
 #pragma unroll
     for (int o = 0; o < CUBIC_RUN; o++) {
@@ -350,9 +350,8 @@ imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
                     cubic_hrow<SC>(S, sx, min(max(top + 3, 0), sh - 1), a0, a1, a2, a3, h3);
                 }
             }
-            const int2 bv = __ldg(reinterpret_cast<const int2*>(yb + by * 4));
-            const float f0 = __fmul_rn(imp_i2f22((short)(bv.x & 0xffff)), sc), f1 = __fmul_rn(imp_i2f22(bv.x >> 16), sc);
-            const float f2 = __fmul_rn(imp_i2f22((short)(bv.y & 0xffff)), sc), f3 = __fmul_rn(imp_i2f22(bv.y >> 16), sc);
+            const float4 fv = __ldg(reinterpret_cast<const float4*>(ybf) + by);          // coefficient * 2^-22, tabulated by the planner
+            const float f0 = fv.x, f1 = fv.y, f2 = fv.z, f3 = fv.w;
 #pragma unroll
             for (int c = 0; c < SC; c++) {
                 const float t3 = __fmul_rn(h3[c], f3);

@@ -70,7 +70,7 @@ struct ImpPass {
     float area_scale;         // AREA_INT: f32(1/(nx*ny))
     int xofs_off, xcoef_off;  // NN: xofs[bw]; CUBIC/LINEAR: xofs[bw], short xcoef[bw*ksize];
     int yofs_off, ycoef_off;  // AREA_FRAC: int2 range[b] (first tap, count) + coef = {int si; float a}[taps]
-    int taps_off;             // BLUR: int taps[n]
+    int taps_off;             // BLUR: int taps[n]; CUBIC: float ycoef[bh*4] = short coefficient * 2^-22 (exact)
     int blur_r;               // BLUR tile kernel: padded tap radius (3, 6, 9 or 12); 0 = generic two-launch path only
     int tapsr_off;            // BLUR tile kernel: int taps[2*blur_r+1] (zero taps trimmed, then zero-padded symmetrically)
     int max_xtaps, max_ytaps; // AREA_FRAC: largest tap count per output column / row

@@ -579,6 +579,12 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
             P.xcoef_off = L.bb.add(xa.data(), xa.size() * 2);
             P.yofs_off = L.bb.add(yo.data(), yo.size() * 4);
             P.ycoef_off = L.bb.add(yb.data(), yb.size() * 2);
+            if (cubic) {
+                // the float form OpenCV's SIMD vertical pass multiplies with: b * 2^-22, exact (imp_cubic_run_kernel)
+                std::vector<float> ybf(yb.size());
+                for (size_t i = 0; i < yb.size(); i++) ybf[i] = (float)yb[i] * (1.0f / 4194304.0f);
+                P.taps_off = L.bb.add(ybf.data(), ybf.size() * 4);
+            }
         }
     }
 
