@@ -311,6 +311,16 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * e2e_pix * a.e2e_steps / float(t.item()) / 1e6
+    # one request at a time through the C ABI (imp_gpu_run_host: H2D of the crop window, kernel(s), D2H, sync): what a single
+    # nginx request pays once its frame is decoded
+    lat = []
+    if rank == 0:
+        same = [s_ for p_, s_ in zip(h_plans, h_srcs) if p_ is h_plans[0]][:32]
+        for k in range(60):
+            t1 = time.perf_counter()
+            h_plans[0].run_host(same[k % len(same)], h_dsts[0])
+            lat.append((time.perf_counter() - t1) * 1e3)
+        lat = sorted(lat[10:])
     stop.set(); th.join(timeout=2)            # clocks were sampled across the device-timed and the end-to-end regions
 
     if rank != 0:
@@ -337,6 +347,8 @@ def main():
                    "rank_cpu_binding": "NVML cpu affinity of the rank's GPU" if numa_bound else "none"},
         "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "jobs_per_step": len(h_plans), "steps": a.e2e_steps},
         "gpu_launches": int(launches),
+        "single_request_latency_ms": {"p50": lat[len(lat) // 2], "p99": lat[-1], "n": len(lat),
+                                      "what": "imp_gpu_run_host on the workload's first request shape: H2D of the crop window + kernel(s) + D2H + sync, pinned host frames"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_step": int(algo_bytes), "kernel_launches_per_step": launches_per_step,
                      "ms_per_launch_group": float(np.mean(step_ms)), "ms_min": float(np.min(step_ms))},
