@@ -109,7 +109,8 @@ int  imp_gpu_device_count(void);
 /* Selects which initialised device subsequent calls from THIS thread use. */
 int  imp_gpu_set_device(int device);
 const char* imp_gpu_last_error(void);          /* thread-local text of the last IMP_ERROR_GPU */
-/* Kernels launched by this library since process start (all devices). */
+/* Pixel-stage kernels launched by this library since process start (all devices). The host paths' window
+ * re-pitch copy (short rows travel as one linear H2D copy and are laid out on the device) is not counted. */
 unsigned long long imp_gpu_launch_count(void);
 
 /* ---- plans -------------------------------------------------------------------------------------- */

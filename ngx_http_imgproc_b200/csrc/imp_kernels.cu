@@ -100,6 +100,31 @@ cudaError_t imp_launch_ascii(const uint8_t* d_img, int pitch, int w, int h, int 
     return cudaGetLastError();
 }
 
+// Window extraction / re-pitching on the device for the end-to-end path: the host frame's rows travel as ONE linear copy
+// (a 2-D host-to-device copy costs ~0.15 us per row, i.e. only 23 GB/s for 3.5 KB rows) and this kernel then lays the crop
+// window out with the 16-byte-aligned pitch the TMA kernels need. One thread per 4 destination bytes.
+__global__ void __launch_bounds__(256) imp_repitch_kernel(const uint8_t* __restrict__ src, int sp, uint8_t* __restrict__ dst, int dp,
+                                                          int row_bytes, int rows) {
+    const int words = (row_bytes + 3) >> 2;
+    const long long total = (long long)words * rows;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / words), xw = (int)(i - (long long)y * words);
+        const uint8_t* s = src + (size_t)y * sp + (size_t)xw * 4;
+        const int n = min(4, row_bytes - xw * 4);
+        uint32_t w = 0;
+        if ((reinterpret_cast<uintptr_t>(s) & 3) == 0 && n == 4) w = __ldg(reinterpret_cast<const uint32_t*>(s));
+        else for (int b = 0; b < n; b++) w |= (uint32_t)__ldg(s + b) << (8 * b);
+        *reinterpret_cast<uint32_t*>(dst + (size_t)y * dp + (size_t)xw * 4) = w;       // the pad bytes of the last word are inside the pitch
+    }
+}
+
+cudaError_t imp_launch_repitch(const uint8_t* d_src, int sp, uint8_t* d_dst, int dp, int row_bytes, int rows, cudaStream_t st) {
+    const long long total = (long long)((row_bytes + 3) >> 2) * rows;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    imp_repitch_kernel<<<std::max(blocks, 1), 256, 0, st>>>(d_src, sp, d_dst, dp, row_bytes, rows);
+    return cudaGetLastError();                 // a copy, not a pixel stage: not counted by imp_gpu_launch_count()
+}
+
 // GIF canvas expansion (advancedio.c:195-248): every canvas pixel walks the frames in order, carrying the
 // reference's `master` index for the disposal replay in a register, and writes one BGRA pixel per frame. Frames travel
 // over PCIe as 8-bit indices (4x fewer bytes than the BGRA canvases the CPU path builds).
