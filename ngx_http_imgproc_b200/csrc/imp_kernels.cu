@@ -351,56 +351,63 @@ imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
     for (int t = 0; t < 4; t++) sx[t] = min(max(x0 + t, 0), sw - 1);
     const int2 av = __ldg(reinterpret_cast<const int2*>(xa + bx * 4));   // 4 shorts, 8-byte aligned
     const int a0 = (short)(av.x & 0xffff), a1 = av.x >> 16, a2 = (short)(av.y & 0xffff), a3 = av.y >> 16;
-    float h0[SC], h1[SC], h2[SC], h3[SC];
-    int top = 0;
+    // Code size matters here (ncu: the first fully unrolled version was 14.6 K instructions and its top stall reason was
+    // instruction fetch): the four-row window is loaded once before the run, the run only slides it, the rare non-SIMD
+    // tail pixels take a rolled loop of their own, and the op list is instantiated once for both groups of four.
     unsigned q[CUBIC_RUN];                      // gathered pixels, packed B|G<<8|R<<16|A<<24 while the H window is live
+    if (fast) {
+        float h0[SC], h1[SC], h2[SC], h3[SC];
+        int top = __ldg(yofs + by0) - 1;
+        cubic_hrow<SC>(S, sx, min(max(top, 0), sh - 1), a0, a1, a2, a3, h0);
+        cubic_hrow<SC>(S, sx, min(max(top + 1, 0), sh - 1), a0, a1, a2, a3, h1);
+        cubic_hrow<SC>(S, sx, min(max(top + 2, 0), sh - 1), a0, a1, a2, a3, h2);
+        cubic_hrow<SC>(S, sx, min(max(top + 3, 0), sh - 1), a0, a1, a2, a3, h3);
 #pragma unroll
-    for (int o = 0; o < CUBIC_RUN; o++) {
-        const int by = by0 + o;
-        if (by >= bh) { q[o] = q[o > 0 ? o - 1 : 0]; continue; }      // past the bottom edge: a copy, never stored
-        int v[4] = {0, 0, 0, 255};
-        if (fast) {
-            const int want = __ldg(yofs + by) - 1;
-            if (o == 0 || want - top > 3 || want < top) {
-                top = want;
-                cubic_hrow<SC>(S, sx, min(max(top, 0), sh - 1), a0, a1, a2, a3, h0);
-                cubic_hrow<SC>(S, sx, min(max(top + 1, 0), sh - 1), a0, a1, a2, a3, h1);
-                cubic_hrow<SC>(S, sx, min(max(top + 2, 0), sh - 1), a0, a1, a2, a3, h2);
+        for (int o = 0; o < CUBIC_RUN; o++) {
+            const int by = min(by0 + o, bh - 1);                       // past the bottom edge: the last row again, never stored
+            const int want = __ldg(yofs + by) - 1;                     // non-decreasing in by
+            while (top < want) {
+#pragma unroll
+                for (int c = 0; c < SC; c++) { h0[c] = h1[c]; h1[c] = h2[c]; h2[c] = h3[c]; }
+                top++;
                 cubic_hrow<SC>(S, sx, min(max(top + 3, 0), sh - 1), a0, a1, a2, a3, h3);
-            } else {
-                while (top < want) {
-#pragma unroll
-                    for (int c = 0; c < SC; c++) { h0[c] = h1[c]; h1[c] = h2[c]; h2[c] = h3[c]; }
-                    top++;
-                    cubic_hrow<SC>(S, sx, min(max(top + 3, 0), sh - 1), a0, a1, a2, a3, h3);
-                }
             }
             const float4 fv = __ldg(reinterpret_cast<const float4*>(ybf) + by);          // coefficient * 2^-22, tabulated by the planner
-            const float f0 = fv.x, f1 = fv.y, f2 = fv.z, f3 = fv.w;
+            int v[4] = {0, 0, 0, 255};
 #pragma unroll
             for (int c = 0; c < SC; c++) {
-                const float t3 = __fmul_rn(h3[c], f3);
-                const float t2 = __fadd_rn(__fmul_rn(h2[c], f2), t3);
-                const float t1 = __fadd_rn(__fmul_rn(h1[c], f1), t2);
-                const float t0 = __fadd_rn(__fmul_rn(h0[c], f0), t1);
+                const float t3 = __fmul_rn(h3[c], fv.w);
+                const float t2 = __fadd_rn(__fmul_rn(h2[c], fv.z), t3);
+                const float t1 = __fadd_rn(__fmul_rn(h1[c], fv.y), t2);
+                const float t0 = __fadd_rn(__fmul_rn(h0[c], fv.x), t1);
                 v[c] = imp_sat8(imp_rint22(t0));
             }
-        } else {
-            imp_gather_cubic<SC>(S, sw, sh, xofs, xa, yofs, yb, simd_end, bx, by, v);
+            ImpPx p;
+            promote<SC>(v, p);
+            q[o] = (unsigned)p.b | ((unsigned)p.g << 8) | ((unsigned)p.r << 16) | ((unsigned)p.a << 24);
         }
-        ImpPx p;
-        promote<SC>(v, p);
-        q[o] = (unsigned)p.b | ((unsigned)p.g << 8) | ((unsigned)p.r << 16) | ((unsigned)p.a << 24);
+    } else {
+#pragma unroll 1
+        for (int o = 0; o < CUBIC_RUN; o++) {
+            int v[4] = {0, 0, 0, 255};
+            imp_gather_cubic<SC>(S, sw, sh, xofs, xa, yofs, yb, simd_end, bx, min(by0 + o, bh - 1), v);
+            ImpPx p;
+            promote<SC>(v, p);
+            const unsigned w = (unsigned)p.b | ((unsigned)p.g << 8) | ((unsigned)p.r << 16) | ((unsigned)p.a << 24);
+#pragma unroll
+            for (int k = 0; k < CUBIC_RUN; k++) if (k == o) q[k] = w;          // register select, no local-memory array
+        }
     }
     // op list + store, four pixels at a time (the op loop is the outer loop inside imp_run_ops_n)
-#pragma unroll
+    static_assert(CUBIC_RUN == 8, "two groups of four below");
+#pragma unroll 1
     for (int g = 0; g < CUBIC_RUN; g += 4) {
         if (by0 + g >= bh) break;
         ImpPx px[4];
         int bxs[4], bys[4];
 #pragma unroll
         for (int o = 0; o < 4; o++) {
-            const unsigned w = q[g + o];
+            const unsigned w = g ? q[4 + o] : q[o];
             bxs[o] = bx; bys[o] = min(by0 + g + o, bh - 1);
             px[o].b = w & 255; px[o].g = (w >> 8) & 255; px[o].r = (w >> 16) & 255; px[o].a = w >> 24;
         }
