@@ -218,7 +218,7 @@ struct PassHdrSmem {
 };
 
 template <int KIND, int SC>
-__global__ void __launch_bounds__(TILE_W * TILE_H)
+__global__ void __launch_bounds__(TILE_W * TILE_H, 6)
 imp_pass_kernel(const ImpJob* __restrict__ jobs, int first, int count, const ImpJob one) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(16) PassHdrSmem H;
