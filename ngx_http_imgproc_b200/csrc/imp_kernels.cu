@@ -320,7 +320,7 @@ __device__ __forceinline__ void cubic_hrow(const ImpSrcGlobal<SC>& S, const int 
 }
 
 template <int SC>
-__global__ void __launch_bounds__(TILE_W * TILE_H, 3)
+__global__ void __launch_bounds__(TILE_W * TILE_H, 4)
 imp_cubic_run_kernel(const ImpJob* __restrict__ jobs, int first, int count, const ImpJob one) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int jn = blockIdx.y + blockIdx.z * 65535;
