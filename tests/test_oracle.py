@@ -340,3 +340,24 @@ def test_runjob_on_gif_pages_vs_reference(orc):
             assert np.array_equal(out, o2), q
     finally:
         orc.Ref.use_cv2(False)
+
+
+def test_integration_edits_apply_to_the_reference():
+    """INTEGRATION.md's call-site edits (oracle/make_gpu_bridge.py) still match the reference's bridge.c: every edit
+    applies exactly once and no direct call to the CPU operators is left inside RunJob."""
+    import importlib.util
+    import os
+    ref = "/root/reference/bridge.c"
+    if not os.path.exists(ref):
+        pytest.skip("reference sources not present on this box")
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_gpu_bridge", os.path.join(here, "oracle", "make_gpu_bridge.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.patched_bridge(open(ref).read())
+    run_job = out[out.index("JobResult* RunJob"):]
+    for gone in ("= Crop(&image", "= Resize(&image", "= Filter(&image", "= Watermark(image", "\tBlendWithPaper(image)", "CV_GRAY2BGR"):
+        assert gone not in run_job, gone
+    for once in ("imp_Crop(&image", "imp_Resize(&image", "imp_Filter(&image", "imp_Watermark(image", "imp_BlendWithPaper(image)", "imp_FlushAll(", "imp_Discard(image)"):
+        assert run_job.count(once) == 1, once
+    assert "imp_gpu_init(0)" in out
