@@ -131,3 +131,43 @@ def test_error_code_matrix_appendix_e(hostsim):
     for r in ["100", "100,60", "0,30", "140,0,up"]:
         assert code(resize=r) == 0
     assert code(resize="3000,0,up") == 54
+
+
+def test_hostsim_random_requests_vs_oracle(hostsim, orc):
+    """Random requests (crop, every resize flavour, up to four filters, watermark, flatten, FI packing) through the planner
+    and the kernels' own per-pixel headers walked on the CPU, against the oracle: the CPU-box twin of scratch/fuzz_gpu.py."""
+    rng = np.random.default_rng(2024)
+    filt = ["flip=10", "flip=01", "rotate=90", "rotate=180", "rotate=270", "modulate=30,120,90", "modulate=12,0,140", "colorize=336699,0.4", "gamma=0.7",
+            "contrast=1.3", "gradmap=102030,f0e0d0", "vignette=0.7", "gotham=1", "lomo=1", "kelvin=1", "rainbow=mid", "scanline=0.6,0.2,2,1",
+            "blur=0.6", "blur=1.4", "blur=2.3"]
+    done = 0
+    for it in range(160):
+        c = int(rng.choice([1, 3, 4])); h = int(rng.integers(1, 70)); w = int(rng.integers(1, 90))
+        img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        rq = {}
+        if rng.random() < 0.4:
+            cw, ch = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
+            rq["crop"] = f"{cw}px,{ch}px,{int(rng.integers(0, w - cw + 1))}px,{int(rng.integers(0, h - ch + 1))}px"
+        if rng.random() < 0.7:
+            rq["resize"] = f"{int(rng.integers(1, 120))},{int(rng.integers(1, 100))}" + (",up" if rng.random() < 0.5 else "")
+            if rng.random() < 0.15: rq["simple"] = True
+            if rng.random() < 0.15: rq["interp"] = 1
+        rq["filters"] = [str(f) for f in rng.choice(filt, int(rng.integers(0, 5)))]
+        if rng.random() < 0.3: rq["flatten"] = True
+        if rng.random() < 0.2: rq["pack"] = int(rng.choice([24, 32]))
+        kw = dict(allow_experiments=True, max_filters=8, max_w=0, max_h=0)
+        if rng.random() < 0.4:
+            kw.update(watermark=rng.integers(0, 256, (int(rng.integers(1, 20)), int(rng.integers(1, 25)), int(rng.choice([3, 4]))), dtype=np.uint8),
+                      wm_gravity_x=str(rng.choice(list("lcr"))), wm_gravity_y=str(rng.choice(list("tcb"))),
+                      wm_offset_x=int(rng.integers(-8, 12)), wm_offset_y=int(rng.integers(-8, 12)), wm_opacity=int(rng.integers(1, 101)))
+        code, step, out = hostsim.run(img, api.Config(**kw), **rq)
+        c2, s2, o2 = _oracle(orc, img, rq, kw)
+        assert code == c2, (it, rq, code, c2)
+        if code:
+            assert step == s2, (it, rq)
+            continue
+        tol = 1 if any("vignette" in f for f in rq["filters"]) else 0
+        assert out.shape == o2.shape, (it, rq)
+        assert np.abs(out.astype(int) - o2.astype(int)).max() <= tol, (it, (h, w, c), rq)
+        done += 1
+    assert done > 100
