@@ -138,6 +138,9 @@ int pass_pitch(const ImpHostPass& hp) { return align16(hp.out_w * hp.out_c); }
 // Scratch a plan needs on the device: intermediates between passes + the u16 plane of each generic blur.
 // off[k] = offset of pass k's output (non-final passes); blur_off[k] = offset of pass k's u16 plane.
 int pick_variant(const ImpPass& h, const ImpJob& j);
+int variant_param(const ImpPass& h, int variant);
+int variant_smem(const ImpPass& h, int variant, int param);
+constexpr int kTileSmemLimit = 200 * 1024;     // cudaFuncAttributeMaxDynamicSharedMemorySize of every tile kernel (imp_kernels.cu)
 
 // `src`/`sp`: the job's source (null = one of the library's own aligned buffers). The u16 plane is only reserved for a
 // blur that cannot take the fused tile kernel (radius > 12, or a pass-0 source whose rows are not 16-byte addressable).
@@ -217,22 +220,24 @@ int pick_variant(const ImpPass& h, const ImpJob& j) {
     // the fallback paths — unaligned pitches, oversized footprints, large sigma — covered on the GPU).
     static const bool force_direct = [] { const char* e = getenv("IMP_GPU_FORCE_DIRECT"); return e && *e == '1'; }();
     if (force_direct) return 0;
-    if (h.kind == IMP_G_CUBIC) return 3;                             // column-run kernel: no alignment requirements
-    if (h.tile_smem <= 0 || !encode_tiled()) return 0;
-    if (j.src_pitch % 16) return 0;
+    const int fallback = h.kind == IMP_G_CUBIC ? 3 : 0;              // cubic: the column-run kernel has no alignment requirements
+    if (h.tile_smem <= 0 || !encode_tiled()) return fallback;
+    if (j.src_pitch % 16) return fallback;
     const uintptr_t img = (uintptr_t)j.src;
     const uintptr_t win = img + (size_t)h.sy0 * j.src_pitch + (size_t)h.sx0 * h.sc;
-    if (img % 16 && win % 16) return 0;
-    if (h.kind == IMP_G_BLUR) return h.blur_r > 0 ? 2 : 0;           // fused blur tile kernel
-    return 1;                                                        // area strip kernels
+    if (img % 16 && win % 16) return fallback;
+    int variant = 1;                                                 // strip kernels: INTER_AREA, INTER_NN, INTER_LINEAR, index map
+    if (h.kind == IMP_G_BLUR) variant = h.blur_r > 0 ? 2 : 0;        // fused blur tile kernel
+    if (h.kind == IMP_G_CUBIC) variant = 4;                          // cubic tile kernel
+    // the launch must fit the opt-in shared-memory limit the kernels are configured with (many LUT filters can push a
+    // pass over it: ADVICE r1); the direct kernels stage only the ops
+    if (variant && variant_smem(h, variant, variant_param(h, variant)) > kTileSmemLimit) return fallback;
+    return variant;
 }
 int blur_smem_bytes(const ImpPass& h) {
     const int ops = (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15;
-    const int span = 32 + 2 * h.blur_r;
-    return 128 + ((ops + 127) & ~127) + ((h.tile_rs * span + 127) & ~127) + span * 32 * h.sc * 2 + 32 * (32 * h.sc + 4) + 64;
+    return imp_blur_dyn_smem(h.sc, h.blur_r, ops, h.tile_rs);
 }
-int variant_param(const ImpPass& h, int variant);
-int variant_smem(const ImpPass& h, int variant, int param);
 int variant_tiles(const ImpPass& h, int variant);
 int tile_stage_bytes(const ImpPass& h) {
     const int extra = h.kind == IMP_G_AREA_FRAC ? (((h.tile_ytaps * 8 + 15) & ~15) + 128) : 0;    // staged y taps + the 8 rows' int4 descriptors
@@ -252,12 +257,14 @@ int tile_smem_bytes(const ImpPass& h, int stages) {
 
 int variant_param(const ImpPass& h, int variant) { return variant == 1 ? tile_stages(h) : variant == 2 ? h.blur_r : 0; }
 int variant_smem(const ImpPass& h, int variant, int param) {
+    if (variant == 4) return imp_cubic_dyn_smem(h.sc, (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15, h.tile_rs, h.tile_rows);
     return variant == 1 ? tile_smem_bytes(h, param) : variant == 2 ? blur_smem_bytes(h) : ops_smem(h);
 }
 int variant_tiles(const ImpPass& h, int variant) {
     if (variant == 1) return (h.bw + 31) / 32;
-    if (variant == 2) return ((h.bw + 31) / 32) * ((h.bh + 31) / 32);
+    if (variant == 2) return ((h.bw + IMP_BLUR_TW - 1) / IMP_BLUR_TW) * ((h.bh + IMP_BLUR_TH - 1) / IMP_BLUR_TH);   // same count in destination space
     if (variant == 3) return ((h.bw + 31) / 32) * ((h.bh + 8 * IMP_CUBIC_RUN - 1) / (8 * IMP_CUBIC_RUN));
+    if (variant == 4) return ((h.bw + IMP_CUBIC_T - 1) / IMP_CUBIC_T) * ((h.bh + IMP_CUBIC_T - 1) / IMP_CUBIC_T);
     return pass_tiles(h);
 }
 
@@ -298,7 +305,7 @@ int batch_compile(imp_gpu_batch* b) {
             const ImpHostPass& hp = it.plan->passes[k];
             ImpJob jb = make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->d_scratch, off[i]);
             const int variant = pick_variant(hp.hdr, jb);
-            if (variant == 1 || variant == 2) { int rc = encode_job_tmap(hp.hdr, jb); if (rc) return rc; }
+            if (variant == 1 || variant == 2 || variant == 4) { int rc = encode_job_tmap(hp.hdr, jb); if (rc) return rc; }
             const int param = variant_param(hp.hdr, variant);
             pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, param, occ_class(hp.hdr, variant, param), jb, hp.hdr, boff[i][k]});
         }
@@ -355,7 +362,7 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
         const ImpHostPass& hp = p->passes[k];
         ImpJob j = make_job(p, t_dev, k, src, sp, dst, dp, scratch, off);
         const int variant = pick_variant(hp.hdr, j);
-        if (variant == 1 || variant == 2) { int rc = encode_job_tmap(hp.hdr, j); if (rc) return rc; }
+        if (variant == 1 || variant == 2 || variant == 4) { int rc = encode_job_tmap(hp.hdr, j); if (rc) return rc; }
         if (hp.hdr.kind == IMP_G_BLUR && variant == 0) {
             CK(imp_launch_blur_generic(j, hp.hdr, (uint16_t*)(scratch + boff[k]), ops_smem(hp.hdr), st));
         } else {

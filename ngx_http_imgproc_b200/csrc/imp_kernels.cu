@@ -9,6 +9,8 @@
 #include <algorithm>
 #include "imp_gather.cuh"
 #include "imp_tiles.cuh"
+#include "imp_blur.cuh"
+#include "imp_cubic.cuh"
 
 #include <atomic>
 static std::atomic<unsigned long long> g_imp_launches{0};
@@ -495,9 +497,9 @@ template <int SC, int MODE>
 cudaError_t launch_area_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
     static std::atomic<bool> attr_set[16];                 // per device; setting the attribute twice is harmless
     int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_area_strip_kernel<SC, MODE>;
+    auto kern = imp_tiles::imp_strip_kernel<SC, MODE>;
     if (!attr_set[dev & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 15] = true;
     }
@@ -519,7 +521,7 @@ cudaError_t launch_blur_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, cons
         attr_set[dev & 15] = true;
     }
     dim3 block(imp_tiles::BLUR_THREADS);
-    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);      // max_tiles = 32x32 tiles
+    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);      // max_tiles = 32x64 tiles
     kern<<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o);
     g_imp_launches++;
     return cudaGetLastError();
@@ -534,6 +536,23 @@ cudaError_t launch_blur_tile_r(const ImpLaunchGroup& g, const ImpJob* d_jobs, co
         case 12: return launch_blur_tile<SC, 12>(g, d_jobs, o, st);
     }
     return cudaErrorInvalidValue;
+}
+
+template <int SC>
+cudaError_t launch_cubic_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
+    static std::atomic<bool> attr_set[16];
+    int dev = 0; cudaGetDevice(&dev);
+    auto kern = imp_tiles::imp_cubic_tile_kernel<SC>;
+    if (!attr_set[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 15] = true;
+    }
+    dim3 block(imp_tiles::CUBIC_THREADS);
+    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);      // max_tiles = 32x32 output tiles
+    kern<<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o);
+    g_imp_launches++;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_cubic_run(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st) {
@@ -560,21 +579,37 @@ cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, cons
         if (g.sc == 4) return launch_blur_tile_r<4>(g, d_jobs, o, st);
         return cudaErrorInvalidValue;
     }
-    if (g.variant == 1 && (g.kind == IMP_G_AREA_FRAC || g.kind == IMP_G_AREA_INT)) {
+    if (g.variant == 4 && g.kind == IMP_G_CUBIC) {
         const ImpJob dummy{};
         const ImpJob& o = one ? *one : dummy;
-        if (g.kind == IMP_G_AREA_FRAC) {
-            switch (g.sc) {
-                case 1: return launch_area_tile<1, 0>(g, d_jobs, o, st);
-                case 3: return launch_area_tile<3, 0>(g, d_jobs, o, st);
-                case 4: return launch_area_tile<4, 0>(g, d_jobs, o, st);
-            }
-        } else {
-            switch (g.sc) {
-                case 1: return launch_area_tile<1, 1>(g, d_jobs, o, st);
-                case 3: return launch_area_tile<3, 1>(g, d_jobs, o, st);
-                case 4: return launch_area_tile<4, 1>(g, d_jobs, o, st);
-            }
+        switch (g.sc) {
+            case 1: return launch_cubic_tile<1>(g, d_jobs, o, st);
+            case 3: return launch_cubic_tile<3>(g, d_jobs, o, st);
+            case 4: return launch_cubic_tile<4>(g, d_jobs, o, st);
+        }
+        return cudaErrorInvalidValue;
+    }
+    if (g.variant == 1) {
+        const ImpJob dummy{};
+        const ImpJob& o = one ? *one : dummy;
+        // strip kernel modes (imp_tiles.cuh): 0 fractional INTER_AREA, 1 integer INTER_AREA, 2 INTER_NN, 3 INTER_LINEAR, 4 index map
+        const int mode = g.kind == IMP_G_AREA_FRAC ? 0 : g.kind == IMP_G_AREA_INT ? 1 : g.kind == IMP_G_NN ? 2 : g.kind == IMP_G_LINEAR ? 3 : g.kind == IMP_G_COPY ? 4 : -1;
+        switch (mode * 8 + g.sc) {
+            case 0 * 8 + 1: return launch_area_tile<1, 0>(g, d_jobs, o, st);
+            case 0 * 8 + 3: return launch_area_tile<3, 0>(g, d_jobs, o, st);
+            case 0 * 8 + 4: return launch_area_tile<4, 0>(g, d_jobs, o, st);
+            case 1 * 8 + 1: return launch_area_tile<1, 1>(g, d_jobs, o, st);
+            case 1 * 8 + 3: return launch_area_tile<3, 1>(g, d_jobs, o, st);
+            case 1 * 8 + 4: return launch_area_tile<4, 1>(g, d_jobs, o, st);
+            case 2 * 8 + 1: return launch_area_tile<1, 2>(g, d_jobs, o, st);
+            case 2 * 8 + 3: return launch_area_tile<3, 2>(g, d_jobs, o, st);
+            case 2 * 8 + 4: return launch_area_tile<4, 2>(g, d_jobs, o, st);
+            case 3 * 8 + 1: return launch_area_tile<1, 3>(g, d_jobs, o, st);
+            case 3 * 8 + 3: return launch_area_tile<3, 3>(g, d_jobs, o, st);
+            case 3 * 8 + 4: return launch_area_tile<4, 3>(g, d_jobs, o, st);
+            case 4 * 8 + 1: return launch_area_tile<1, 4>(g, d_jobs, o, st);
+            case 4 * 8 + 3: return launch_area_tile<3, 4>(g, d_jobs, o, st);
+            case 4 * 8 + 4: return launch_area_tile<4, 4>(g, d_jobs, o, st);
         }
         return cudaErrorInvalidValue;
     }

@@ -73,6 +73,8 @@ struct ImpPass {
     int taps_off;             // BLUR: int taps[n]; CUBIC: float ycoef[bh*4] = short coefficient * 2^-22 (exact)
     int blur_r;               // BLUR tile kernel: padded tap radius (3, 6, 9 or 12); 0 = generic two-launch path only
     int tapsr_off;            // BLUR tile kernel: int taps[2*blur_r+1] (zero taps trimmed, then zero-padded symmetrically)
+    int taph_off, tapv_off;   // BLUR tile kernel: the same taps as u8 dot-product words: u32 taph[4][NWH] (dp4a, four byte
+                              // alignments), u32 tapv[2][NWV] (dp2a, two parities); ImpBlurDims<R> below
     int max_xtaps, max_ytaps; // AREA_FRAC: largest tap count per output column / row
     int tile_rs, tile_rows;   // tile kernels: shared-memory row stride (bytes) and max source rows per 32x8 tile
     int tile_smem;            // tile kernels: source-tile bytes (tile_rs*tile_rows); 0 = no tile variant for this pass
@@ -86,6 +88,43 @@ struct ImpPass {
     int dc;                   // destination channels (== oc)
     int blob_bytes;
 };
+
+// Geometry of the fused blur tile kernel (imp_blur.cuh), shared with the planner (tap tables, TMA box) and the runtime
+// (shared-memory size). A CTA blurs a BTW x BTH tile of the base frame with taps padded to radius R.
+#define IMP_CUBIC_T 32        // imp_cubic.cuh: output tile edge
+#define IMP_CUBIC_HRS(sc) ((sc) == 4 ? IMP_CUBIC_T * 4 + 4 : IMP_CUBIC_T * (sc) + 1)     // floats per row of its horizontal-pass buffer
+// the TMA box region doubles as the 32 x 32 x 3-byte out stage of 3-channel results
+#define IMP_CUBIC_TILE_BYTES(tile_rs, tile_rows) \
+    (((((tile_rs) * (tile_rows)) > IMP_CUBIC_T * IMP_CUBIC_T * 3 ? ((tile_rs) * (tile_rows)) : IMP_CUBIC_T * IMP_CUBIC_T * 3) + 127) & ~127)
+inline int imp_cubic_dyn_smem(int sc, int ops_bytes16, int tile_rs, int tile_rows) {
+    return 128 + ((ops_bytes16 + 127) & ~127) + IMP_CUBIC_TILE_BYTES(tile_rs, tile_rows) + tile_rows * IMP_CUBIC_HRS(sc) * 4 + 64;
+}
+#define IMP_BLUR_TW 32
+#define IMP_BLUR_TH 64
+template <int R> struct ImpBlurDims {
+    static constexpr int SPANX = IMP_BLUR_TW + 2 * R, SPANY = IMP_BLUR_TH + 2 * R;   // source neighbourhood
+    static constexpr int NWH = (2 * R + 4 + 3) / 4;           // tap words per byte alignment (2R+1 taps shifted by up to 3)
+    static constexpr int NWIN = NWH + 1;                      // planar words a thread loads for 8 adjacent outputs
+    static constexpr int PWW = (6 + NWIN) | 1;                // planar row stride in words: covers SPANX bytes, odd (banks)
+    static constexpr int NDV = R + 1;                         // dp2a per output: ceil((2R+1 taps + 1 parity shift) / 2)
+    static constexpr int NWV = (NDV + 1) / 2;                 // tap words per parity (one word feeds a dp2a.lo and a dp2a.hi)
+    static constexpr int NV128 = (8 + 2 * R + 7) / 8;         // 16-byte loads covering the 8+2R u16 window of 8 outputs
+    static constexpr int HNEED = SPANY > IMP_BLUR_TH - 8 + 8 * NV128 ? SPANY : IMP_BLUR_TH - 8 + 8 * NV128;
+    static constexpr int HS = ((HNEED - 8 + 15) & ~15) + 8;   // u16 row stride of the transposed sums: % 16 == 8 (banks)
+    static constexpr int planar_bytes(int sc) { return (sc * SPANY * PWW * 4 + 127) & ~127; }
+    static constexpr int hbuf_bytes(int sc) { return sc * IMP_BLUR_TW * HS * 2; }
+};
+inline int imp_blur_dyn_smem(int sc, int r, int ops_bytes16, int tile_rs) {
+    const int spany = IMP_BLUR_TH + 2 * r;
+    int planar = 0, hbuf = 0;
+    switch (r) {
+        case 3:  planar = ImpBlurDims<3>::planar_bytes(sc);  hbuf = ImpBlurDims<3>::hbuf_bytes(sc);  break;
+        case 6:  planar = ImpBlurDims<6>::planar_bytes(sc);  hbuf = ImpBlurDims<6>::hbuf_bytes(sc);  break;
+        case 9:  planar = ImpBlurDims<9>::planar_bytes(sc);  hbuf = ImpBlurDims<9>::hbuf_bytes(sc);  break;
+        default: planar = ImpBlurDims<12>::planar_bytes(sc); hbuf = ImpBlurDims<12>::hbuf_bytes(sc); break;
+    }
+    return 128 + ((ops_bytes16 + 127) & ~127) + ((tile_rs * spany + 127) & ~127) + planar + hbuf + 64;
+}
 
 // One job of a batch: which pass blob, where the pixels are.
 struct ImpJob {

@@ -152,6 +152,34 @@ std::vector<int> gaussian_taps(double sigma) {
     return k;
 }
 
+// Strip-kernel tables for the plain gathers (imp_tiles.cuh, modes NN / LINEAR / COPY): per strip of 32 output columns the
+// first and last source pixel it touches, per tile of 8 output rows the first source row and the row count; the TMA box is
+// the largest such rectangle. x_lo/x_hi(bx), y_lo/y_hi(by): clamped source coordinates an output column / row reads.
+template <class FXL, class FXH, class FYL, class FYH>
+void gather_strip_tables(BlobBuilder& bb, ImpPass& P, int c, FXL x_lo, FXH x_hi, FYL y_lo, FYH y_hi) {
+    const int rw = P.bw, rh = P.bh;
+    int span = 0, rows = 0;
+    std::vector<int> xtile, ytile;
+    for (int x0 = 0; x0 < rw; x0 += 32) {
+        int p0 = x_lo(x0), p1 = x_hi(std::min(x0 + 32, rw) - 1);
+        for (int x = x0; x < std::min(x0 + 32, rw); x++) { p0 = std::min(p0, x_lo(x)); p1 = std::max(p1, x_hi(x)); }
+        xtile.push_back(p0); xtile.push_back(p1);
+        span = std::max(span, p1 - p0 + 1);
+    }
+    for (int y0 = 0; y0 < rh; y0 += 8) {
+        int p0 = y_lo(y0), p1 = y_hi(std::min(y0 + 8, rh) - 1);
+        for (int y = y0; y < std::min(y0 + 8, rh); y++) { p0 = std::min(p0, y_lo(y)); p1 = std::max(p1, y_hi(y)); }
+        ytile.push_back(p0); ytile.push_back(p1 - p0 + 1); ytile.push_back(0); ytile.push_back(0);
+        rows = std::max(rows, p1 - p0 + 1);
+    }
+    P.xtile_off = bb.add(xtile.data(), xtile.size() * 4);
+    P.ytile_off = bb.add(ytile.data(), ytile.size() * 4);
+    P.tile_rs = (span * c + 15 + 15) & ~15;                     // +15 for the 16-byte alignment of the box origin
+    if ((P.tile_rs / 4) % 32 == 0) P.tile_rs += 16;
+    P.tile_rows = rows;
+    P.tile_smem = (P.tile_rs <= 2048 && rows <= 256 && (long long)P.tile_rs * rows <= 64 * 1024) ? P.tile_rs * rows : 0;
+}
+
 // ---- lowering state -----------------------------------------------------------------------------------
 struct Lower {
     imp_gpu_plan* plan;
@@ -170,6 +198,9 @@ struct Lower {
         bb = BlobBuilder(); ops.clear(); luts.clear(); uses_wm = false; sigma = 0;
         hdr.kind = kind; in_w = in_w_; in_h = in_h_; in_c = in_c_;
         hdr.sc = in_c_;
+    }
+    void copy_tables() {
+        gather_strip_tables(bb, hdr, hdr.sc, [](int x) { return x; }, [](int x) { return x; }, [](int y) { return y; }, [](int y) { return y; });
     }
     int add_lut(const uint8_t* p, int n) { int off = (int)luts.size(); luts.insert(luts.end(), p, p + n); return off; }
     int final_dc = 0;              // destination channels of the LAST pass when the encoder-side packing changes them
@@ -204,6 +235,7 @@ struct Lower {
         } else {
             ImpFrameMap ident{0, 0, 0, hdr.bw, hdr.bh};
             int bw = hdr.bw, bh = hdr.bh, oc = hdr.oc;
+            if (hdr.kind == IMP_G_COPY) copy_tables();
             end_pass(ident, bw, bh);
             begin_pass(IMP_G_BLUR, bw, bh, oc);
             hdr.oc = oc; hdr.sx0 = hdr.sy0 = 0; hdr.sw = hdr.bw = bw; hdr.sh = hdr.bh = bh;
@@ -211,23 +243,41 @@ struct Lower {
         hdr.ksize = (int)k.size();
         hdr.taps_off = bb.add(k.data(), k.size() * sizeof(int));
         sigma = sg;
-        // tile kernel (imp_tiles.cuh): effective radius after trimming zero outer taps, padded up to 3/6/9/12
+        // tile kernel (imp_blur.cuh): effective radius after trimming zero outer taps, padded up to 3/6/9/12
         int lo = 0, hi = (int)k.size() - 1;
         while (lo < hi && k[lo] == 0 && k[hi] == 0) { lo++; hi--; }
         const int r_eff = (hi - lo) / 2;
         hdr.blur_r = r_eff <= 3 ? 3 : r_eff <= 6 ? 6 : r_eff <= 9 ? 9 : r_eff <= 12 ? 12 : 0;
         if (k.size() == 1) hdr.blur_r = 0;                          // n == 1 holds the single tap 256, a plain copy
+        for (int v : k) if (v < 0 || v > 255) hdr.blur_r = 0;       // the dot-product taps are u8 (a lone centre tap of 256 is not)
         if (hdr.blur_r) {
             const int R = hdr.blur_r;
             std::vector<int> kr(2 * R + 1, 0);
             for (int i = lo; i <= hi; i++) kr[R - r_eff + (i - lo)] = k[i];
             hdr.tapsr_off = bb.add(kr.data(), kr.size() * sizeof(int));
-            hdr.tile_rows = 32 + 2 * R;
-            hdr.tile_rs = ((32 + 2 * R) * hdr.sc + 15 + 15) & ~15;
+            // taph[m][w]: byte e of word w = tap (4w + e - m), i.e. the taps shifted right by m bytes (horizontal, dp4a);
+            // tapv[m][w]: the same with m in {0,1} (vertical, dp2a: bytes 0,1 feed .lo, bytes 2,3 feed .hi)
+            const int nwh = (2 * R + 4 + 3) / 4, nwv = ((R + 1) + 1) / 2;
+            std::vector<uint32_t> th((size_t)4 * nwh, 0), tv((size_t)2 * nwv, 0);
+            for (int m = 0; m < 4; m++)
+                for (int b = 0; b < 4 * nwh; b++) {
+                    const int t = b - m;
+                    if (t >= 0 && t <= 2 * R) th[(size_t)m * nwh + b / 4] |= (uint32_t)kr[t] << (8 * (b % 4));
+                }
+            for (int m = 0; m < 2; m++)
+                for (int b = 0; b < 4 * nwv; b++) {
+                    const int t = b - m;
+                    if (t >= 0 && t <= 2 * R) tv[(size_t)m * nwv + b / 4] |= (uint32_t)kr[t] << (8 * (b % 4));
+                }
+            hdr.taph_off = bb.add(th.data(), th.size() * 4);
+            hdr.tapv_off = bb.add(tv.data(), tv.size() * 4);
+            hdr.tile_rows = IMP_BLUR_TH + 2 * R;
+            hdr.tile_rs = ((IMP_BLUR_TW + 2 * R) * hdr.sc + 15 + 15) & ~15;
             hdr.tile_smem = hdr.tile_rs * hdr.tile_rows;
         }
     }
 };
+
 
 const char* const kFilterNames[] = {"flip", "rotate", "modulate", "colorize", "blur", "gamma", "contrast", "gradmap",
                                     "vignette", "gotham", "lomo", "kelvin", "rainbow", "scanline"};   // filters.c:10-24
@@ -440,8 +490,9 @@ int parse_crop(const char* args_s, const char* gravity, size_t col, size_t row, 
     int wx, wy;
     if (!axis(g.size() > 0 ? &g[0] : nullptr, "l", "r", "c", (long)col, (long)ww, wx)) return IMP_ERROR_INVALID_ARGS;
     if (!axis(g.size() > 1 ? &g[1] : nullptr, "t", "b", "t", (long)row, (long)wh, wy)) return IMP_ERROR_INVALID_ARGS;
-    if (wx + (int)ww > (int)col || wy + (int)wh > (int)row) return IMP_ERROR_INVALID_ARGS;
     if (wx < 0 || wy < 0) return IMP_ERROR_INVALID_ARGS;          // reference: OpenCV size-mismatch assert
+    // 64-bit: a pixel offset near INT_MAX must not wrap past the bound (the reference stops it at cvSetImageROI)
+    if ((long long)wx + (long long)ww > (long long)col || (long long)wy + (long long)wh > (long long)row) return IMP_ERROR_INVALID_ARGS;
     X = wx; Y = wy; W = (int)ww; H = (int)wh;
     return IMP_OK;
 }
@@ -487,6 +538,8 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
         int code = parse_crop(req->crop, req->gravity, (size_t)w, (size_t)h, cx, cy, cw, ch);
         if (code) return code;
     }
+    // every kernel and the host paths address src + win_y*step + win_x*c: the window must lie inside the frame
+    if (cx < 0 || cy < 0 || cw <= 0 || ch <= 0 || (long long)cx + cw > w || (long long)cy + ch > h) return IMP_ERROR_INVALID_ARGS;
     plan->win_x = cx; plan->win_y = cy; plan->win_w = cw; plan->win_h = ch;
 
     // step 4: resize (bridge.c:589-604)
@@ -511,6 +564,8 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
             P.kind = IMP_G_NN;
             P.xofs_off = L.bb.add(xo.data(), xo.size() * 4);
             P.yofs_off = L.bb.add(yo.data(), yo.size() * 4);
+            gather_strip_tables(L.bb, P, c, [&](int x) { return xo[x]; }, [&](int x) { return xo[x]; },
+                                [&](int y) { return yo[y]; }, [&](int y) { return yo[y]; });
         } else if (mode == 3 && scale_x >= 1 && scale_y >= 1) {
             {
                 // The strip kernel (imp_tiles.cuh) walks the same tap tables for both flavours; with integer scales
@@ -579,11 +634,29 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
             P.xcoef_off = L.bb.add(xa.data(), xa.size() * 2);
             P.yofs_off = L.bb.add(yo.data(), yo.size() * 4);
             P.ycoef_off = L.bb.add(yb.data(), yb.size() * 2);
+            auto clampi = [](int v, int lo, int hi) { return std::min(std::max(v, lo), hi); };
             if (cubic) {
-                // the float form OpenCV's SIMD vertical pass multiplies with: b * 2^-22, exact (imp_cubic_run_kernel)
+                // the float form OpenCV's SIMD vertical pass multiplies with: b * 2^-22, exact (imp_cubic.cuh)
                 std::vector<float> ybf(yb.size());
                 for (size_t i = 0; i < yb.size(); i++) ybf[i] = (float)yb[i] * (1.0f / 4194304.0f);
                 P.taps_off = L.bb.add(ybf.data(), ybf.size() * 4);
+                // tile kernel (imp_cubic.cuh): 32 x 32 output tiles at ANY origin (it tiles in destination space); the TMA
+                // box is the largest source rectangle such a tile's clamped 4x4 footprints span
+                int span = 0, rows = 0;
+                for (int x0 = 0; x0 < rw; x0++) {
+                    const int x1 = std::min(x0 + IMP_CUBIC_T, rw) - 1;
+                    span = std::max(span, clampi(xo[x1] + 2, 0, cw - 1) - clampi(xo[x0] - 1, 0, cw - 1) + 1);
+                }
+                for (int y0 = 0; y0 < rh; y0++) {
+                    const int y1 = std::min(y0 + IMP_CUBIC_T, rh) - 1;
+                    rows = std::max(rows, clampi(yo[y1] + 2, 0, ch - 1) - clampi(yo[y0] - 1, 0, ch - 1) + 1);
+                }
+                P.tile_rs = (span * c + 15 + 15) & ~15;
+                P.tile_rows = rows;
+                P.tile_smem = (P.tile_rs <= 2048 && rows <= 96 && (long long)P.tile_rs * rows <= 48 * 1024) ? P.tile_rs * rows : 0;
+            } else {
+                gather_strip_tables(L.bb, P, c, [&](int x) { return clampi(xo[x], 0, cw - 1); }, [&](int x) { return clampi(xo[x] + 1, 0, cw - 1); },
+                                    [&](int y) { return clampi(yo[y], 0, ch - 1); }, [&](int y) { return clampi(yo[y] + 1, 0, ch - 1); });
             }
         }
     }
@@ -597,6 +670,9 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
         if (code) return code;
         if ((int)L.ops.size() > IMP_MAX_OPS) return IMP_ERROR_TOO_MUCH_FILTERS;
     }
+
+    // a pass 0 that stayed a plain index map (crop / no resize) streams through the strip kernel as well
+    if (L.hdr.kind == IMP_G_COPY) L.copy_tables();
 
     // step 6: watermark (bridge.c:629-640, 239-281)
     *step = IMP_STEP_WATERMARK;

@@ -306,9 +306,85 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
     }
 }
 
+// Plain-gather consumers of the strip kernel (modes 2 = INTER_NN, 3 = INTER_LINEAR, 4 = index map / crop): the same TMA ring,
+// one output row per warp, but the pixel comes from one (NN, COPY) or 2x2 (LINEAR) staged source pixels. The per-column
+// part of the gather (source offset, x coefficients) is loaded once per strip.
+template <int SC, int MODE>
+__device__ __forceinline__ void gather_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* __restrict__ blob,
+                                                     const uint8_t* tile0, int stage_bytes, uint64_t* full, uint64_t* empty,
+                                                     const uint8_t* s_ops, int nops, int bx0, int col_off, int tiles_y, int NSTAGE) {
+    const int bw = P->bw, bh = P->bh, sw = P->sw, sh = P->sh, rs = P->tile_rs, oc = P->oc, dc = P->dc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool in_x = bx0 + lane < bw;
+    const int bx = min(bx0 + lane, bw - 1);
+    const int* __restrict__ yofs = reinterpret_cast<const int*>(blob + P->yofs_off);
+    const int4* __restrict__ ytile = reinterpret_cast<const int4*>(blob + P->ytile_off);
+    int xo0 = 0, xo1 = 0, a0 = 0, a1 = 0;
+    if (MODE == 2) xo0 = col_off + __ldg(reinterpret_cast<const int*>(blob + P->xofs_off) + bx) * SC;
+    else if (MODE == 4) xo0 = col_off + bx * SC;
+    else {
+        const int xs = __ldg(reinterpret_cast<const int*>(blob + P->xofs_off) + bx);
+        xo0 = col_off + min(max(xs, 0), sw - 1) * SC; xo1 = col_off + min(max(xs + 1, 0), sw - 1) * SC;
+        const short* xa = reinterpret_cast<const short*>(blob + P->xcoef_off);
+        a0 = __ldg(xa + bx * 2); a1 = __ldg(xa + bx * 2 + 1);
+    }
+    const StripStore st = strip_store_line(P->out, job.dst, job.dst_pitch, dc, bx);
+    const StripOpsRows orows = strip_ops_rows(s_ops, nops, bx);
+    int stage = 0, phase = 0;
+    for (int t = 0; t < tiles_y; t++) {
+        const int by = min(t * TH + warp, bh - 1);
+        const bool in_y = t * TH + warp < bh;
+        const int row0 = __ldg(ytile + t).x;                            // first source row staged for this tile
+        int r0, r1 = 0, b0 = 0, b1 = 0;
+        if (MODE == 2) r0 = __ldg(yofs + by) - row0;
+        else if (MODE == 4) r0 = by - row0;
+        else {
+            const int ys = __ldg(yofs + by);
+            r0 = min(max(ys, 0), sh - 1) - row0; r1 = min(max(ys + 1, 0), sh - 1) - row0;
+            const short* yb = reinterpret_cast<const short*>(blob + P->ycoef_off);
+            b0 = __ldg(yb + by * 2); b1 = __ldg(yb + by * 2 + 1);
+        }
+        mbar_wait(full + stage, phase);
+        const uint8_t* sbase = tile0 + stage * stage_bytes;
+        int v[SC];
+        if (MODE == 3) {
+            const uint8_t* q0 = sbase + r0 * rs; const uint8_t* q1 = sbase + r1 * rs;
+            int p00[SC], p01[SC], p10[SC], p11[SC];
+            if (SC == 4) {
+                const uint32_t w00 = *reinterpret_cast<const uint32_t*>(q0 + xo0), w01 = *reinterpret_cast<const uint32_t*>(q0 + xo1);
+                const uint32_t w10 = *reinterpret_cast<const uint32_t*>(q1 + xo0), w11 = *reinterpret_cast<const uint32_t*>(q1 + xo1);
+#pragma unroll
+                for (int c = 0; c < SC; c++) { p00[c] = (w00 >> (8 * c)) & 255; p01[c] = (w01 >> (8 * c)) & 255; p10[c] = (w10 >> (8 * c)) & 255; p11[c] = (w11 >> (8 * c)) & 255; }
+            } else {
+#pragma unroll
+                for (int c = 0; c < SC; c++) { p00[c] = q0[xo0 + c]; p01[c] = q0[xo1 + c]; p10[c] = q1[xo0 + c]; p11[c] = q1[xo1 + c]; }
+            }
+#pragma unroll
+            for (int c = 0; c < SC; c++) {                              // SURVEY App. A.4 / imp_gather_linear
+                const int h0 = p00[c] * a0 + p01[c] * a1, h1 = p10[c] * a0 + p11[c] * a1;
+                v[c] = ((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2) & 255;
+            }
+        } else {
+            const uint8_t* q = sbase + r0 * rs + xo0;
+            if (SC == 4) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(q);
+#pragma unroll
+                for (int c = 0; c < SC; c++) v[c] = (w >> (8 * c)) & 255;
+            } else {
+#pragma unroll
+                for (int c = 0; c < SC; c++) v[c] = q[c];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
+        if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+    }
+}
+
 template <int SC, int MODE>
 __global__ void __launch_bounds__(STRIP_THREADS, 3)
-imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one, const int NSTAGE) {
+imp_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one, const int NSTAGE) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int jn = blockIdx.y + blockIdx.z * 65535;
     if (jn >= count) return;
@@ -380,7 +456,9 @@ imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
     // ---- consumers ----
     const int col_off = job.tm_x0 - c0 * 8;                           // tile byte offset of source pixel 0
     const int bx0 = blockIdx.x * TW;
-    if (MODE == 0) {
+    if constexpr (MODE >= 2) {
+        gather_strip_consume<SC, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE);
+    } else if constexpr (MODE == 0) {
         switch (P->max_xtaps) {                                       // uniform over the pass
         case 1: area_strip_consume<SC, 1, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
         case 2: area_strip_consume<SC, 2, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
@@ -413,145 +491,36 @@ imp_area_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
     }
 }
 
-// ---- Gaussian blur (cvSmooth CV_GAUSSIAN) fused with the op list and the oriented store ------------
-// One CTA per 32x32 output tile. The (32+2R)^2 source neighbourhood arrives by ONE TMA box load (zero-filled outside
-// the tensor), border pixels are then replicated in shared memory (BORDER_REPLICATE), a horizontal pass leaves exact
-// u16 sums in shared memory, a vertical pass produces the blurred bytes, the op list runs per pixel, and the tile is
-// written in destination orientation so that a rotate=90/270 still stores 32-pixel contiguous rows.
-// Each thread keeps a sliding window of 8+2R samples in registers (8 outputs per window): ~2.5 shared loads and 2R+1
-// integer MACs per output byte and pass. R is the tap radius padded to {3,6,9,12}; zero taps change nothing.
-constexpr int BT = 32;                              // blur tile edge
-constexpr int BLUR_THREADS = 256;
-
-template <int SC, int R>
-__global__ void __launch_bounds__(BLUR_THREADS)
-imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int jn = blockIdx.y + blockIdx.z * 65535;
-    if (jn >= count) return;
-    const ImpJob* __restrict__ jp = jobs ? jobs + first + jn : &one;
-    ImpJob job;
-    job.src = jp->src; job.dst = jp->dst; job.pass = jp->pass; job.wm = jp->wm;
-    job.src_pitch = jp->src_pitch; job.dst_pitch = jp->dst_pitch; job.wm_pitch = jp->wm_pitch; job.wm_c = jp->wm_c; job.tm_x0 = jp->tm_x0;
-    const uint8_t* __restrict__ blob = job.pass;
-    const ImpPass* __restrict__ P = reinterpret_cast<const ImpPass*>(blob);
-    const int w = P->sw, h = P->sh;                                   // blur: base frame == source window
-    const int tiles_x = (w + BT - 1) / BT, tiles_y = (h + BT - 1) / BT;
-    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
-    constexpr int SPAN = BT + 2 * R;                                   // source rows / columns per tile
-    constexpr int HROW = BT * SC;                                      // u16 per row of the horizontal-pass buffer
-    constexpr int SROW = BT * SC + 4;                                  // staging row stride (bytes), padded against bank conflicts
-    const int rs = P->tile_rs;
-    const int nops = P->nops;
-    const int ops_bytes = (nops * (int)sizeof(ImpOp) + P->lut_bytes + 15) & ~15;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    uint8_t* s_ops = smem + 128;
-    uint8_t* tile = s_ops + ((ops_bytes + 127) & ~127);
-    uint16_t* hbuf = reinterpret_cast<uint16_t*>(tile + ((rs * SPAN + 127) & ~127));
-    uint8_t* stage = reinterpret_cast<uint8_t*>(hbuf + SPAN * HROW);
-    const int tid = threadIdx.x;
-    const int x0 = (blockIdx.x % tiles_x) * BT, y0 = (blockIdx.x / tiles_x) * BT;
-    // box origin: source pixel (x0-R, y0-R); 16-byte aligned in x as TMA requires (coordinates may be negative)
-    const int xbyte = job.tm_x0 + (x0 - R) * SC;
-    const int c0 = (xbyte >> 4) << 1;
-    const int col_off = job.tm_x0 - c0 * 8;                            // tile byte offset of source pixel 0
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, (uint32_t)(rs * SPAN));
-        tma_load_2d(tile, jp->tmap, c0, y0 - R, bar);
-    }
-    {
-        const uint4* gsrc = reinterpret_cast<const uint4*>(blob + P->ops_off);
-        uint4* sdst = reinterpret_cast<uint4*>(s_ops);
-        for (int i = tid; i < ops_bytes / 16; i += BLUR_THREADS) sdst[i] = __ldg(gsrc + i);
-    }
-    int k[2 * R + 1];
-    {
-        const int* taps = reinterpret_cast<const int*>(blob + P->tapsr_off);
-#pragma unroll
-        for (int i = 0; i < 2 * R + 1; i++) k[i] = __ldg(taps + i);
-    }
-    __syncthreads();
-    mbar_wait(bar, 0);
-
-    // BORDER_REPLICATE: fill the part of the neighbourhood that lies outside the image from the clamped pixel
-    if (x0 - R < 0 || y0 - R < 0 || x0 + BT + R > w || y0 + BT + R > h) {
-        for (int i = tid; i < SPAN * SPAN; i += BLUR_THREADS) {
-            const int ty = i / SPAN, tx = i - ty * SPAN;
-            const int X = x0 - R + tx, Y = y0 - R + ty;
-            const int cx = min(max(X, 0), w - 1), cy = min(max(Y, 0), h - 1);
-            if (cx != X || cy != Y) {
-                const uint8_t* s = tile + (cy - (y0 - R)) * rs + col_off + cx * SC;
-                uint8_t* d = tile + ty * rs + col_off + X * SC;
-#pragma unroll
-                for (int c = 0; c < SC; c++) d[c] = s[c];
-            }
+// Copies `rows` rows of `row_bytes` bytes from a shared-memory stage (row stride `ss`, a multiple of 16, stage 16-byte
+// aligned) to global rows: 16 bytes per thread when the destination rows are 16-byte addressable (the library's own
+// buffers always are), 4 bytes or single bytes otherwise. Consecutive threads write consecutive chunks of a row.
+__device__ __forceinline__ void tile_copy_out(const uint8_t* s, int ss, uint8_t* d, int dp, int row_bytes, int rows, int tid, int nt) {
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(d) | (unsigned)dp);
+    if ((mis & 15) == 0) {
+        const int nch = row_bytes >> 4, tail = row_bytes & 15;
+        for (int i = tid; i < rows * nch; i += nt) {
+            const int ry = i / nch, ch = i - ry * nch;
+            *reinterpret_cast<uint4*>(d + (size_t)ry * dp + 16 * ch) = *reinterpret_cast<const uint4*>(s + ry * ss + 16 * ch);
         }
-        __syncthreads();
-    }
-
-    // horizontal pass: item = (row, 8-pixel group, channel)
-    for (int item = tid; item < SPAN * 4 * SC; item += BLUR_THREADS) {
-        const int c = item % SC, g = (item / SC) & 3, row = item / (SC * 4);
-        const uint8_t* p = tile + row * rs + col_off + (x0 + g * 8 - R) * SC + c;
-        int sv[8 + 2 * R];
-#pragma unroll
-        for (int j = 0; j < 8 + 2 * R; j++) sv[j] = p[j * SC];
-        uint16_t* hp = hbuf + row * HROW + g * 8 * SC + c;
-#pragma unroll
-        for (int o = 0; o < 8; o++) {
-            int acc = 0;
-#pragma unroll
-            for (int i = 0; i < 2 * R + 1; i++) acc += sv[o + i] * k[i];
-            hp[o * SC] = (uint16_t)acc;
+        for (int i = tid; i < rows * tail; i += nt) {
+            const int ry = i / tail, b = (nch << 4) + i - ry * tail;
+            d[(size_t)ry * dp + b] = s[ry * ss + b];
         }
-    }
-    __syncthreads();
-    // vertical pass: item = (byte column, 8-row group)
-    for (int item = tid; item < HROW * 4; item += BLUR_THREADS) {
-        const int xb = item % HROW, g = item / HROW;
-        const uint16_t* p = hbuf + (g * 8) * HROW + xb;
-        int sv[8 + 2 * R];
-#pragma unroll
-        for (int j = 0; j < 8 + 2 * R; j++) sv[j] = p[j * HROW];
-#pragma unroll
-        for (int o = 0; o < 8; o++) {
-            unsigned acc = 32768u;
-#pragma unroll
-            for (int i = 0; i < 2 * R + 1; i++) acc += (unsigned)(sv[o + i] * k[i]);
-            stage[(g * 8 + o) * SROW + xb] = (uint8_t)(acc >> 16);
+    } else if ((mis & 3) == 0) {
+        const int nch = row_bytes >> 2, tail = row_bytes & 3;
+        for (int i = tid; i < rows * nch; i += nt) {
+            const int ry = i / nch, ch = i - ry * nch;
+            *reinterpret_cast<uint32_t*>(d + (size_t)ry * dp + 4 * ch) = *reinterpret_cast<const uint32_t*>(s + ry * ss + 4 * ch);
         }
-    }
-    __syncthreads();
-    // op list + store. With a transposing output map the lane runs along the tile's y so that consecutive lanes still
-    // write consecutive destination pixels.
-    const ImpFrameMap om = P->out;
-    const int oc = P->oc, dc = P->dc;
-    const int lane = tid & 31, wrp = tid >> 5;
-    constexpr int NPX = BT / 8;                                        // pixels per thread: the op loop runs once over all of them
-    ImpPx px[NPX];
-    int bxs[NPX], bys[NPX];
-    bool live[NPX];
-#pragma unroll
-    for (int it = 0; it < NPX; it++) {
-        const int u = wrp + it * 8;
-        const int lx = om.swap ? u : lane, ly = om.swap ? lane : u;
-        const int bx = x0 + lx, by = y0 + ly;
-        live[it] = bx < w && by < h;
-        bxs[it] = min(bx, w - 1); bys[it] = min(by, h - 1);            // out-of-frame slots compute on a valid pixel, never stored
-        const uint8_t* sp = stage + (bys[it] - y0) * SROW + (bxs[it] - x0) * SC;
-        px[it].b = sp[0]; px[it].g = sp[1]; px[it].r = sp[2]; px[it].a = (SC == 4) ? sp[3 % SC] : 255;
-    }
-    if (nops) imp_run_ops_n<NPX>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
-#pragma unroll
-    for (int it = 0; it < NPX; it++) {
-        if (!live[it]) continue;
-        const ImpPx& p = px[it];
-        int X, Y;
-        imp_map_xy(om, bxs[it], bys[it], X, Y);
-        uint8_t* d = job.dst + (size_t)Y * job.dst_pitch + (size_t)X * dc;
-        if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
-        else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
+        for (int i = tid; i < rows * tail; i += nt) {
+            const int ry = i / tail, b = (nch << 2) + i - ry * tail;
+            d[(size_t)ry * dp + b] = s[ry * ss + b];
+        }
+    } else {
+        for (int i = tid; i < rows * row_bytes; i += nt) {
+            const int ry = i / row_bytes, b = i - ry * row_bytes;
+            d[(size_t)ry * dp + b] = s[ry * ss + b];
+        }
     }
 }
 

@@ -412,6 +412,59 @@ def test_strip_kernels_watermark_under_all_orientations(gpu, orc):
                         _assert_same(out, ref, (rq, gx, gy, ox, oy), False)
 
 
+ORIENT = [[], ["flip=10"], ["flip=01"], ["rotate=90"], ["rotate=180"], ["rotate=270"], ["rotate=90", "flip=10"], ["flip=01", "rotate=270"]]
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_tile_kernels_orientations_sizes_and_packing(gpu, orc, c):
+    """The TMA tile kernels of round 2 — fused blur (dp4a/dp2a, tiled in destination space), cubic tile, and the strip
+    kernel's NN / LINEAR / index-map modes — on odd sizes that leave partial tiles on either side, under every output
+    orientation, with a watermark and the encoder-side packings (destination channel count != source's)."""
+    wm = rnd_image(5, 9, 13, 4)
+    kw = dict(allow_experiments=True, max_filters=8, max_w=0, max_h=0, watermark=wm, wm_gravity_x="r", wm_gravity_y="b", wm_offset_x=3, wm_offset_y=2, wm_opacity=70)
+    gathers = [dict(filters=["blur=0.7"]), dict(filters=["blur=2.3"]), dict(filters=["blur=3.2"]), dict(filters=["blur=4.1"]),
+               dict(resize="150,101,up"), dict(resize="97,140,up"), dict(resize="200,30,up"),
+               dict(resize="150,101,up", simple=True), dict(resize="31,23", simple=True),
+               dict(resize="150,101,up", interp=1), dict(resize="41,29", interp=1),
+               dict(crop="61px,37px,5px,3px"), dict()]
+    n = 0
+    for (h, w) in [(45, 70), (67, 131), (97, 33)]:
+        img = smooth_image(h + w + c, h, w, c)
+        for gi, g in enumerate(gathers):
+            if c == 1 and "filters" in g:
+                continue                                   # a gray frame is promoted before the blur: covered by c == 3
+            for oi, fl in enumerate(ORIENT):
+                rq = dict(g); rq["filters"] = list(g.get("filters", [])) + fl
+                if (gi + oi) % 3 == 0: rq["filters"] = rq["filters"] + ["vignette=0.7"]
+                if (gi + oi) % 4 == 1: rq["pack"] = 32 if oi % 2 else 24
+                if (gi + oi) % 5 == 2: rq["flatten"] = True
+                code, _, out = _gpu_run(gpu, img, kw, rq)
+                c2, _, ref = _oracle(orc, img, rq, kw)
+                assert code == c2 == 0, (rq, code, c2)
+                _assert_same(out, ref, ((h, w, c), rq), _has_vignette(rq))
+                n += 1
+    assert n > 200
+
+
+def test_many_lut_filters_fall_back_instead_of_failing(gpu, orc):
+    """a pass whose op list + LUTs push a tile kernel's shared-memory request over the opt-in limit must take the
+    direct kernel, not fail the launch (imgproc_max_filters_count raised far above the default)."""
+    img = smooth_image(3, 432, 768, 4)
+    kw = dict(max_filters=400, max_w=0, max_h=0)
+    many = ["gradmap=306090,eecc00", "gamma=1.1"] * 20 + ["gamma=0.9"] * 7          # 47 ops, 40 LUTs
+    for rq in (dict(resize="79,45", filters=many), dict(filters=["blur=2.3"] + many[:46])):
+        code, _, out = _gpu_run(gpu, img, kw, rq)
+        c2, _, ref = _oracle(orc, img, rq, kw)
+        assert code == c2 == 0, (code, c2, gpu.last_error())
+        _assert_same(out, ref, rq["filters"][:2], False)
+    # 3840x2160x4 -> resize=395: a 100 KB source tile + 2 ring stages + 33 KB of LUTs is over the limit
+    big = smooth_image(4, 2160, 3840, 4)
+    rq = dict(resize="395", filters=["gradmap=306090,eecc00"] * 40)
+    code, _, out = _gpu_run(gpu, big, kw, rq)
+    assert code == 0, gpu.last_error()
+    _assert_same(out, _oracle(orc, big, rq, kw)[2], "resize=395 + 40 gradmaps", False)
+
+
 def test_reference_runjob_with_the_gpu_path_dropped_in(gpu, orc):
     """The drop-in claim, executed: the reference's OWN RunJob (bridge.c:302-724), decode and encode included, compiled
     with INTEGRATION.md's call-site edits and linked against libimp_gpu.so (oracle/make_gpu_bridge.py ->

@@ -126,6 +126,10 @@ def test_error_code_matrix_appendix_e(hostsim):
         assert code(crop=c) == 0
     for c in ["40px,20", "5000px,10px", "0px,10px", "10px,10px,x,t", "10px,10px,55px,0px"]:
         assert code(crop=c) == 50
+    # pixel offsets near INT_MAX must not wrap past the window check (they reached the kernels as win_x = 2^31-1)
+    for c in ["10px,10px,2147483647px,0px", "10px,10px,0px,2147483647px", "10px,10px,4294967295px,0px", "10px,10px,2147483640px,2147483640px"]:
+        assert code(crop=c) == 50, c
+    assert code(crop="10px,10px", gravity="2147483647px,0px") == 50 and code(crop="10px,10px", gravity="0px,2147483647px") == 50
     assert code(crop="1,1", gravity="r") == 50 and code(crop="1,1", gravity="r,b") == 0
     assert code(resize="0,0") == 50 and code(resize="") == 50
     for r in ["100", "100,60", "0,30", "140,0,up"]:
