@@ -98,8 +98,9 @@ typedef struct imp_gpu_request {
     int                pack;          /* IMP_PACK_*: encoder-side layout of the result */
 } imp_gpu_request;
 
-typedef struct imp_gpu_plan  imp_gpu_plan;    /* validated, lowered, device-resident job recipe */
-typedef struct imp_gpu_batch imp_gpu_batch;   /* a set of (plan, source, destination) jobs launched together */
+typedef struct imp_gpu_plan   imp_gpu_plan;    /* validated, lowered, device-resident job recipe */
+typedef struct imp_gpu_batch  imp_gpu_batch;   /* a set of (plan, source, destination) jobs launched together */
+typedef struct imp_gpu_ticket imp_gpu_ticket;  /* an asynchronous host batch in flight */
 
 /* ---- lifetime ----------------------------------------------------------------------------------- */
 /* Creates the CUDA context on `device` for this process (call after fork). Idempotent per device. */
@@ -113,6 +114,13 @@ const char* imp_gpu_last_error(void);          /* thread-local text of the last 
  * re-pitch copy (short rows travel as one linear H2D copy and are laid out on the device) is not counted. */
 unsigned long long imp_gpu_launch_count(void);
 
+/* ---- overlays: PrepareWatermark (bridge.c:199-237) decodes the watermark ONCE per configuration --------- */
+/* Registers the decoded overlay and uploads it to the current device (call from OnEnvStart, after imp_gpu_init; or
+ * never: the first plan that uses an overlay registers it). Overlays are interned by CONTENT: every plan whose
+ * config carries the same pixels shares one host copy and one device copy per GPU, so a request never re-uploads it.
+ * Returns IMP_ERROR_NO_SUCH_WATERMARK for an unusable descriptor (what Watermark returns, bridge.c:240-242). */
+int  imp_gpu_upload_watermark(const imp_gpu_watermark* wm);
+
 /* ---- plans -------------------------------------------------------------------------------------- */
 /* Validates `req` against a source frame of src_w x src_h x src_c (8-bit, c in {1,3,4}) exactly as the
  * reference's operators would, in the reference's order; on success returns IMP_OK and a plan, else the
@@ -120,6 +128,11 @@ unsigned long long imp_gpu_launch_count(void);
 int  imp_gpu_plan_create(const imp_gpu_request* req, const imp_gpu_config* cfg,
                          int src_w, int src_h, int src_c, imp_gpu_plan** plan, int* step);
 void imp_gpu_plan_destroy(imp_gpu_plan* plan);
+/* Plans are immutable and reference counted: imp_gpu_plan_create serves a repeated (request, frame geometry, config)
+ * from an LRU cache (128 entries; IMP_GPU_PLAN_CACHE=n in the environment, 0 disables) without re-running the
+ * planner or touching the device; imp_gpu_plan_destroy drops the caller's reference. */
+void imp_gpu_plan_cache_stats(unsigned long long* hits, unsigned long long* misses, int* entries);
+void imp_gpu_plan_cache_clear(void);
 void imp_gpu_plan_output(const imp_gpu_plan* plan, int* w, int* h, int* c);
 /* Source window the plan actually reads (the crop window), for callers that upload only those rows. */
 void imp_gpu_plan_source_window(const imp_gpu_plan* plan, int* x, int* y, int* w, int* h);
@@ -149,16 +162,33 @@ int  imp_gpu_batch_size(const imp_gpu_batch* batch);
 unsigned long long imp_gpu_batch_algorithmic_bytes(const imp_gpu_batch* batch);
 int  imp_gpu_batch_launches_per_run(const imp_gpu_batch* batch);
 
-/* End to end over host buffers: n jobs staged through pinned buffers and `n_streams` CUDA streams
- * (H2D / kernels / D2H overlapped), on the current device; synchronous. */
+/* End to end over host buffers, on the current device; synchronous. The n jobs are cut into chunks of consecutive
+ * jobs; each chunk's crop windows are copied H2D, the whole chunk runs as ONE grouped launch per kernel variant
+ * (device job table, as imp_gpu_batch_launch), its results are copied D2H; `n_streams` (1..8) chunks are in flight on
+ * their own streams and pinned staging lanes, so copies and kernels overlap. The frame loops of RunJob
+ * (bridge.c:576-656) over album.Frames[] map onto one call. */
 int  imp_gpu_batch_run_host(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs,
                             const int* src_steps, unsigned char* const* dsts, const int* dst_steps,
                             int n_streams);
-/* Same, sharded round-robin (job i -> GPU i mod n_gpus) over devices 0..n_gpus-1 with one host thread
- * per GPU; no inter-GPU traffic. All devices are initialised on demand. */
+/* Asynchronous form (SURVEY 8b-4 submit/wait): returns at once with a ticket; a helper thread drives the batch on the
+ * caller's current device. The argument arrays are copied, the pixel buffers must stay valid until imp_gpu_batch_wait,
+ * which blocks, returns the batch's code and frees the ticket. imp_gpu_batch_poll: 1 when finished, 0 while running. */
+int  imp_gpu_batch_submit_host(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs,
+                               const int* src_steps, unsigned char* const* dsts, const int* dst_steps,
+                               int n_streams, imp_gpu_ticket** ticket);
+int  imp_gpu_batch_poll(const imp_gpu_ticket* ticket);
+int  imp_gpu_batch_wait(imp_gpu_ticket* ticket);
+/* Same work sharded over devices 0..n_gpus-1 with one host thread per GPU; no inter-GPU traffic (nothing crosses
+ * GPUs: docs/02 - Configuration.md:18 worker_processes is the reference's scale-out model). All devices are
+ * initialised on demand. imp_gpu_farm_run_host is round-robin (job i -> GPU i mod n_gpus). */
+#define IMP_FARM_ROUND_ROBIN 0
+#define IMP_FARM_SIZE_AWARE  1   /* largest job first onto the GPU with the fewest algorithmic bytes so far (mixed sizes) */
 int  imp_gpu_farm_run_host(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs,
                            const int* src_steps, unsigned char* const* dsts, const int* dst_steps,
                            int n_gpus, int n_streams);
+int  imp_gpu_farm_run_host_policy(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs,
+                                  const int* src_steps, unsigned char* const* dsts, const int* dst_steps,
+                                  int n_gpus, int n_streams, int policy);
 
 /* ---- first "next" row: CalcPerceivedBrightness (filters.c:707-729) as a device reduction -------- */
 /* What Info() (bridge.c:283-300) prints as round(brightness*100). The reference accumulates float32 in column-major

@@ -124,6 +124,14 @@ class Library:
         L.imp_gpu_batch_launches_per_run.argtypes = [C.c_void_p]
         L.imp_gpu_batch_run_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.imp_gpu_farm_run_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.imp_gpu_farm_run_host_policy.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.imp_gpu_batch_submit_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.imp_gpu_batch_wait.argtypes = [C.c_void_p]
+        L.imp_gpu_batch_poll.argtypes = [C.c_void_p]
+        L.imp_gpu_upload_watermark.argtypes = [C.POINTER(CWatermark)]
+        L.imp_gpu_plan_cache_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]
+        L.imp_gpu_plan_cache_stats.restype = None
+        L.imp_gpu_plan_cache_clear.restype = None
         L.imp_gpu_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         L.imp_gpu_free.argtypes = [C.c_void_p]
         L.imp_gpu_malloc_pitch.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int]
@@ -157,6 +165,19 @@ class Library:
 
     def launch_count(self) -> int:
         return int(self.lib.imp_gpu_launch_count())
+
+    def upload_watermark(self, cfg: "Config"):
+        """imp_gpu_upload_watermark: register the config's overlay and upload it to the current device (once)."""
+        ccfg, keep = cfg.to_c()
+        self.check(self.lib.imp_gpu_upload_watermark(ccfg.watermark))
+
+    def plan_cache_stats(self):
+        h, m, n = C.c_ulonglong(), C.c_ulonglong(), C.c_int()
+        self.lib.imp_gpu_plan_cache_stats(C.byref(h), C.byref(m), C.byref(n))
+        return dict(hits=int(h.value), misses=int(m.value), entries=n.value)
+
+    def plan_cache_clear(self):
+        self.lib.imp_gpu_plan_cache_clear()
 
     def ascii(self, img: np.ndarray, args: str = "") -> bytes:
         """ASCII (filters.c:486-522) of a host frame."""
@@ -275,18 +296,140 @@ class Batch:
             self.h = None
 
 
-def run_host_batch(lib: Library, plans: List[Plan], srcs: List[np.ndarray], dsts: List[np.ndarray], n_streams=4, n_gpus=0):
-    """imp_gpu_batch_run_host / imp_gpu_farm_run_host over numpy (or pinned) buffers."""
-    n = len(plans)
-    P = (C.c_void_p * n)(*[p.h for p in plans])
-    S = (C.c_void_p * n)(*[s.ctypes.data for s in srcs])
-    D = (C.c_void_p * n)(*[d.ctypes.data for d in dsts])
-    SS = (C.c_int * n)(*[s.strides[0] for s in srcs])
-    DS = (C.c_int * n)(*[d.strides[0] for d in dsts])
-    if n_gpus:
-        lib.check(lib.lib.imp_gpu_farm_run_host(n, P, S, SS, D, DS, n_gpus, n_streams))
-    else:
-        lib.check(lib.lib.imp_gpu_batch_run_host(n, P, S, SS, D, DS, n_streams))
+FARM_ROUND_ROBIN, FARM_SIZE_AWARE = 0, 1
+
+
+class HostJobs:
+    """The five parallel argument arrays of the host-batch entry points, built once (bench loops reuse them)."""
+
+    def __init__(self, plans: List[Plan], srcs: List[np.ndarray], dsts: List[np.ndarray]):
+        n = self.n = len(plans)
+        self.keep = (plans, srcs, dsts)
+        self.P = (C.c_void_p * n)(*[p.h for p in plans])
+        self.S = (C.c_void_p * n)(*[s.ctypes.data for s in srcs])
+        self.D = (C.c_void_p * n)(*[d.ctypes.data for d in dsts])
+        self.SS = (C.c_int * n)(*[s.strides[0] for s in srcs])
+        self.DS = (C.c_int * n)(*[d.strides[0] for d in dsts])
+
+    def run(self, lib: Library, n_streams=4, n_gpus=0, policy=FARM_ROUND_ROBIN):
+        if n_gpus:
+            lib.check(lib.lib.imp_gpu_farm_run_host_policy(self.n, self.P, self.S, self.SS, self.D, self.DS, n_gpus, n_streams, policy))
+        else:
+            lib.check(lib.lib.imp_gpu_batch_run_host(self.n, self.P, self.S, self.SS, self.D, self.DS, n_streams))
+
+    def submit(self, lib: Library, n_streams=4):
+        """imp_gpu_batch_submit_host: returns a ticket for wait()."""
+        t = C.c_void_p()
+        lib.check(lib.lib.imp_gpu_batch_submit_host(self.n, self.P, self.S, self.SS, self.D, self.DS, n_streams, C.byref(t)))
+        return t
+
+    @staticmethod
+    def poll(lib: Library, ticket) -> bool:
+        return bool(lib.lib.imp_gpu_batch_poll(ticket))
+
+    @staticmethod
+    def wait(lib: Library, ticket):
+        lib.check(lib.lib.imp_gpu_batch_wait(ticket))
+
+
+def run_host_batch(lib: Library, plans: List[Plan], srcs: List[np.ndarray], dsts: List[np.ndarray], n_streams=4, n_gpus=0, policy=FARM_ROUND_ROBIN):
+    """imp_gpu_batch_run_host / imp_gpu_farm_run_host[_policy] over numpy (or pinned) buffers."""
+    HostJobs(plans, srcs, dsts).run(lib, n_streams, n_gpus, policy)
+
+
+# ---- the reference-signature operator layer (include/imp_ops.h) -----------------------------------------------------
+class IplROI(C.Structure):
+    _fields_ = [("coi", C.c_int), ("xOffset", C.c_int), ("yOffset", C.c_int), ("width", C.c_int), ("height", C.c_int)]
+
+
+class IplImage(C.Structure):
+    """OpenCV 2.4 types_c.h layout (sizeof == 144 on x86-64), as include/imp_ops.h declares it."""
+    pass
+
+
+IplImage._fields_ = [("nSize", C.c_int), ("ID", C.c_int), ("nChannels", C.c_int), ("alphaChannel", C.c_int), ("depth", C.c_int),
+                     ("colorModel", C.c_char * 4), ("channelSeq", C.c_char * 4), ("dataOrder", C.c_int), ("origin", C.c_int),
+                     ("align", C.c_int), ("width", C.c_int), ("height", C.c_int), ("roi", C.POINTER(IplROI)),
+                     ("maskROI", C.POINTER(IplImage)), ("imageId", C.c_void_p), ("tileInfo", C.c_void_p), ("imageSize", C.c_int),
+                     ("imageData", C.c_void_p), ("widthStep", C.c_int), ("BorderMode", C.c_int * 4), ("BorderConst", C.c_int * 4),
+                     ("imageDataOrigin", C.c_void_p)]
+
+
+class OpsLayer:
+    """imp_Crop / imp_Resize / imp_Filter / imp_Watermark / imp_BlendWithPaper / imp_FlushAll driven the way RunJob's
+    loops (bridge.c:574-656) drive the reference's operators: record + validate per operator, one fused flush."""
+    CREATE_T = C.CFUNCTYPE(C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int)
+    RELEASE_T = C.CFUNCTYPE(None, C.POINTER(C.c_void_p))
+
+    def __init__(self, lib: Library):
+        self.L = lib
+        L = lib.lib
+        PP = C.POINTER(C.POINTER(IplImage))
+        L.imp_Crop.argtypes = [PP, C.c_char_p, C.c_char_p]
+        L.imp_Resize.argtypes = [PP, C.c_char_p, C.POINTER(CConfig), C.c_int]
+        L.imp_Filter.argtypes = [PP, C.c_char_p, C.c_int]
+        L.imp_Watermark.argtypes = [C.POINTER(IplImage), C.POINTER(CConfig)]
+        L.imp_BlendWithPaper.argtypes = [C.POINTER(IplImage)]
+        L.imp_FlushAll.argtypes = [PP, C.c_int]
+        L.imp_Discard.argtypes = [C.POINTER(IplImage)]
+        self.keep = []
+        self._cb = (self.CREATE_T(self._create), self.RELEASE_T(self._release))
+        L.imp_ops_set_image_allocator.argtypes = [self.CREATE_T, self.RELEASE_T]
+        L.imp_ops_set_image_allocator(*self._cb)
+
+    @staticmethod
+    def header(img: np.ndarray):
+        """IplImage header over `img` (H x W x C uint8, C-contiguous rows; widthStep = its row stride)."""
+        h, w, c = img.shape
+        im = IplImage()
+        im.nSize = C.sizeof(IplImage); im.nChannels = c; im.depth = 8; im.width = w; im.height = h; im.align = 4
+        im.widthStep = img.strides[0]; im.imageSize = img.strides[0] * h
+        im.imageData = img.ctypes.data; im.imageDataOrigin = img.ctypes.data
+        return im
+
+    def _create(self, w, h, depth, c):
+        step = (w * c + 3) & ~3
+        buf = np.empty((h, step), np.uint8)
+        im = IplImage()
+        im.nSize = C.sizeof(IplImage); im.nChannels = c; im.depth = depth; im.width = w; im.height = h; im.align = 4
+        im.widthStep = step; im.imageSize = step * h
+        im.imageData = buf.ctypes.data; im.imageDataOrigin = buf.ctypes.data
+        self.keep.append((im, buf))
+        return C.addressof(im)
+
+    def _release(self, pp):
+        pp[0] = None
+
+    def request(self, frames, cfg: Config, crop=None, gravity=None, resize=None, filters=(), simple=False, flatten=False):
+        """Steps 3-7 of RunJob over `frames` (numpy images): returns (code, list of results or None)."""
+        L = self.L.lib
+        self.keep = []
+        ccfg, keep = cfg.to_c()
+        enc = lambda t: None if t is None else t.encode("latin-1")
+        hdrs = [self.header(f) for f in frames]
+        ptrs = [C.pointer(h) for h in hdrs]
+        code = 0
+        for p in ptrs:                                                   # the per-frame loops of bridge.c:576-656
+            if crop is not None and not code: code = L.imp_Crop(C.byref(p), enc(crop), enc(gravity))
+            if resize is not None and not code: code = L.imp_Resize(C.byref(p), enc(resize), C.byref(ccfg), 1 if simple else 0)
+            for f in filters:
+                if not code: code = L.imp_Filter(C.byref(p), enc(f), 1 if cfg.allow_experiments else 0)
+            if cfg.watermark is not None and not code: code = L.imp_Watermark(p, C.byref(ccfg))
+            if flatten and not code: code = L.imp_BlendWithPaper(p)
+        if code:
+            for p in ptrs: L.imp_Discard(p)
+            return code, None
+        arr = (C.POINTER(IplImage) * len(ptrs))(*ptrs)
+        code = L.imp_FlushAll(arr, len(ptrs))
+        if code:
+            return code, None
+        outs = []
+        for k in range(len(ptrs)):
+            im = arr[k].contents
+            raw = (C.c_ubyte * (im.widthStep * im.height)).from_address(im.imageData)
+            a = np.frombuffer(raw, np.uint8).reshape(im.height, im.widthStep)[:, :im.width * im.nChannels]
+            outs.append(a.reshape(im.height, im.width, im.nChannels))
+        return 0, outs
 
 
 _default: Optional[Library] = None

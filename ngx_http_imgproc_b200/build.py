@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimp_gpu.so")
 SOURCES = ["imp_kernels.cu", "imp_gpu.cu", "imp_planner.cpp", "imp_ops.cpp"]
-HEADERS = ["imp_plan.h", "imp_pixel.cuh", "imp_gather.cuh", "imp_internal.h", "imp_tiles.cuh",
+HEADERS = ["imp_plan.h", "imp_pixel.cuh", "imp_gather.cuh", "imp_internal.h", "imp_tiles.cuh", "imp_blur.cuh", "imp_cubic.cuh",
            os.path.join("..", "..", "include", "imp_gpu.h"), os.path.join("..", "..", "include", "imp_ops.h")]
 
 NVCC_FLAGS = [
@@ -27,24 +27,50 @@ def nvcc() -> str:
     raise RuntimeError("nvcc not found; libimp_gpu.so cannot be built (there is no CPU fallback)")
 
 
-def stale() -> bool:
-    if not os.path.exists(LIB):
+OBJ = os.path.join(HERE, "build")
+COMPILE_FLAGS = [f for f in NVCC_FLAGS if f != "--shared"]
+
+
+def _deps(src: str):
+    return [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS]
+
+
+def _obj(src: str) -> str:
+    return os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+
+
+def _newer(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    t = os.path.getmtime(target)
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+def stale() -> bool:
+    return _newer(LIB, [d for s in SOURCES for d in _deps(s)])
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One object per source (compiled in parallel, only when its source or a header changed), then one link."""
     if not force and not stale():
         return LIB
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    todo = [s for s in srcs if force or _newer(_obj(s), _deps(s))]
+    procs = []
+    for s in todo:
+        cmd = [nvcc()] + COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj(s), os.path.join(CSRC, s)]
+        procs.append((s, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for s, pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}:\n" + out + err)
+        if verbose:
+            print(err)
+    link = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-o", LIB] + [_obj(s) for s in srcs]
+    res = subprocess.run(link, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

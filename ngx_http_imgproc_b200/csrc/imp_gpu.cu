@@ -10,33 +10,17 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <atomic>
-#include <map>
+#include <list>
 #include <mutex>
 #include <new>
 #include <thread>
+#include <unordered_map>
 
 namespace {
 
 constexpr int MAX_DEV = 16;
 thread_local char t_err[512] = "";
 thread_local int t_dev = -1;
-
-struct Lane {            // one in-flight host job of the end-to-end path
-    cudaStream_t st = nullptr;
-    uint8_t* d_in = nullptr; size_t in_cap = 0; uint8_t* d_out = nullptr; size_t out_cap = 0;
-    uint8_t* h_in = nullptr; size_t hin_cap = 0; uint8_t* h_out = nullptr; size_t hout_cap = 0;
-    uint8_t* d_scratch = nullptr; size_t scratch_cap = 0;
-    uint8_t* d_stage = nullptr; size_t stage_cap = 0;          // linear landing zone of the host rows (see issue())
-    int pending = -1; bool out_staged = false;
-};
-struct DevCtx {
-    bool ready = false;
-    cudaStream_t stream = nullptr;
-    std::vector<Lane> lanes;       // persistent staging, reused across calls
-    std::mutex run_mu;             // serialises users of `lanes`
-};
-DevCtx g_dev[MAX_DEV];
-std::mutex g_mu;
 
 int fail(cudaError_t e, const char* what, int line) {
     snprintf(t_err, sizeof t_err, "%s failed at imp_gpu.cu:%d: %s", what, line, cudaGetErrorString(e));
@@ -45,6 +29,82 @@ int fail(cudaError_t e, const char* what, int line) {
 int fail_msg(const char* msg) { snprintf(t_err, sizeof t_err, "%s", msg); return IMP_ERROR_GPU; }
 
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(e__, #call, __LINE__); } while (0)
+
+int align16(int v) { return (v + 15) & ~15; }
+size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+// A growable buffer (device or pinned host) that is only ever re-allocated when a request outgrows it.
+struct Buf {
+    uint8_t* p = nullptr; size_t cap = 0;
+    int grow(size_t need, bool host) {
+        if (need <= cap) return IMP_OK;
+        if (p) { if (host) CK(cudaFreeHost(p)); else CK(cudaFree(p)); p = nullptr; cap = 0; }
+        need = (need * 5 / 4 + 4095) & ~size_t(4095);
+        if (host) CK(cudaHostAlloc((void**)&p, need, cudaHostAllocDefault)); else CK(cudaMalloc((void**)&p, need));
+        cap = need;
+        return IMP_OK;
+    }
+    void release(bool host) { if (p) { if (host) cudaFreeHost(p); else cudaFree(p); } p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+// ---- batch ---------------------------------------------------------------------------------------------
+struct ImpTmKey {
+    uintptr_t a0; unsigned long long g0, g1; int pitch; unsigned b0, b1;
+    bool operator==(const ImpTmKey& o) const { return a0 == o.a0 && g0 == o.g0 && g1 == o.g1 && pitch == o.pitch && b0 == o.b0 && b1 == o.b1; }
+};
+struct ImpTmKeyHash {
+    size_t operator()(const ImpTmKey& k) const {
+        unsigned long long h = k.a0 * 0x9E3779B97F4A7C15ull;
+        h ^= (k.g0 + 0x632BE59BD9B4E019ull + (h << 6) + (h >> 2));
+        h ^= (k.g1 * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+        h ^= ((unsigned long long)(unsigned)k.pitch << 32 | k.b0) + (h << 6) + (h >> 2);
+        h ^= k.b1 + (h << 6) + (h >> 2);
+        return (size_t)h;
+    }
+};
+struct ImpTmap { unsigned char bytes[128]; };
+
+struct imp_gpu_batch {
+    struct Item { imp_gpu_plan* plan; const uint8_t* src; int sp; uint8_t* dst; int dp; };
+    std::vector<Item> items;
+    int dev = -1;
+    bool dirty = true;
+    // compiled form
+    std::vector<ImpJob> h_jobs;
+    ImpJob* d_jobs = nullptr; size_t jobs_cap = 0;
+    Buf h_pin;                                   // pinned staging of the job table (the upload is asynchronous)
+    cudaEvent_t up_ev = nullptr; bool up_pending = false;
+    bool table_needed = false;                   // false when every launch group holds one job (passed by value)
+    Buf scratch;
+    struct Step { bool generic_blur; ImpLaunchGroup g; int job; ImpPass hdr; size_t scratch_off; int smem; };
+    std::vector<Step> steps;
+    unsigned long long algo_bytes = 0;
+    int launches = 0;
+    // tensor maps are encoded once per (buffer, geometry): the staging lanes present the same addresses again and again
+    std::unordered_map<ImpTmKey, ImpTmap, ImpTmKeyHash> tmaps;
+};
+
+namespace {
+
+struct Lane {            // one in-flight chunk of host jobs of the end-to-end path
+    cudaStream_t st = nullptr;
+    Buf d_in, d_out, d_stage;                    // device: re-pitched crop windows, results, linear landing zone of short rows
+    Buf h_in, h_out;                             // pinned staging for host buffers that are not page-locked
+    imp_gpu_batch batch;                         // the chunk's job table, scratch and tensor maps
+    struct Out { int job; long long staged_off; };   // staged_off >= 0: copy from h_out after the sync
+    std::vector<Out> pend;
+};
+struct DevCtx {
+    bool ready = false;
+    cudaStream_t stream = nullptr;               // uploads (plans, overlays) and the library's default stream
+    Buf h_up; cudaEvent_t up_ev = nullptr; bool up_pending = false;   // pinned staging of plan uploads
+    std::vector<Lane*> lanes;                    // persistent staging, reused across calls
+    std::mutex run_mu;                           // serialises users of `lanes`
+};
+DevCtx g_dev[MAX_DEV];
+std::mutex g_mu;
 
 int cur_dev() {
     if (t_dev >= 0) return t_dev;
@@ -62,39 +122,82 @@ int bind() {          // make the thread's device current
 
 cudaStream_t pick_stream(void* s) { return s ? (cudaStream_t)s : g_dev[t_dev].stream; }
 
-int align16(int v) { return (v + 15) & ~15; }
+// The overlay on device `d` (uploaded once per device for the life of the image; caller holds g_mu).
+int wm_to_device(ImpWmImage* wm, int d) {
+    ImpWmImage::Dev& wd = wm->dev[d];
+    if (wd.d) return IMP_OK;
+    wd.pitch = align16(wm->w * wm->c);
+    CK(cudaMalloc((void**)&wd.d, (size_t)wd.pitch * wm->h));
+    // `pixels` lives as long as the image does, so the copy may stay in flight on the upload stream
+    CK(cudaMemcpy2DAsync(wd.d, wd.pitch, wm->pixels.data(), (size_t)wm->w * wm->c, (size_t)wm->w * wm->c, wm->h, cudaMemcpyHostToDevice, g_dev[d].stream));
+    return IMP_OK;
+}
 
-// Uploads the plan's pass blobs and watermark to the current device (once).
+void wm_release_device(ImpWmImage* wm) {
+    for (int d = 0; d < MAX_DEV; d++) {
+        if (!wm->dev[d].d) continue;
+        if (g_dev[d].ready && cudaSetDevice(d) == cudaSuccess) cudaFree(wm->dev[d].d);
+        wm->dev[d].d = nullptr;
+    }
+    if (t_dev >= 0) cudaSetDevice(t_dev);
+}
+struct WmHook { WmHook() { imp_wm_dev_release = wm_release_device; } } g_wm_hook;
+
+// Uploads the plan's pass blobs (+ vignette tables, overlay) to the current device, once. Nothing here blocks on the GPU:
+// one stream-ordered allocation, one copy from pinned staging on the device's upload stream, an event for the consumers.
 int plan_to_device(imp_gpu_plan* plan) {
     const int d = t_dev;
-    std::lock_guard<std::mutex> lk(g_mu);
     imp_gpu_plan::Dev& pd = plan->dev[d];
+    std::lock_guard<std::mutex> lk(g_mu);
     if (pd.ready) return IMP_OK;
+    DevCtx& ctx = g_dev[d];
+    std::vector<size_t> off(plan->passes.size());
+    size_t blob_total = 0;
+    for (size_t i = 0; i < plan->passes.size(); i++) { off[i] = blob_total; blob_total += align256(plan->passes[i].blob.size()); }
+    size_t total = blob_total;
+    struct Tab { size_t pass, op, off; };
+    std::vector<Tab> tabs;
+    for (size_t i = 0; i < plan->passes.size(); i++) {
+        const ImpPass& h = plan->passes[i].hdr;
+        const ImpOp* ops = reinterpret_cast<const ImpOp*>(plan->passes[i].blob.data() + h.ops_off);
+        for (int k = 0; k < h.nops; k++)
+            if (ops[k].kind == IMP_OP_VIGNETTE && ops[k].i[2] > 0) { tabs.push_back(Tab{i, (size_t)k, total}); total += align256((size_t)ops[k].i[2] * sizeof(float)); }
+    }
+    if (ctx.up_pending) { CK(cudaEventSynchronize(ctx.up_ev)); ctx.up_pending = false; }      // the staging buffer is free again
+    int rc = ctx.h_up.grow(blob_total, true); if (rc) return rc;
+    CK(cudaMallocAsync((void**)&pd.arena, std::max<size_t>(total, 256), ctx.stream));
     pd.pass_blobs.assign(plan->passes.size(), nullptr);
     for (size_t i = 0; i < plan->passes.size(); i++) {
-        std::vector<uint8_t> b = plan->passes[i].blob;            // per-device copy: vignette table pointers are patched in
-        const ImpPass& h = plan->passes[i].hdr;
-        ImpOp* ops = reinterpret_cast<ImpOp*>(b.data() + h.ops_off);
-        for (int k = 0; k < h.nops; k++) {
-            if (ops[k].kind != IMP_OP_VIGNETTE || ops[k].i[2] <= 0) continue;
-            float* tab = nullptr;
-            CK(cudaMalloc((void**)&tab, (size_t)ops[k].i[2] * sizeof(float)));
-            pd.vignette_tabs.push_back(tab);
-            CK(imp_build_vignette_table(tab, ops[k].i[2], ops[k].f[0], ops[k].f[1], g_dev[d].stream));
-            const unsigned long long v = (unsigned long long)(uintptr_t)tab;
-            ops[k].i[4] = (int)(unsigned)(v & 0xffffffffu); ops[k].i[5] = (int)(unsigned)(v >> 32);
-        }
-        CK(cudaMalloc((void**)&pd.pass_blobs[i], b.size()));
-        CK(cudaMemcpy(pd.pass_blobs[i], b.data(), b.size(), cudaMemcpyHostToDevice));
+        memcpy(ctx.h_up.p + off[i], plan->passes[i].blob.data(), plan->passes[i].blob.size());
+        pd.pass_blobs[i] = pd.arena + off[i];
     }
-    CK(cudaStreamSynchronize(g_dev[d].stream));
-    if (!plan->wm_pixels.empty()) {
-        pd.wm_pitch = align16(plan->wm_w * plan->wm_c);
-        CK(cudaMalloc((void**)&pd.wm, (size_t)pd.wm_pitch * plan->wm_h));
-        CK(cudaMemcpy2D(pd.wm, pd.wm_pitch, plan->wm_pixels.data(), (size_t)plan->wm_w * plan->wm_c,
-                        (size_t)plan->wm_w * plan->wm_c, plan->wm_h, cudaMemcpyHostToDevice));
+    for (const Tab& t : tabs) {                  // per-device copy of the op: the table pointer is patched in
+        const ImpPass& h = plan->passes[t.pass].hdr;
+        ImpOp* op = reinterpret_cast<ImpOp*>(ctx.h_up.p + off[t.pass] + h.ops_off) + t.op;
+        float* tab = reinterpret_cast<float*>(pd.arena + t.off);
+        CK(imp_build_vignette_table(tab, op->i[2], op->f[0], op->f[1], ctx.stream));
+        const unsigned long long v = (unsigned long long)(uintptr_t)tab;
+        op->i[4] = (int)(unsigned)(v & 0xffffffffu); op->i[5] = (int)(unsigned)(v >> 32);
     }
+    if (blob_total) CK(cudaMemcpyAsync(pd.arena, ctx.h_up.p, blob_total, cudaMemcpyHostToDevice, ctx.stream));
+    if (plan->wm) { rc = wm_to_device(plan->wm.get(), d); if (rc) return rc; }
+    if (!pd.ready_ev) CK(cudaEventCreateWithFlags(&pd.ready_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(pd.ready_ev, ctx.stream));
+    CK(cudaEventRecord(ctx.up_ev, ctx.stream));
+    ctx.up_pending = true;
+    pd.settled = false;
     pd.ready = true;
+    return IMP_OK;
+}
+
+// Orders work on `st` behind the plan's upload (a no-op once the upload is known to be complete).
+int plan_wait_ready(imp_gpu_plan* plan, cudaStream_t st) {
+    imp_gpu_plan::Dev& pd = plan->dev[t_dev];
+    if (pd.settled.load(std::memory_order_acquire)) return IMP_OK;
+    cudaError_t e = cudaEventQuery(pd.ready_ev);
+    if (e == cudaSuccess) { pd.settled.store(true, std::memory_order_release); return IMP_OK; }
+    if (e != cudaErrorNotReady) return fail(e, "cudaEventQuery", __LINE__);
+    if (st != g_dev[t_dev].stream) CK(cudaStreamWaitEvent(st, pd.ready_ev, 0));
     return IMP_OK;
 }
 
@@ -102,36 +205,67 @@ void plan_free_device(imp_gpu_plan* plan) {
     for (int d = 0; d < MAX_DEV; d++) {
         imp_gpu_plan::Dev& pd = plan->dev[d];
         if (!pd.ready) continue;
-        if (cudaSetDevice(d) != cudaSuccess) continue;
-        for (uint8_t* p : pd.pass_blobs) cudaFree(p);
-        if (pd.wm) cudaFree(pd.wm);
-        for (float* t : pd.vignette_tabs) cudaFree(t);
-        pd.vignette_tabs.clear(); pd.wm = nullptr;
+        if (g_dev[d].ready && cudaSetDevice(d) == cudaSuccess) {
+            if (pd.arena) cudaFree(pd.arena);            // synchronises: kernels that still read the blobs finish first
+            if (pd.ready_ev) cudaEventDestroy(pd.ready_ev);
+        }
+        pd.arena = nullptr; pd.ready_ev = nullptr; pd.pass_blobs.clear();
         pd.ready = false;
     }
 }
 
-int ops_smem(const ImpPass& h) { return std::max(16, h.nops * (int)sizeof(ImpOp) + h.lut_bytes); }
+void plan_release(imp_gpu_plan* plan) {          // drops one reference
+    if (!plan) return;
+    if (plan->refs.fetch_sub(1) > 1) return;
+    { std::lock_guard<std::mutex> lk(g_mu); plan_free_device(plan); }
+    if (t_dev >= 0) cudaSetDevice(t_dev);
+    delete plan;
+}
 
-}  // namespace
-
-// ---- batch ---------------------------------------------------------------------------------------------
-struct imp_gpu_batch {
-    struct Item { imp_gpu_plan* plan; const uint8_t* src; int sp; uint8_t* dst; int dp; };
-    std::vector<Item> items;
-    int dev = -1;
-    bool dirty = true;
-    // compiled form
-    std::vector<ImpJob> h_jobs;
-    ImpJob* d_jobs = nullptr; size_t jobs_cap = 0;
-    uint8_t* d_scratch = nullptr; size_t scratch_cap = 0;
-    struct Step { bool generic_blur; ImpLaunchGroup g; int job; ImpPass hdr; size_t scratch_off; int smem; };
-    std::vector<Step> steps;
-    unsigned long long algo_bytes = 0;
-    int launches = 0;
+// ---- plan cache: the same request on the same frame geometry under the same configuration is lowered once ---------------
+// (the reference re-parses every request, bridge.c:346-372; its per-config work, PrepareWatermark, happens once per cycle)
+struct PlanCache {
+    std::mutex mu;
+    std::list<std::pair<std::string, imp_gpu_plan*>> lru;             // most recent first; the cache holds one reference each
+    std::unordered_map<std::string, std::list<std::pair<std::string, imp_gpu_plan*>>::iterator> map;
+    size_t cap = 128;
+    unsigned long long hits = 0, misses = 0;
+    PlanCache() { const char* e = getenv("IMP_GPU_PLAN_CACHE"); if (e) cap = (size_t)std::max(0, atoi(e)); }
 };
+PlanCache g_cache;
 
-namespace {
+void key_str(std::string& k, const char* s) { if (s) { k += '1'; k += s; } else k += '0'; k += '\x1f'; }
+void key_int(std::string& k, long long v) { char b[32]; snprintf(b, sizeof b, "%lld\x1f", v); k += b; }
+
+std::string plan_key(const imp_gpu_request* req, const imp_gpu_config* cfg, int w, int h, int c, const ImpWmImage* wm) {
+    std::string k; k.reserve(192);
+    key_int(k, w); key_int(k, h); key_int(k, c);
+    key_str(k, req->crop); key_str(k, req->gravity); key_str(k, req->resize);
+    key_int(k, req->filter_count);
+    for (int i = 0; i < req->filter_count; i++) key_str(k, req->filters[i]);
+    key_int(k, req->simple_resize); key_int(k, req->flatten); key_int(k, req->interp); key_int(k, req->pack);
+    if (cfg) {
+        key_int(k, cfg->max_target_w); key_int(k, cfg->max_target_h); key_int(k, cfg->max_filters); key_int(k, cfg->allow_experiments);
+        if (cfg->watermark) {
+            const imp_gpu_watermark* m = cfg->watermark;
+            key_int(k, (long long)(uintptr_t)wm); key_int(k, m->gravity_x); key_int(k, m->gravity_y);
+            key_int(k, m->offset_x); key_int(k, m->offset_y); key_int(k, m->opacity);
+        } else k += "nowm";
+    } else k += "nocfg";
+    return k;
+}
+
+void cache_clear() {
+    std::vector<imp_gpu_plan*> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        for (auto& e : g_cache.lru) drop.push_back(e.second);
+        g_cache.lru.clear(); g_cache.map.clear();
+    }
+    for (imp_gpu_plan* p : drop) plan_release(p);
+}
+
+int ops_smem(const ImpPass& h) { return std::max(16, h.nops * (int)sizeof(ImpOp) + h.lut_bytes); }
 
 int pass_pitch(const ImpHostPass& hp) { return align16(hp.out_w * hp.out_c); }
 
@@ -167,7 +301,7 @@ ImpJob make_job(const imp_gpu_plan* p, int d, size_t k, const uint8_t* src, int 
     const imp_gpu_plan::Dev& pd = p->dev[d];
     ImpJob j{};
     j.pass = pd.pass_blobs[k];
-    j.wm = pd.wm; j.wm_pitch = pd.wm_pitch; j.wm_c = p->wm_c;
+    if (p->wm) { j.wm = p->wm->dev[d].d; j.wm_pitch = p->wm->dev[d].pitch; j.wm_c = p->wm->c; }
     if (k == 0) { j.src = src; j.src_pitch = sp; }
     else { j.src = scratch + off[k - 1]; j.src_pitch = pass_pitch(p->passes[k - 1]); }
     if (k + 1 == p->passes.size()) { j.dst = dst; j.dst_pitch = dp; }
@@ -196,7 +330,7 @@ EncodeTiledFn encode_tiled() {
 // Tensor map over the job's source window for the strip kernels: 8-byte elements, rows = window rows, origin =
 // the window's first byte aligned down to 16; box = tile_rs bytes x tile_rows rows. Out-of-range box parts are
 // zero-filled by the TMA unit, so edge tiles never touch memory outside the window's rows.
-int encode_job_tmap(const ImpPass& h, ImpJob& j) {
+int encode_job_tmap(const ImpPass& h, ImpJob& j, std::unordered_map<ImpTmKey, ImpTmap, ImpTmKeyHash>* cache = nullptr) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail_msg("cuTensorMapEncodeTiled is unavailable in this driver");
     const uintptr_t win = (uintptr_t)j.src + (size_t)h.sy0 * j.src_pitch + (size_t)h.sx0 * h.sc;
@@ -207,11 +341,21 @@ int encode_job_tmap(const ImpPass& h, ImpJob& j) {
     const cuuint32_t box[2] = {(cuuint32_t)(h.tile_rs / 8), (cuuint32_t)h.tile_rows};
     const cuuint32_t estr[2] = {1, 1};
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    const ImpTmKey key{a0, gdim[0], gdim[1], j.src_pitch, box[0], box[1]};
+    if (cache) {
+        auto it = cache->find(key);
+        if (it != cache->end()) { memcpy(j.tmap, it->second.bytes, 128); return IMP_OK; }
+    }
     CUtensorMap tm;
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)a0, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(t_err, sizeof t_err, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return IMP_ERROR_GPU; }
     memcpy(j.tmap, &tm, 128);
+    if (cache) {
+        if (cache->size() > 8192) cache->clear();
+        ImpTmap v; memcpy(v.bytes, &tm, 128);
+        cache->emplace(key, v);
+    }
     return IMP_OK;
 }
 
@@ -268,7 +412,9 @@ int variant_tiles(const ImpPass& h, int variant) {
     return pass_tiles(h);
 }
 
-int batch_compile(imp_gpu_batch* b) {
+// `up`: the stream the job table is uploaded on (the stream the launches follow on). Nothing here blocks unless a buffer
+// has to grow or the previous table of this batch is still being copied out of the pinned staging.
+int batch_compile(imp_gpu_batch* b, cudaStream_t up) {
     const int d = t_dev;
     b->dev = d;
     b->steps.clear(); b->h_jobs.clear(); b->algo_bytes = 0; b->launches = 0;
@@ -279,16 +425,12 @@ int batch_compile(imp_gpu_batch* b) {
         imp_gpu_plan* p = b->items[i].plan;
         int rc = plan_to_device(p);
         if (rc) return rc;
+        if ((rc = plan_wait_ready(p, up))) return rc;
         max_passes = std::max(max_passes, (int)p->passes.size());
         b->algo_bytes += p->algo_bytes;
         scratch = plan_scratch_layout(p, scratch, off[i], boff[i], b->items[i].src, b->items[i].sp);
     }
-    if (scratch > b->scratch_cap) {
-        if (b->d_scratch) CK(cudaFree(b->d_scratch));
-        b->d_scratch = nullptr; b->scratch_cap = 0;
-        CK(cudaMalloc((void**)&b->d_scratch, scratch));
-        b->scratch_cap = scratch;
-    }
+    { int rc = b->scratch.grow(scratch, false); if (rc) return rc; }
     // `occ`: how many CTAs of the job's shared-memory footprint fit an SM (capped at the 3 the register budget allows).
     // A launch takes the largest footprint of its group, so strip jobs are grouped by this class as well: a few big
     // tiles must not drag thousands of small ones down to two CTAs per SM.
@@ -303,9 +445,9 @@ int batch_compile(imp_gpu_batch* b) {
             const auto& it = b->items[i];
             if ((int)it.plan->passes.size() <= k) continue;
             const ImpHostPass& hp = it.plan->passes[k];
-            ImpJob jb = make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->d_scratch, off[i]);
+            ImpJob jb = make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->scratch.p, off[i]);
             const int variant = pick_variant(hp.hdr, jb);
-            if (variant == 1 || variant == 2 || variant == 4) { int rc = encode_job_tmap(hp.hdr, jb); if (rc) return rc; }
+            if (variant == 1 || variant == 2 || variant == 4) { int rc = encode_job_tmap(hp.hdr, jb, &b->tmaps); if (rc) return rc; }
             const int param = variant_param(hp.hdr, variant);
             pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, param, occ_class(hp.hdr, variant, param), jb, hp.hdr, boff[i][k]});
         }
@@ -342,15 +484,45 @@ int batch_compile(imp_gpu_batch* b) {
             s = e;
         }
     }
-    if (b->h_jobs.size() > b->jobs_cap) {
-        if (b->d_jobs) CK(cudaFree(b->d_jobs));
-        b->d_jobs = nullptr; b->jobs_cap = 0;
-        CK(cudaMalloc((void**)&b->d_jobs, b->h_jobs.size() * sizeof(ImpJob)));
-        b->jobs_cap = b->h_jobs.size();
+    // a launch group of one job takes it by value (kernel parameter): the device table is only needed for real groups
+    b->table_needed = false;
+    for (const auto& st : b->steps) if (!st.generic_blur && st.g.count > 1) b->table_needed = true;
+    if (b->table_needed) {
+        if (b->h_jobs.size() > b->jobs_cap) {
+            if (b->d_jobs) CK(cudaFree(b->d_jobs));
+            b->d_jobs = nullptr; b->jobs_cap = 0;
+            const size_t cap = b->h_jobs.size() * 5 / 4 + 16;
+            CK(cudaMalloc((void**)&b->d_jobs, cap * sizeof(ImpJob)));
+            b->jobs_cap = cap;
+        }
+        const size_t bytes = b->h_jobs.size() * sizeof(ImpJob);
+        if (b->up_pending) { CK(cudaEventSynchronize(b->up_ev)); b->up_pending = false; }
+        int rc = b->h_pin.grow(bytes, true); if (rc) return rc;
+        memcpy(b->h_pin.p, b->h_jobs.data(), bytes);
+        CK(cudaMemcpyAsync(b->d_jobs, b->h_pin.p, bytes, cudaMemcpyHostToDevice, up));
+        if (!b->up_ev) CK(cudaEventCreateWithFlags(&b->up_ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(b->up_ev, up));
+        b->up_pending = true;
     }
-    if (!b->h_jobs.empty()) CK(cudaMemcpy(b->d_jobs, b->h_jobs.data(), b->h_jobs.size() * sizeof(ImpJob), cudaMemcpyHostToDevice));
     b->dirty = false;
     return IMP_OK;
+}
+
+int batch_launch_steps(imp_gpu_batch* b, cudaStream_t st) {
+    for (const auto& s : b->steps) {
+        if (s.generic_blur) CK(imp_launch_blur_generic(b->h_jobs[s.job], s.hdr, (uint16_t*)(b->scratch.p + s.scratch_off), s.smem, st));
+        else if (s.g.count == 1) { ImpLaunchGroup g = s.g; g.first = 0; CK(imp_launch_group(g, nullptr, &b->h_jobs[s.g.first], st)); }
+        else CK(imp_launch_group(s.g, b->d_jobs, nullptr, st));
+    }
+    return IMP_OK;
+}
+
+void batch_release(imp_gpu_batch* b) {          // device/pinned memory of a batch (its device must be current)
+    if (b->d_jobs) cudaFree(b->d_jobs);
+    b->d_jobs = nullptr; b->jobs_cap = 0;
+    b->scratch.release(false); b->h_pin.release(true);
+    if (b->up_ev) cudaEventDestroy(b->up_ev);
+    b->up_ev = nullptr; b->up_pending = false;
 }
 
 // One frame with by-value job descriptors: no device job table, nothing to free afterwards.
@@ -362,7 +534,7 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
         const ImpHostPass& hp = p->passes[k];
         ImpJob j = make_job(p, t_dev, k, src, sp, dst, dp, scratch, off);
         const int variant = pick_variant(hp.hdr, j);
-        if (variant == 1 || variant == 2 || variant == 4) { int rc = encode_job_tmap(hp.hdr, j); if (rc) return rc; }
+        if (variant == 1 || variant == 2 || variant == 4) { int rc = encode_job_tmap(hp.hdr, j, nullptr); if (rc) return rc; }
         if (hp.hdr.kind == IMP_G_BLUR && variant == 0) {
             CK(imp_launch_blur_generic(j, hp.hdr, (uint16_t*)(scratch + boff[k]), ops_smem(hp.hdr), st));
         } else {
@@ -376,7 +548,167 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
 
 size_t plan_scratch_bytes(const imp_gpu_plan* p, const uint8_t* src = nullptr, int sp = 0) { std::vector<size_t> a, b; return plan_scratch_layout(p, 0, a, b, src, sp); }
 
+
+// ---- the chunked end-to-end path over host buffers ---------------------------------------------------------------------
+// Requests are cut into CHUNKS of consecutive jobs (up to kChunkJobs jobs / kChunkBytes of crop windows); a chunk owns one
+// lane (stream + staging) while it is in flight: H2D of every window, ONE grouped launch per kernel variant over the whole
+// chunk through a device job table (the path the device-resident batches take), D2H of every result. Lanes rotate, so the
+// copies of chunk k+1 overlap the kernels of chunk k and the D2H of chunk k-1 (PCIe is full duplex).
+constexpr int kChunkJobs = 256;
+constexpr size_t kChunkBytes = 128u << 20;
+
+struct HostJobs {
+    int n; imp_gpu_plan* const* plans; const unsigned char* const* srcs; const int* src_steps;
+    unsigned char* const* dsts; const int* dst_steps;
+};
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int lane_finish(Lane& L, const HostJobs& J) {
+    if (L.pend.empty()) return IMP_OK;
+    cudaError_t e = cudaStreamSynchronize(L.st);
+    if (e == cudaSuccess) {
+        for (const Lane::Out& o : L.pend) {
+            if (o.staged_off < 0) continue;
+            const imp_gpu_plan* p = J.plans[o.job];
+            const size_t row = (size_t)p->out_w * p->out_c;
+            for (int y = 0; y < p->out_h; y++) memcpy(J.dsts[o.job] + (size_t)y * J.dst_steps[o.job], L.h_out.p + o.staged_off + (size_t)y * row, row);
+        }
+    }
+    L.pend.clear();
+    if (e != cudaSuccess) return fail(e, "cudaStreamSynchronize", __LINE__);
+    return IMP_OK;
+}
+
+int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
+    const int m = last - first;
+    struct Lay { size_t in_off, out_off, stage_off, hin_off; long long hout_off; int in_pitch, out_pitch; bool src_pinned, dst_pinned, linear; size_t lin_bytes; };
+    std::vector<Lay> lay(m);
+    size_t in_total = 0, out_total = 0, stage_total = 0, hin_total = 0, hout_total = 0;
+    for (int k = 0; k < m; k++) {
+        const int i = first + k;
+        imp_gpu_plan* p = J.plans[i];
+        if (!p || !J.srcs[i] || !J.dsts[i]) return IMP_ERROR_INVALID_ARGS;
+        Lay& l = lay[k];
+        const size_t in_row = (size_t)p->win_w * p->src_c, out_row = (size_t)p->out_w * p->out_c;
+        l.in_pitch = align16((int)in_row); l.out_pitch = align16((int)out_row);
+        l.in_off = in_total; in_total += align256((size_t)l.in_pitch * p->win_h);
+        l.out_off = out_total; out_total += align256((size_t)l.out_pitch * p->out_h);
+        l.src_pinned = is_pinned(J.srcs[i]); l.dst_pinned = is_pinned(J.dsts[i]);
+        l.linear = false; l.lin_bytes = 0; l.stage_off = 0; l.hin_off = 0; l.hout_off = -1;
+        if (l.src_pinned) {
+            // A 2-D host-to-device copy pays ~0.15 us per row whatever its width (measured: 3.5 KB rows move at 23 GB/s,
+            // 14 KB rows at the link's 54 GB/s). Short rows therefore travel as ONE linear copy of the rows the window
+            // touches (full width) and a small kernel extracts / re-pitches the window on the device.
+            if (J.src_steps[i] <= 8192) {
+                l.linear = true;
+                l.lin_bytes = (size_t)(p->win_h - 1) * J.src_steps[i] + (size_t)p->win_x * p->src_c + in_row;
+                const bool direct = J.src_steps[i] == l.in_pitch && p->win_x == 0;
+                if (!direct) { l.stage_off = stage_total; stage_total += align256(l.lin_bytes); }
+            }
+        } else {
+            l.hin_off = hin_total; hin_total += align256((size_t)l.in_pitch * p->win_h);       // packed with the device pitch
+        }
+        if (!l.dst_pinned) { l.hout_off = (long long)hout_total; hout_total += align256(out_row * p->out_h); }
+    }
+    int r;
+    if ((r = L.d_in.grow(in_total, false)) || (r = L.d_out.grow(out_total, false)) || (r = L.d_stage.grow(stage_total, false)) ||
+        (r = L.h_in.grow(hin_total, true)) || (r = L.h_out.grow(hout_total, true))) return r;
+    imp_gpu_batch& B = L.batch;
+    B.items.clear(); B.dirty = true;
+    for (int k = 0; k < m; k++) {
+        const int i = first + k;
+        imp_gpu_plan* p = J.plans[i];
+        const Lay& l = lay[k];
+        const int sc = p->src_c;
+        const size_t in_row = (size_t)p->win_w * sc;
+        uint8_t* d_in = L.d_in.p + l.in_off;
+        const uint8_t* win = J.srcs[i] + (size_t)p->win_y * J.src_steps[i] + (size_t)p->win_x * sc;
+        if (!l.src_pinned) {
+            uint8_t* h = L.h_in.p + l.hin_off;
+            if ((size_t)J.src_steps[i] == (size_t)l.in_pitch && in_row == (size_t)l.in_pitch) memcpy(h, win, (size_t)l.in_pitch * p->win_h);
+            else for (int y = 0; y < p->win_h; y++) memcpy(h + (size_t)y * l.in_pitch, win + (size_t)y * J.src_steps[i], in_row);
+            CK(cudaMemcpyAsync(d_in, h, (size_t)l.in_pitch * p->win_h, cudaMemcpyHostToDevice, L.st));    // already in the device layout
+        } else if (l.linear) {
+            const uint8_t* h_lin = J.srcs[i] + (size_t)p->win_y * J.src_steps[i];
+            if (J.src_steps[i] == l.in_pitch && p->win_x == 0) {
+                CK(cudaMemcpyAsync(d_in, h_lin, l.lin_bytes, cudaMemcpyHostToDevice, L.st));
+            } else {
+                uint8_t* stage = L.d_stage.p + l.stage_off;
+                CK(cudaMemcpyAsync(stage, h_lin, l.lin_bytes, cudaMemcpyHostToDevice, L.st));
+                CK(imp_launch_repitch(stage + (size_t)p->win_x * sc, J.src_steps[i], d_in, l.in_pitch, (int)in_row, p->win_h, L.st));
+            }
+        } else {
+            CK(cudaMemcpy2DAsync(d_in, l.in_pitch, win, J.src_steps[i], in_row, p->win_h, cudaMemcpyHostToDevice, L.st));
+        }
+        // The device copy holds only the crop window; bias the base pointer so the pass's (sx0,sy0) lands on it.
+        const uint8_t* biased = d_in - ((size_t)p->win_y * l.in_pitch + (size_t)p->win_x * sc);
+        B.items.push_back(imp_gpu_batch::Item{p, biased, l.in_pitch, L.d_out.p + l.out_off, l.out_pitch});
+    }
+    if ((r = batch_compile(&B, L.st))) return r;
+    if ((r = batch_launch_steps(&B, L.st))) return r;
+    for (int k = 0; k < m; k++) {
+        const int i = first + k;
+        const imp_gpu_plan* p = J.plans[i];
+        const Lay& l = lay[k];
+        const size_t out_row = (size_t)p->out_w * p->out_c;
+        const uint8_t* d_out = L.d_out.p + l.out_off;
+        if (l.dst_pinned) {
+            if ((size_t)J.dst_steps[i] == (size_t)l.out_pitch) CK(cudaMemcpyAsync(J.dsts[i], d_out, (size_t)l.out_pitch * (p->out_h - 1) + out_row, cudaMemcpyDeviceToHost, L.st));
+            else CK(cudaMemcpy2DAsync(J.dsts[i], J.dst_steps[i], d_out, l.out_pitch, out_row, p->out_h, cudaMemcpyDeviceToHost, L.st));
+        } else {
+            CK(cudaMemcpy2DAsync(L.h_out.p + l.hout_off, out_row, d_out, l.out_pitch, out_row, p->out_h, cudaMemcpyDeviceToHost, L.st));
+        }
+        L.pend.push_back(Lane::Out{i, l.hout_off});
+    }
+    return IMP_OK;
+}
+
+int run_host_chunked(const HostJobs& J, int n_streams) {
+    DevCtx& ctx = g_dev[t_dev];
+    std::lock_guard<std::mutex> run_lk(ctx.run_mu);
+    n_streams = std::max(1, std::min(n_streams, 8));
+    while ((int)ctx.lanes.size() < n_streams) {
+        Lane* L = new (std::nothrow) Lane();
+        if (!L) return IMP_ERROR_MALLOC_FAILED;
+        cudaError_t e = cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete L; return fail(e, "cudaStreamCreateWithFlags", __LINE__); }
+        ctx.lanes.push_back(L);
+    }
+    int result = IMP_OK, chunk = 0, i = 0;
+    while (i < J.n && result == IMP_OK) {
+        Lane& L = *ctx.lanes[chunk % n_streams];
+        if ((result = lane_finish(L, J))) break;
+        int e = i; size_t bytes = 0;
+        // small batches are spread over the lanes instead of filling one chunk, so that copies and kernels still overlap
+        const int max_jobs = std::max(1, std::min(kChunkJobs, (J.n + n_streams - 1) / n_streams));
+        while (e < J.n && e - i < max_jobs) {
+            const imp_gpu_plan* p = J.plans[e];
+            if (!p) break;
+            const size_t need = (size_t)align16(p->win_w * p->src_c) * p->win_h;
+            if (e > i && bytes + need > kChunkBytes) break;
+            bytes += need; e++;
+        }
+        if (e == i) { result = IMP_ERROR_INVALID_ARGS; break; }
+        try { result = lane_issue(L, J, i, e); } catch (const std::bad_alloc&) { result = IMP_ERROR_MALLOC_FAILED; }
+        i = e; chunk++;
+    }
+    for (Lane* L : ctx.lanes) { int r = lane_finish(*L, J); if (result == IMP_OK) result = r; }
+    return result;
+}
+
 }  // namespace
+
+struct imp_gpu_ticket {
+    std::thread th;
+    int rc = IMP_OK; std::string err;
+    std::atomic<bool> done{false};
+    std::vector<imp_gpu_plan*> plans; std::vector<const unsigned char*> srcs; std::vector<unsigned char*> dsts; std::vector<int> ss, ds;
+};
 
 extern "C" {
 
@@ -408,6 +740,14 @@ int imp_gpu_init(int device) {
             }
             CK(cudaFree(0));
             CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c.up_ev, cudaEventDisableTiming));
+            // stream-ordered allocations (plan arenas, per-call scratch) keep their memory in the pool instead of going
+            // back to the driver at every synchronisation
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
             CK(imp_upload_tables());
             c.ready = true;
         }
@@ -425,25 +765,27 @@ int imp_gpu_set_device(int device) {
 }
 
 void imp_gpu_shutdown(void) {
+    cache_clear();                     // cached plans and registered overlays go first: their device memory is still reachable
+    imp_wm_registry_clear();
     std::lock_guard<std::mutex> lk(g_mu);
     for (int d = 0; d < MAX_DEV; d++) {
         DevCtx& c = g_dev[d];
         if (!c.ready) continue;
         if (cudaSetDevice(d) == cudaSuccess) {
             cudaDeviceSynchronize();
-            for (Lane& L : c.lanes) {
-                if (L.d_in) cudaFree(L.d_in);
-                if (L.d_out) cudaFree(L.d_out);
-                if (L.d_scratch) cudaFree(L.d_scratch);
-                if (L.d_stage) cudaFree(L.d_stage);
-                if (L.h_in) cudaFreeHost(L.h_in);
-                if (L.h_out) cudaFreeHost(L.h_out);
-                if (L.st) cudaStreamDestroy(L.st);
+            for (Lane* L : c.lanes) {
+                L->d_in.release(false); L->d_out.release(false); L->d_stage.release(false);
+                L->h_in.release(true); L->h_out.release(true);
+                batch_release(&L->batch);
+                if (L->st) cudaStreamDestroy(L->st);
+                delete L;
             }
             c.lanes.clear();
+            c.h_up.release(true);
+            if (c.up_ev) cudaEventDestroy(c.up_ev);
             if (c.stream) cudaStreamDestroy(c.stream);
         }
-        c.stream = nullptr; c.ready = false;
+        c.stream = nullptr; c.up_ev = nullptr; c.up_pending = false; c.ready = false;
     }
     t_dev = -1;
 }
@@ -451,15 +793,64 @@ void imp_gpu_shutdown(void) {
 const char* imp_gpu_last_error(void) { return t_err; }
 unsigned long long imp_gpu_launch_count(void) { return imp_launches(); }
 
+// ---- overlays -------------------------------------------------------------------------------------------
+int imp_gpu_upload_watermark(const imp_gpu_watermark* wm) {
+    int rc = bind(); if (rc) return rc;
+    if (!wm || !wm->pixels || wm->width <= 0 || wm->height <= 0 || (wm->channels != 3 && wm->channels != 4) || wm->step < wm->width * wm->channels)
+        return IMP_ERROR_NO_SUCH_WATERMARK;
+    try {
+        std::shared_ptr<ImpWmImage> img = imp_wm_intern(wm);
+        std::lock_guard<std::mutex> lk(g_mu);
+        return wm_to_device(img.get(), t_dev);
+    } catch (const std::bad_alloc&) { return IMP_ERROR_MALLOC_FAILED; }
+}
+
 // ---- plans ---------------------------------------------------------------------------------------------
 int imp_gpu_plan_create(const imp_gpu_request* req, const imp_gpu_config* cfg, int w, int h, int c, imp_gpu_plan** out, int* step) {
     if (out) *out = nullptr;
     if (!out) return IMP_ERROR_INVALID_ARGS;
     imp_gpu_plan* p = nullptr;
     try {
+        std::string key;
+        const bool cacheable = g_cache.cap > 0 && req && w > 0 && h > 0 && req->filter_count >= 0 && (req->filter_count == 0 || req->filters);
+        if (cacheable) {
+            std::shared_ptr<ImpWmImage> wm;
+            const imp_gpu_watermark* m = cfg ? cfg->watermark : nullptr;
+            if (m && m->pixels && m->width > 0 && m->height > 0 && (m->channels == 3 || m->channels == 4)) wm = imp_wm_intern(m);
+            key = plan_key(req, cfg, w, h, c, wm.get());
+            std::lock_guard<std::mutex> lk(g_cache.mu);
+            auto it = g_cache.map.find(key);
+            if (it != g_cache.map.end()) {
+                g_cache.lru.splice(g_cache.lru.begin(), g_cache.lru, it->second);
+                imp_gpu_plan* hit = it->second->second;
+                hit->refs.fetch_add(1);
+                g_cache.hits++;
+                if (step) *step = IMP_STEP_ENCODE;
+                *out = hit;
+                return IMP_OK;
+            }
+            g_cache.misses++;
+        }
         p = new imp_gpu_plan();
         int rc = imp_build_plan(req, cfg, w, h, c, p, step);
         if (rc) { delete p; return rc; }
+        if (cacheable) {
+            imp_gpu_plan* evicted = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(g_cache.mu);
+                if (g_cache.map.find(key) == g_cache.map.end()) {
+                    p->refs.fetch_add(1);                              // the cache's reference
+                    g_cache.lru.emplace_front(key, p);
+                    g_cache.map[key] = g_cache.lru.begin();
+                    if (g_cache.lru.size() > g_cache.cap) {
+                        evicted = g_cache.lru.back().second;
+                        g_cache.map.erase(g_cache.lru.back().first);
+                        g_cache.lru.pop_back();
+                    }
+                }
+            }
+            if (evicted) plan_release(evicted);
+        }
     } catch (const std::bad_alloc&) {
         delete p; return IMP_ERROR_MALLOC_FAILED;
     } catch (...) {
@@ -469,12 +860,13 @@ int imp_gpu_plan_create(const imp_gpu_request* req, const imp_gpu_config* cfg, i
     return IMP_OK;
 }
 
-void imp_gpu_plan_destroy(imp_gpu_plan* plan) {
-    if (!plan) return;
-    { std::lock_guard<std::mutex> lk(g_mu); plan_free_device(plan); }
-    if (t_dev >= 0) cudaSetDevice(t_dev);
-    delete plan;
+void imp_gpu_plan_destroy(imp_gpu_plan* plan) { plan_release(plan); }
+
+void imp_gpu_plan_cache_stats(unsigned long long* hits, unsigned long long* misses, int* entries) {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    if (hits) *hits = g_cache.hits; if (misses) *misses = g_cache.misses; if (entries) *entries = (int)g_cache.lru.size();
 }
+void imp_gpu_plan_cache_clear(void) { cache_clear(); }
 
 void imp_gpu_plan_output(const imp_gpu_plan* p, int* w, int* h, int* c) {
     if (w) *w = p->out_w; if (h) *h = p->out_h; if (c) *c = p->out_c;
@@ -494,8 +886,7 @@ int imp_gpu_batch_create(imp_gpu_batch** out) {
 void imp_gpu_batch_destroy(imp_gpu_batch* b) {
     if (!b) return;
     if (b->dev >= 0 && cudaSetDevice(b->dev) == cudaSuccess) {
-        if (b->d_jobs) cudaFree(b->d_jobs);
-        if (b->d_scratch) cudaFree(b->d_scratch);
+        batch_release(b);
         if (t_dev >= 0) cudaSetDevice(t_dev);
     }
     delete b;
@@ -520,16 +911,12 @@ int imp_gpu_batch_launch(imp_gpu_batch* b, void* stream) {
     int rc = bind(); if (rc) return rc;
     if (!b) return IMP_ERROR_INVALID_ARGS;
     if (b->items.empty()) return IMP_OK;
+    cudaStream_t st = pick_stream(stream);
     if (b->dirty || b->dev != t_dev) {
-        try { rc = batch_compile(b); } catch (const std::bad_alloc&) { return IMP_ERROR_MALLOC_FAILED; }
+        try { rc = batch_compile(b, st); } catch (const std::bad_alloc&) { return IMP_ERROR_MALLOC_FAILED; }
         if (rc) return rc;
     }
-    cudaStream_t st = pick_stream(stream);
-    for (const auto& s : b->steps) {
-        if (s.generic_blur) CK(imp_launch_blur_generic(b->h_jobs[s.job], s.hdr, (uint16_t*)(b->d_scratch + s.scratch_off), s.smem, st));
-        else CK(imp_launch_group(s.g, b->d_jobs, nullptr, st));
-    }
-    return IMP_OK;
+    return batch_launch_steps(b, st);
 }
 
 // ---- one frame -----------------------------------------------------------------------------------------
@@ -541,6 +928,7 @@ int imp_gpu_run_device(imp_gpu_plan* plan, const void* d_src, int sp, void* d_ds
     if (plan->src_c == 4 && (sp % 4 || ((uintptr_t)d_src) % 4)) return IMP_ERROR_INVALID_ARGS;
     if ((rc = plan_to_device(plan))) return rc;
     cudaStream_t st = pick_stream(stream);
+    if ((rc = plan_wait_ready(plan, st))) return rc;
     const size_t need = plan_scratch_bytes(plan, (const uint8_t*)d_src, sp);
     uint8_t* scratch = nullptr;
     if (need) CK(cudaMallocAsync((void**)&scratch, need, st));        // stream-ordered: stays asynchronous
@@ -557,109 +945,86 @@ int imp_gpu_run_host(imp_gpu_plan* plan, const unsigned char* src, int src_step,
     return imp_gpu_batch_run_host(1, plans, srcs, ss, dsts, ds, 1);
 }
 
-// End-to-end: per lane (stream) a device input/output buffer; jobs are issued round-robin so that the
-// H2D of job i+1 overlaps the kernels of job i and the D2H of job i-1. Only the crop window travels.
-// A host pointer that is not page-locked is first copied into a pinned staging buffer.
+// End to end over host buffers (see run_host_chunked above). Only the crop window of a frame travels; a host pointer
+// that is not page-locked goes through the lane's pinned staging.
 int imp_gpu_batch_run_host(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs, const int* src_steps,
                            unsigned char* const* dsts, const int* dst_steps, int n_streams) {
     int rc = bind(); if (rc) return rc;
     if (n <= 0) return IMP_OK;
     if (!plans || !srcs || !src_steps || !dsts || !dst_steps) return IMP_ERROR_INVALID_ARGS;
-    DevCtx& ctx = g_dev[t_dev];
-    std::lock_guard<std::mutex> run_lk(ctx.run_mu);
-    n_streams = std::max(1, std::min(n_streams, std::min(n, 8)));
-    while ((int)ctx.lanes.size() < n_streams) {
-        Lane L;
-        CK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
-        ctx.lanes.push_back(L);
-    }
-    auto is_pinned = [](const void* p) {
-        cudaPointerAttributes a;
-        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-        return a.type == cudaMemoryTypeHost;
-    };
-    auto finish = [&](Lane& L) -> int {
-        if (L.pending < 0) return IMP_OK;
-        const int i = L.pending; L.pending = -1;
-        CK(cudaStreamSynchronize(L.st));
-        if (L.out_staged) {
-            const imp_gpu_plan* p = plans[i];
-            const size_t row = (size_t)p->out_w * p->out_c;
-            for (int y = 0; y < p->out_h; y++) memcpy(dsts[i] + (size_t)y * dst_steps[i], L.h_out + (size_t)y * row, row);
-        }
-        return IMP_OK;
-    };
-    auto grow = [&](uint8_t*& p, size_t& cap, size_t need, bool host) -> int {
-        if (need <= cap) return IMP_OK;
-        if (p) { if (host) CK(cudaFreeHost(p)); else CK(cudaFree(p)); p = nullptr; cap = 0; }
-        need = (need * 5 / 4 + 4095) & ~size_t(4095);
-        if (host) CK(cudaHostAlloc((void**)&p, need, cudaHostAllocDefault)); else CK(cudaMalloc((void**)&p, need));
-        cap = need;
-        return IMP_OK;
-    };
-    auto issue = [&](Lane& L, int i) -> int {
-        imp_gpu_plan* p = plans[i];
-        if (!p || !srcs[i] || !dsts[i]) return IMP_ERROR_INVALID_ARGS;
-        int r = plan_to_device(p); if (r) return r;
-        const int sc = p->src_c;
-        const size_t in_row = (size_t)p->win_w * sc, out_row = (size_t)p->out_w * p->out_c;
-        const int in_pitch = align16((int)in_row), out_pitch = align16((int)out_row);
-        if ((r = grow(L.d_in, L.in_cap, (size_t)in_pitch * p->win_h, false))) return r;
-        if ((r = grow(L.d_out, L.out_cap, (size_t)out_pitch * p->out_h, false))) return r;
-        if ((r = grow(L.d_scratch, L.scratch_cap, plan_scratch_bytes(p), false))) return r;
-        const uint8_t* win = srcs[i] + (size_t)p->win_y * src_steps[i] + (size_t)p->win_x * sc;
-        // A 2-D host-to-device copy pays ~0.15 us per row whatever its width (measured: 3.5 KB rows move at 23 GB/s,
-        // 14 KB rows at the link's 54 GB/s). Short rows therefore travel as ONE linear copy of the rows the window
-        // touches (full width) and a small kernel extracts / re-pitches the window on the device.
-        const uint8_t* h_lin = nullptr; size_t lin_bytes = 0; int lin_step = 0; size_t lin_off = 0;
-        if (is_pinned(srcs[i])) {
-            if (src_steps[i] <= 8192) {
-                h_lin = srcs[i] + (size_t)p->win_y * src_steps[i]; lin_step = src_steps[i]; lin_off = (size_t)p->win_x * sc;
-                lin_bytes = (size_t)(p->win_h - 1) * src_steps[i] + lin_off + in_row;
-            }
-        } else {
-            if ((r = grow(L.h_in, L.hin_cap, in_row * p->win_h, true))) return r;
-            for (int y = 0; y < p->win_h; y++) memcpy(L.h_in + (size_t)y * in_row, win + (size_t)y * src_steps[i], in_row);
-            h_lin = L.h_in; lin_step = (int)in_row; lin_off = 0; lin_bytes = in_row * p->win_h;
-        }
-        if (h_lin && lin_step == in_pitch && lin_off == 0) {
-            CK(cudaMemcpyAsync(L.d_in, h_lin, lin_bytes, cudaMemcpyHostToDevice, L.st));              // already in the device layout
-        } else if (h_lin) {
-            if ((r = grow(L.d_stage, L.stage_cap, lin_bytes, false))) return r;
-            CK(cudaMemcpyAsync(L.d_stage, h_lin, lin_bytes, cudaMemcpyHostToDevice, L.st));
-            CK(imp_launch_repitch(L.d_stage + lin_off, lin_step, L.d_in, in_pitch, (int)in_row, p->win_h, L.st));
-        } else {
-            CK(cudaMemcpy2DAsync(L.d_in, in_pitch, win, src_steps[i], in_row, p->win_h, cudaMemcpyHostToDevice, L.st));
-        }
-        // The device copy holds only the crop window; bias the base pointer so the pass's (sx0,sy0) lands on it.
-        const uint8_t* biased = L.d_in - ((size_t)p->win_y * in_pitch + (size_t)p->win_x * sc);
-        if ((r = launch_single(p, biased, in_pitch, L.d_out, out_pitch, L.d_scratch, L.st))) return r;
-        L.out_staged = !is_pinned(dsts[i]);
-        if (!L.out_staged) {
-            CK(cudaMemcpy2DAsync(dsts[i], dst_steps[i], L.d_out, out_pitch, out_row, p->out_h, cudaMemcpyDeviceToHost, L.st));
-        } else {
-            if ((r = grow(L.h_out, L.hout_cap, out_row * p->out_h, true))) return r;
-            CK(cudaMemcpy2DAsync(L.h_out, out_row, L.d_out, out_pitch, out_row, p->out_h, cudaMemcpyDeviceToHost, L.st));
-        }
-        L.pending = i;
-        return IMP_OK;
-    };
-    int result = IMP_OK;
-    for (int i = 0; i < n && result == IMP_OK; i++) {
-        Lane& L = ctx.lanes[i % n_streams];
-        if ((result = finish(L))) break;
-        result = issue(L, i);
-    }
-    for (int s = 0; s < n_streams; s++) { int r = finish(ctx.lanes[s]); if (result == IMP_OK) result = r; }
-    return result;
+    const HostJobs J{n, plans, srcs, src_steps, dsts, dst_steps};
+    try { return run_host_chunked(J, n_streams); } catch (const std::bad_alloc&) { return IMP_ERROR_MALLOC_FAILED; }
 }
 
-int imp_gpu_farm_run_host(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs, const int* src_steps,
-                          unsigned char* const* dsts, const int* dst_steps, int n_gpus, int n_streams) {
-    if (n_gpus <= 0) return IMP_ERROR_INVALID_ARGS;
+// Asynchronous form: the call returns at once, a helper thread of the library drives the batch on the caller's current
+// device, imp_gpu_batch_wait() joins it. The argument arrays are copied; the pixel buffers must stay valid until the wait.
+int imp_gpu_batch_submit_host(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs, const int* src_steps,
+                              unsigned char* const* dsts, const int* dst_steps, int n_streams, imp_gpu_ticket** ticket) {
+    if (!ticket) return IMP_ERROR_INVALID_ARGS;
+    *ticket = nullptr;
+    int rc = bind(); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!plans || !srcs || !src_steps || !dsts || !dst_steps))) return IMP_ERROR_INVALID_ARGS;
+    imp_gpu_ticket* t = nullptr;
+    try {
+        t = new imp_gpu_ticket();
+        t->plans.assign(plans, plans + n); t->srcs.assign(srcs, srcs + n); t->dsts.assign(dsts, dsts + n);
+        t->ss.assign(src_steps, src_steps + n); t->ds.assign(dst_steps, dst_steps + n);
+        for (imp_gpu_plan* p : t->plans) if (p) p->refs.fetch_add(1);          // the batch keeps its plans alive
+        const int dev = t_dev;
+        t->th = std::thread([t, dev, n, n_streams]() {
+            int r = imp_gpu_set_device(dev);
+            if (r == IMP_OK) r = imp_gpu_batch_run_host(n, t->plans.data(), t->srcs.data(), t->ss.data(), t->dsts.data(), t->ds.data(), n_streams);
+            t->rc = r;
+            if (r) t->err = t_err;
+            t->done.store(true, std::memory_order_release);
+        });
+    } catch (...) {
+        if (t) { for (imp_gpu_plan* p : t->plans) if (p) plan_release(p); delete t; }
+        return IMP_ERROR_MALLOC_FAILED;
+    }
+    *ticket = t;
+    return IMP_OK;
+}
+
+int imp_gpu_batch_poll(const imp_gpu_ticket* ticket) { return ticket && ticket->done.load(std::memory_order_acquire) ? 1 : 0; }
+
+int imp_gpu_batch_wait(imp_gpu_ticket* ticket) {
+    if (!ticket) return IMP_ERROR_INVALID_ARGS;
+    if (ticket->th.joinable()) ticket->th.join();
+    const int rc = ticket->rc;
+    if (rc) snprintf(t_err, sizeof t_err, "%s", ticket->err.c_str());
+    for (imp_gpu_plan* p : ticket->plans) if (p) plan_release(p);
+    delete ticket;
+    return rc;
+}
+
+// Independent frames over the GPUs of one box, one host thread per GPU, no inter-GPU traffic.
+// IMP_FARM_ROUND_ROBIN: job i -> GPU i mod n_gpus. IMP_FARM_SIZE_AWARE: largest job first onto the GPU with the least
+// algorithmic bytes so far (mixed-size farms: evens out the bytes per GPU).
+int imp_gpu_farm_run_host_policy(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs, const int* src_steps,
+                                 unsigned char* const* dsts, const int* dst_steps, int n_gpus, int n_streams, int policy) {
+    if (n_gpus <= 0 || (policy != IMP_FARM_ROUND_ROBIN && policy != IMP_FARM_SIZE_AWARE)) return IMP_ERROR_INVALID_ARGS;
+    if (n > 0 && (!plans || !srcs || !src_steps || !dsts || !dst_steps)) return IMP_ERROR_INVALID_ARGS;
     const int avail = imp_gpu_device_count();
     if (avail <= 0) return fail_msg("no CUDA device available; libimp_gpu has no CPU fallback");
     if (n_gpus > avail || n_gpus > MAX_DEV) return fail_msg("imp_gpu_farm_run_host: more GPUs requested than present");
+    std::vector<std::vector<int>> share(n_gpus);
+    try {
+        if (policy == IMP_FARM_SIZE_AWARE) {
+            std::vector<int> order(n);
+            for (int i = 0; i < n; i++) { if (!plans[i]) return IMP_ERROR_INVALID_ARGS; order[i] = i; }
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return plans[a]->algo_bytes > plans[b]->algo_bytes; });
+            std::vector<unsigned long long> load(n_gpus, 0);
+            for (int i : order) {
+                int g = 0;
+                for (int k = 1; k < n_gpus; k++) if (load[k] < load[g]) g = k;
+                load[g] += plans[i]->algo_bytes; share[g].push_back(i);
+            }
+            for (auto& s : share) std::sort(s.begin(), s.end());           // each GPU walks its jobs in request order
+        } else {
+            for (int i = 0; i < n; i++) share[i % n_gpus].push_back(i);
+        }
+    } catch (const std::bad_alloc&) { return IMP_ERROR_MALLOC_FAILED; }
     std::vector<int> rcs(n_gpus, IMP_OK);
     std::vector<std::string> errs(n_gpus);
     std::vector<std::thread> th;
@@ -669,7 +1034,7 @@ int imp_gpu_farm_run_host(int n, imp_gpu_plan* const* plans, const unsigned char
             int rc = imp_gpu_set_device(g);
             if (rc == IMP_OK) {
                 std::vector<imp_gpu_plan*> pl; std::vector<const unsigned char*> sr; std::vector<unsigned char*> ds; std::vector<int> ss, dd;
-                for (int i = g; i < n; i += n_gpus) { pl.push_back(plans[i]); sr.push_back(srcs[i]); ds.push_back(dsts[i]); ss.push_back(src_steps[i]); dd.push_back(dst_steps[i]); }
+                for (int i : share[g]) { pl.push_back(plans[i]); sr.push_back(srcs[i]); ds.push_back(dsts[i]); ss.push_back(src_steps[i]); dd.push_back(dst_steps[i]); }
                 if (!pl.empty()) rc = imp_gpu_batch_run_host((int)pl.size(), pl.data(), sr.data(), ss.data(), ds.data(), dd.data(), n_streams);
             }
             rcs[g] = rc;
@@ -680,6 +1045,11 @@ int imp_gpu_farm_run_host(int n, imp_gpu_plan* const* plans, const unsigned char
     if (caller_dev >= 0) { t_dev = caller_dev; cudaSetDevice(caller_dev); }
     for (int g = 0; g < n_gpus; g++) if (rcs[g]) { snprintf(t_err, sizeof t_err, "gpu %d: %s", g, errs[g].c_str()); return rcs[g]; }
     return IMP_OK;
+}
+
+int imp_gpu_farm_run_host(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs, const int* src_steps,
+                          unsigned char* const* dsts, const int* dst_steps, int n_gpus, int n_streams) {
+    return imp_gpu_farm_run_host_policy(n, plans, srcs, src_steps, dsts, dst_steps, n_gpus, n_streams, IMP_FARM_ROUND_ROBIN);
 }
 
 // ---- "next" row §8f-1: perceived brightness as a device reduction ------------------------------------------

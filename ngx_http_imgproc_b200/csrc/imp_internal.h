@@ -1,6 +1,8 @@
 // imp_internal.h — host-side internals of libimp_gpu.so (not part of the ABI).
 #pragma once
 #include <stdint.h>
+#include <atomic>
+#include <memory>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -17,28 +19,46 @@ struct ImpHostPass {
     double sigma;                      // BLUR only
 };
 
+// A decoded overlay (what PrepareWatermark leaves in the conf pool, bridge.c:199-237). The reference decodes it ONCE at
+// configuration time and every request blends the same pixels (bridge.c:239-281); here it is interned by content, shared
+// by every plan that uses it and uploaded once per device (imp_gpu_upload_watermark, or lazily on first use).
+struct ImpWmImage {
+    std::vector<uint8_t> pixels;       // tightly packed, w*c bytes per row
+    int w = 0, h = 0, c = 0;
+    unsigned long long hash = 0;
+    struct Dev { uint8_t* d = nullptr; int pitch = 0; };
+    Dev dev[16];
+    ~ImpWmImage();                     // releases the device copies through imp_wm_dev_release (set by imp_gpu.cu)
+};
+extern void (*imp_wm_dev_release)(ImpWmImage*);
+// imp_planner.cpp: the shared image holding exactly these pixels (registered on first sight; bounded registry).
+std::shared_ptr<ImpWmImage> imp_wm_intern(const imp_gpu_watermark* wm);
+void imp_wm_registry_clear();
+
 struct imp_gpu_plan {
     std::vector<ImpHostPass> passes;
     int src_w, src_h, src_c;
     int win_x, win_y, win_w, win_h;    // crop window in the source
     int out_w, out_h, out_c;
     unsigned long long algo_bytes;
-    // watermark (host copy, tightly packed) — uploaded lazily per device
-    std::vector<uint8_t> wm_pixels;
-    int wm_w = 0, wm_h = 0, wm_c = 0;
-    // per-device state
+    std::shared_ptr<ImpWmImage> wm;    // overlay the plan blends (shared, uploaded once per device), or null
+    std::atomic<int> refs{1};          // the plan cache and every imp_gpu_plan_create caller hold one reference each
+    // per-device state: ONE stream-ordered allocation holds every pass blob (+ vignette tables), filled by an
+    // asynchronous copy from pinned staging; `ready_ev` orders the first kernels behind it
     struct Dev {
-        std::vector<uint8_t*> pass_blobs;
-        uint8_t* wm = nullptr; int wm_pitch = 0;
-        std::vector<float*> vignette_tabs;         // one per vignette op that is tabulated
+        std::vector<uint8_t*> pass_blobs;          // pointers into `arena`
+        uint8_t* arena = nullptr;
+        cudaEvent_t ready_ev = nullptr;
+        std::atomic<bool> settled{false};          // the upload is known to have completed
         bool ready = false;
     };
     Dev dev[16];
 };
 
-// imp_planner.cpp
+// imp_planner.cpp. `dry`: validate only — same codes, steps and output geometry, but no tables, LUTs, blobs or
+// watermark pixels are materialised (what each recorded operator of the imp_ops layer needs).
 int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w, int h, int c,
-                   imp_gpu_plan* plan, int* step);
+                   imp_gpu_plan* plan, int* step, bool dry = false);
 
 // imp_kernels.cu
 #define IMP_CUBIC_RUN 8           // imp_cubic_run_kernel: output rows per thread; a CTA covers 32 x (8 * IMP_CUBIC_RUN) pixels

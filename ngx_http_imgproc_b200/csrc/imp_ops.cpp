@@ -70,12 +70,14 @@ void to_request(const Pending& p, Built& b) {
     b.cfg.watermark = p.has_wm ? &p.wm : nullptr;
 }
 
-// Validates the recorded chain (the newest op included); on success fixes the header up.
+// Validates the recorded chain (the newest op included); on success fixes the header up. The planner runs in its
+// validate-only mode: same codes and geometry, no tables, LUTs or overlay pixels (the lowering happens once, at the flush,
+// and is served from the plan cache for every further frame and request of the same shape).
 int validate(IplImage* im, Pending& p) {
     Built b; to_request(p, b);
     imp_gpu_plan plan;
     int step = 0;
-    int rc = imp_build_plan(&b.req, &b.cfg, p.w, p.h, p.c, &plan, &step);
+    int rc = imp_build_plan(&b.req, &b.cfg, p.w, p.h, p.c, &plan, &step, true);
     if (rc) return rc;
     im->width = p.cur_w = plan.out_w; im->height = p.cur_h = plan.out_h; im->nChannels = p.cur_c = plan.out_c;
     // imageData still holds the undisturbed source; widthStep/imageSize keep describing THAT buffer until imp_Flush
@@ -97,6 +99,10 @@ int run_one(IplImage** pointer, Pending& p, imp_gpu_plan** plan_out, IplImage** 
 
 }  // namespace
 
+// The C frames of bridge.c cannot unwind: a C++ exception (bad_alloc, length_error) ends as a return code.
+#define IMP_OPS_TRY try {
+#define IMP_OPS_CATCH } catch (const std::bad_alloc&) { return IMP_ERROR_MALLOC_FAILED; } catch (...) { return IMP_ERROR_INVALID_ARGS; }
+
 extern "C" {
 
 void imp_ops_set_image_allocator(imp_ops_create_image_fn create, imp_ops_release_image_fn release) {
@@ -105,6 +111,7 @@ void imp_ops_set_image_allocator(imp_ops_create_image_fn create, imp_ops_release
 }
 
 int imp_Crop(IplImage** pointer, char* args, char* gravity) {
+    IMP_OPS_TRY
     if (!pointer || !*pointer || !args) return IMP_ERROR_INVALID_ARGS;
     std::lock_guard<std::mutex> lk(g_ops_mu);
     Pending& p = entry(*pointer);
@@ -115,9 +122,11 @@ int imp_Crop(IplImage** pointer, char* args, char* gravity) {
     int rc = validate(*pointer, p);
     if (rc) p = saved;
     return rc;
+    IMP_OPS_CATCH
 }
 
 int imp_Resize(IplImage** pointer, char* args, const imp_gpu_config* config, int simple) {
+    IMP_OPS_TRY
     if (!pointer || !*pointer || !args) return IMP_ERROR_INVALID_ARGS;
     std::lock_guard<std::mutex> lk(g_ops_mu);
     Pending& p = entry(*pointer);
@@ -128,9 +137,11 @@ int imp_Resize(IplImage** pointer, char* args, const imp_gpu_config* config, int
     int rc = validate(*pointer, p);
     if (rc) p = saved;
     return rc;
+    IMP_OPS_CATCH
 }
 
 int imp_Filter(IplImage** pointer, char* request, int allowExperiments) {
+    IMP_OPS_TRY
     if (!pointer || !*pointer || !request) return IMP_ERROR_INVALID_ARGS;
     std::lock_guard<std::mutex> lk(g_ops_mu);
     Pending& p = entry(*pointer);
@@ -140,9 +151,11 @@ int imp_Filter(IplImage** pointer, char* request, int allowExperiments) {
     int rc = validate(*pointer, p);
     if (rc) p = saved;
     return rc;
+    IMP_OPS_CATCH
 }
 
 int imp_Watermark(IplImage* image, const imp_gpu_config* config) {
+    IMP_OPS_TRY
     if (!image) return IMP_ERROR_INVALID_ARGS;
     if (!config || !config->watermark) return IMP_OK;
     std::lock_guard<std::mutex> lk(g_ops_mu);
@@ -153,9 +166,11 @@ int imp_Watermark(IplImage* image, const imp_gpu_config* config) {
     int rc = validate(image, p);
     if (rc) p = saved;
     return rc;
+    IMP_OPS_CATCH
 }
 
 int imp_BlendWithPaper(IplImage* image) {
+    IMP_OPS_TRY
     if (!image) return IMP_ERROR_INVALID_ARGS;
     std::lock_guard<std::mutex> lk(g_ops_mu);
     Pending& p = entry(image);
@@ -164,6 +179,7 @@ int imp_BlendWithPaper(IplImage* image) {
     int rc = validate(image, p);
     if (rc) p = saved;
     return rc;
+    IMP_OPS_CATCH
 }
 
 int imp_ops_pending(const IplImage* image) {
@@ -182,6 +198,7 @@ void imp_Discard(IplImage* image) {
 }
 
 int imp_FlushAll(IplImage** frames, int count) {
+    IMP_OPS_TRY
     if (!frames || count < 0) return IMP_ERROR_INVALID_ARGS;
     std::vector<imp_gpu_plan*> plans; std::vector<IplImage*> outs; std::vector<int> idx;
     std::vector<const unsigned char*> srcs; std::vector<unsigned char*> dsts; std::vector<int> ss, ds;
@@ -222,6 +239,7 @@ int imp_FlushAll(IplImage** frames, int count) {
         }
     }
     return rc;
+    IMP_OPS_CATCH
 }
 
 int imp_Flush(IplImage** pointer) {

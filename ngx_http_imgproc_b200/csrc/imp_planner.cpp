@@ -21,6 +21,54 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
+
+// ---- overlay registry: one shared image per distinct watermark content -----------------------------------------
+void (*imp_wm_dev_release)(ImpWmImage*) = nullptr;
+ImpWmImage::~ImpWmImage() { if (imp_wm_dev_release) imp_wm_dev_release(this); }
+
+namespace {
+std::mutex g_wm_mu;
+std::vector<std::shared_ptr<ImpWmImage>> g_wm_registry;     // most recently used last
+constexpr size_t kWmRegistryCap = 32;
+
+unsigned long long hash_bytes(unsigned long long h, const uint8_t* p, size_t n) {
+    // 8 bytes per step (multiply-xorshift); collisions are harmless: a hit is confirmed with memcmp
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { unsigned long long v; memcpy(&v, p + i, 8); h = (h ^ v) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; }
+    for (; i < n; i++) { h = (h ^ p[i]) * 0x100000001B3ull; }
+    return h;
+}
+}  // namespace
+
+std::shared_ptr<ImpWmImage> imp_wm_intern(const imp_gpu_watermark* wm) {
+    const size_t row = (size_t)wm->width * wm->channels;
+    unsigned long long h = 0xcbf29ce484222325ull ^ ((unsigned long long)wm->width << 40) ^ ((unsigned long long)wm->height << 16) ^ (unsigned)wm->channels;
+    for (int y = 0; y < wm->height; y++) h = hash_bytes(h, wm->pixels + (size_t)y * wm->step, row);
+    std::lock_guard<std::mutex> lk(g_wm_mu);
+    for (size_t i = g_wm_registry.size(); i-- > 0;) {
+        const std::shared_ptr<ImpWmImage>& e = g_wm_registry[i];
+        if (e->hash != h || e->w != wm->width || e->h != wm->height || e->c != wm->channels) continue;
+        bool same = true;
+        for (int y = 0; y < wm->height && same; y++) same = memcmp(e->pixels.data() + (size_t)y * row, wm->pixels + (size_t)y * wm->step, row) == 0;
+        if (!same) continue;
+        std::shared_ptr<ImpWmImage> hit = e;
+        if (i + 1 != g_wm_registry.size()) { g_wm_registry.erase(g_wm_registry.begin() + i); g_wm_registry.push_back(hit); }
+        return hit;
+    }
+    auto img = std::make_shared<ImpWmImage>();
+    img->w = wm->width; img->h = wm->height; img->c = wm->channels; img->hash = h;
+    img->pixels.resize(row * wm->height);
+    for (int y = 0; y < wm->height; y++) memcpy(img->pixels.data() + (size_t)y * row, wm->pixels + (size_t)y * wm->step, row);
+    if (g_wm_registry.size() >= kWmRegistryCap) g_wm_registry.erase(g_wm_registry.begin());   // plans keep theirs alive
+    g_wm_registry.push_back(img);
+    return img;
+}
+
+void imp_wm_registry_clear() {
+    std::vector<std::shared_ptr<ImpWmImage>> drop;
+    { std::lock_guard<std::mutex> lk(g_wm_mu); drop.swap(g_wm_registry); }
+}
 
 namespace {
 
@@ -191,6 +239,7 @@ struct Lower {
     std::vector<uint8_t> luts;
     int in_w, in_h, in_c;
     bool uses_wm = false;
+    bool dry = false;               // validate only: no tables, LUTs or blobs
     double sigma = 0;
 
     void begin_pass(int kind, int in_w_, int in_h_, int in_c_) {
@@ -205,6 +254,7 @@ struct Lower {
     int add_lut(const uint8_t* p, int n) { int off = (int)luts.size(); luts.insert(luts.end(), p, p + n); return off; }
     int final_dc = 0;              // destination channels of the LAST pass when the encoder-side packing changes them
     void end_pass(const ImpFrameMap& out, int out_w, int out_h) {
+        if (dry) return;
         hdr.nops = (int)ops.size();
         while (luts.size() % 16) luts.push_back(0);
         std::vector<uint8_t> tail(ops.size() * sizeof(ImpOp) + luts.size());
@@ -228,6 +278,11 @@ struct Lower {
     }
     // A Gaussian blur: close the running pass (stored in base orientation) and open a stencil pass.
     void split_for_blur(double sg) {
+        if (dry) {                                  // only what later validation depends on: a new pass starts an empty op list
+            if (!(hdr.kind == IMP_G_COPY && ops.empty() && hdr.sc >= 3)) { ops.clear(); hdr.sc = hdr.oc; }
+            hdr.kind = IMP_G_BLUR;
+            return;
+        }
         std::vector<int> k = gaussian_taps(sg);
         const bool trivial = hdr.kind == IMP_G_COPY && ops.empty() && hdr.sc >= 3;
         if (trivial) {
@@ -296,7 +351,11 @@ void push_addcolor(Lower& L, const int* rgb, float alpha) {     // filters.c:608
     o.i[0] = (beta >= 0 && o.f[1] >= 0 && o.f[2] >= 0 && o.f[3] >= 0) ? 1 : 0;     // enables the XU-free truncation path
     L.ops.push_back(o);
 }
-void push_gamma(Lower& L, float g) { uint8_t lut[256]; gamma_lut(g, lut); ImpOp o{}; o.kind = IMP_OP_LUT_ALL; o.i[0] = L.add_lut(lut, 256); L.ops.push_back(o); }
+void push_gamma(Lower& L, float g) {
+    ImpOp o{}; o.kind = IMP_OP_LUT_ALL;
+    if (!L.dry) { uint8_t lut[256]; gamma_lut(g, lut); o.i[0] = L.add_lut(lut, 256); }
+    L.ops.push_back(o);
+}
 void push_contrast(Lower& L, float br, float ct) { ImpOp o{}; o.kind = IMP_OP_CONTRAST; o.f[0] = ct; o.f[1] = br * 255; L.ops.push_back(o); }
 
 int hex2(const std::string& s, int i) { return (int)strtol(s.substr(i * 2, 2).c_str(), nullptr, 16); }
@@ -521,7 +580,7 @@ int parse_resize(const char* args_s, size_t col, size_t row, const imp_gpu_confi
 
 }  // namespace
 
-int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w, int h, int c, imp_gpu_plan* plan, int* step) {
+int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w, int h, int c, imp_gpu_plan* plan, int* step, bool dry) {
     int dummy; if (!step) step = &dummy;
     *step = 0;                                   // IMP_STEP_START: the filter-count guard fires while RunJob
     if (!req || w <= 0 || h <= 0 || (c != 1 && c != 3 && c != 4)) return IMP_ERROR_INVALID_ARGS;
@@ -530,7 +589,7 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
     if (cfg && req->filter_count > cfg->max_filters) return IMP_ERROR_TOO_MUCH_FILTERS;
     *step = IMP_STEP_CROP;
     plan->src_w = w; plan->src_h = h; plan->src_c = c;
-    Lower L; L.plan = plan;
+    Lower L; L.plan = plan; L.dry = dry;
 
     // step 3: crop (bridge.c:576-586)
     int cx = 0, cy = 0, cw = w, ch = h;
@@ -553,7 +612,8 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
     L.begin_pass(IMP_G_COPY, w, h, c);
     ImpPass& P = L.hdr;
     P.sx0 = cx; P.sy0 = cy; P.sw = cw; P.sh = ch; P.bw = rw; P.bh = rh;
-    if (mode >= 0 && !(rw == cw && rh == ch)) {
+    if (dry && mode >= 0 && !(rw == cw && rh == ch)) P.kind = IMP_G_NN;      // "not an index map" is all the validation needs
+    if (!dry && mode >= 0 && !(rw == cw && rh == ch)) {
         double scale_x = 1.0 / ((double)rw / cw), scale_y = 1.0 / ((double)rh / ch);
         int isx = (int)lrint(scale_x), isy = (int)lrint(scale_y);
         bool fast = fabs(scale_x - isx) < DBL_EPSILON && fabs(scale_y - isy) < DBL_EPSILON;
@@ -672,7 +732,7 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
     }
 
     // a pass 0 that stayed a plain index map (crop / no resize) streams through the strip kernel as well
-    if (L.hdr.kind == IMP_G_COPY) L.copy_tables();
+    if (!dry && L.hdr.kind == IMP_G_COPY) L.copy_tables();
 
     // step 6: watermark (bridge.c:629-640, 239-281)
     *step = IMP_STEP_WATERMARK;
@@ -700,10 +760,7 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
         o.map = L.fr.map();
         L.ops.push_back(o);
         L.uses_wm = true;
-        plan->wm_w = wm->width; plan->wm_h = wm->height; plan->wm_c = wm->channels;
-        plan->wm_pixels.resize((size_t)wm->width * wm->height * wm->channels);
-        for (int y = 0; y < wm->height; y++)
-            memcpy(plan->wm_pixels.data() + (size_t)y * wm->width * wm->channels, wm->pixels + (size_t)y * wm->step, (size_t)wm->width * wm->channels);
+        if (!dry) plan->wm = imp_wm_intern(wm);         // shared by content: PrepareWatermark decodes once (bridge.c:199-237)
         wm_bytes = (unsigned long long)ew * eh * wm->channels;
     }
 

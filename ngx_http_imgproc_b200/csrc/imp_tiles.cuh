@@ -171,6 +171,14 @@ constexpr int STRIP_THREADS = STRIP_CONSUMERS + 32 * STRIP_PRODUCER_WARPS;
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Orders this thread's earlier generic-proxy accesses to shared memory (plain LDS) before later async-proxy ones (the TMA
+// refill a released stage receives). The AREA consumers do not need it: their arithmetic has consumed every loaded byte
+// before the stage is released. The plain gathers only LOAD before releasing — the values are first used by the
+// epilogue — and without the fence the refill overtook loads still queued behind the scattered byte stores of a
+// rotated 3-channel store (round 2: rotate=90/270 on 3-channel frames read the tile of 8 rows later).
+__device__ __forceinline__ void fence_generic_to_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 // The destination address of base pixel (bx, by) is affine in by for a fixed bx under all eight output orientations
 // (dst + Y*pitch + X*dc with (X,Y) = imp_map_xy): a thread of a strip owns one bx, so it keeps {address of (bx,0), step
@@ -375,6 +383,8 @@ __device__ __forceinline__ void gather_strip_consume(const ImpJob& job, const Im
                 for (int c = 0; c < SC; c++) v[c] = q[c];
             }
         }
+        // every lane's loads must have been performed before lane 0 hands the stage back to the TMA producer
+        fence_generic_to_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
         if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);

@@ -63,6 +63,13 @@ int hostsim_plan_create(const imp_gpu_request* req, const imp_gpu_config* cfg, i
     if (rc) { delete p; *out = nullptr; return rc; }
     *out = p; return 0;
 }
+// validate-only mode of the planner (what the operator layer runs per recorded op): code, step and output geometry only
+int hostsim_plan_validate(const imp_gpu_request* req, const imp_gpu_config* cfg, int w, int h, int c, int* step, int* out3) {
+    imp_gpu_plan p;
+    int rc = imp_build_plan(req, cfg, w, h, c, &p, step, true);
+    if (!rc) { out3[0] = p.out_w; out3[1] = p.out_h; out3[2] = p.out_c; }
+    return rc;
+}
 void hostsim_plan_destroy(imp_gpu_plan* p) { delete p; }
 void hostsim_plan_output(const imp_gpu_plan* p, int* w, int* h, int* c) { *w = p->out_w; *h = p->out_h; *c = p->out_c; }
 int hostsim_plan_passes(const imp_gpu_plan* p) { return (int)p->passes.size(); }
@@ -71,16 +78,17 @@ unsigned long long hostsim_plan_bytes(const imp_gpu_plan* p) { return p->algo_by
 int hostsim_run(const imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int dp) {
     std::vector<uint8_t> prev, cur;
     const uint8_t* in = src; int in_pitch = sp;
-    const uint8_t* wm = p->wm_pixels.empty() ? nullptr : p->wm_pixels.data();
+    const uint8_t* wm = p->wm ? p->wm->pixels.data() : nullptr;
+    const int wm_w = p->wm ? p->wm->w : 0, wm_c = p->wm ? p->wm->c : 0;
     for (size_t k = 0; k < p->passes.size(); k++) {
         const ImpHostPass& hp = p->passes[k];
         uint8_t* out; int out_pitch;
         if (k + 1 == p->passes.size()) { out = dst; out_pitch = dp; }
         else { out_pitch = (hp.out_w * hp.out_c + 15) & ~15; cur.assign((size_t)out_pitch * hp.out_h, 0); out = cur.data(); }
         switch (hp.hdr.sc) {
-            case 1: run_pass<1>(hp, in, in_pitch, out, out_pitch, wm, p->wm_w * p->wm_c, p->wm_c); break;
-            case 3: run_pass<3>(hp, in, in_pitch, out, out_pitch, wm, p->wm_w * p->wm_c, p->wm_c); break;
-            case 4: run_pass<4>(hp, in, in_pitch, out, out_pitch, wm, p->wm_w * p->wm_c, p->wm_c); break;
+            case 1: run_pass<1>(hp, in, in_pitch, out, out_pitch, wm, wm_w * wm_c, wm_c); break;
+            case 3: run_pass<3>(hp, in, in_pitch, out, out_pitch, wm, wm_w * wm_c, wm_c); break;
+            case 4: run_pass<4>(hp, in, in_pitch, out, out_pitch, wm, wm_w * wm_c, wm_c); break;
             default: return 1;
         }
         prev.swap(cur); in = prev.data(); in_pitch = out_pitch;

@@ -1,0 +1,188 @@
+"""GPU tests of the host-facing machinery round 2 added under the C ABI: the plan cache, the upload-once overlay, the
+chunked host batches (one grouped launch per chunk), the asynchronous submit/wait pair, the size-aware farm, and the
+strip kernels' stage hand-off under slow rotated stores (the race round 2 found). Every result is compared with the
+oracle or with a single-request run of the same plan."""
+import numpy as np
+import pytest
+
+from conftest import rnd_image, smooth_image
+from ngx_http_imgproc_b200 import api
+from test_planner_host import _oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a, b, what=""):
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert np.array_equal(a, b), (what, int(np.abs(a.astype(int) - b.astype(int)).max()), int((a != b).sum()))
+
+
+def test_plan_cache_serves_repeated_requests(gpu, orc):
+    """bridge.c:346-372 re-parses every request; here an identical (request, geometry, config) is lowered once."""
+    gpu.plan_cache_clear()
+    wm = rnd_image(3, 16, 40, 4)
+    kw = dict(watermark=wm, wm_gravity_x="r", wm_gravity_y="b", wm_offset_x=3, wm_offset_y=2, wm_opacity=60)
+    rq = dict(crop="200px,100px,c,c", resize="50,25", filters=["gamma=1.2"])
+    s0 = gpu.plan_cache_stats()
+    p1 = gpu.plan(320, 200, 4, api.Config(**kw), **rq)
+    p2 = gpu.plan(320, 200, 4, api.Config(**kw), **rq)          # a NEW Config object with equal content
+    assert p1.h.value == p2.h.value                              # the same immutable plan, reference counted
+    s1 = gpu.plan_cache_stats()
+    assert s1["hits"] == s0["hits"] + 1 and s1["misses"] == s0["misses"] + 1
+    # anything that changes the lowering is a different key
+    others = [gpu.plan(320, 200, 4, api.Config(**dict(kw, wm_opacity=61)), **rq),
+              gpu.plan(320, 200, 4, api.Config(**dict(kw, watermark=rnd_image(4, 16, 40, 4))), **rq),
+              gpu.plan(320, 200, 3, api.Config(**kw), **rq),
+              gpu.plan(320, 200, 4, api.Config(**kw), **dict(rq, filters=["gamma=1.3"])),
+              gpu.plan(320, 200, 4, api.Config(**kw), **dict(rq, flatten=True))]
+    assert len({p.h.value for p in others} | {p1.h.value}) == 6
+    img = smooth_image(1, 200, 320, 4)
+    ref = _oracle(orc, img, rq, kw)[2]
+    _same(p1.run_host(img), ref)
+    p1.close()
+    _same(p2.run_host(img), ref, "the second reference keeps the plan alive")
+    gpu.plan_cache_clear()
+    _same(p2.run_host(img), ref, "and so does a caller's reference after the cache dropped its own")
+    p2.close()
+    for p in others:
+        p.close()
+
+
+def test_cache_eviction_keeps_live_plans_valid(gpu, orc):
+    gpu.plan_cache_clear()
+    img = smooth_image(2, 90, 120, 3)
+    first = gpu.plan(120, 90, 3, api.Config(max_w=0, max_h=0), resize="33,21")
+    for k in range(140):                                         # more than the 128 entries of the cache
+        gpu.plan(120, 90, 3, api.Config(max_w=0, max_h=0), resize=f"{20 + k},21").close()
+    assert gpu.plan_cache_stats()["entries"] <= 128
+    _same(first.run_host(img), _oracle(orc, img, dict(resize="33,21"), dict(max_w=0, max_h=0))[2])
+    first.close()
+
+
+def test_overlay_is_uploaded_once_and_shared(gpu, orc):
+    """PrepareWatermark decodes once per configuration (bridge.c:199-237): every plan with the same overlay content
+    shares one device copy, registered explicitly or on first use; a different overlay at a recycled host address
+    must NOT alias it (the registry is keyed by content)."""
+    kw = dict(wm_gravity_x="c", wm_gravity_y="c", wm_offset_x=2, wm_offset_y=-1, wm_opacity=80)
+    img = smooth_image(3, 120, 160, 4)
+    buf = np.zeros((20, 30, 4), np.uint8)
+    for seed in (11, 12, 13):
+        buf[...] = rnd_image(seed, 20, 30, 4)                    # same address, new content
+        cfg = api.Config(watermark=buf, **kw)
+        gpu.upload_watermark(cfg)
+        for rq in (dict(resize="80,60"), dict(filters=["rotate=90"]), dict(resize="200,150,up")):
+            out = gpu.run(img, cfg, **rq)
+            _same(out, _oracle(orc, img, rq, dict(kw, watermark=buf.copy()))[2], (seed, rq))
+
+
+def test_chunked_host_batches_group_their_launches(gpu, orc):
+    """A GIF album / a burst of requests through imp_gpu_batch_run_host: chunks of jobs run as one launch per kernel variant
+    (counted), results equal single runs; pinned and pageable buffers, odd steps, mixed plans, several passes."""
+    import torch
+    kw = dict(allow_experiments=True, max_filters=8, max_w=0, max_h=0)
+    frames = [smooth_image(40 + i, 135, 240, 4) for i in range(48)]
+    plan = gpu.plan(240, 135, 4, api.Config(**kw), resize="480,270,up", filters=["modulate=0,0,100", "colorize=704214,0.6"])
+    dsts = [np.zeros((plan.out_h, plan.out_w, plan.out_c), np.uint8) for _ in frames]
+    l0 = gpu.launch_count()
+    api.run_host_batch(gpu, [plan] * len(frames), frames, dsts, n_streams=4)
+    launches = gpu.launch_count() - l0
+    assert launches <= 8, launches                               # 48 frames: 4 chunks of 12, one launch each (was 48)
+    ref = _oracle(orc, frames[7], dict(resize="480,270,up", filters=["modulate=0,0,100", "colorize=704214,0.6"]), kw)[2]
+    _same(dsts[7], ref)
+    for f, d in zip(frames, dsts):
+        _same(d, plan.run_host(f))
+    # mixed plans (several passes, different kernels), pinned sources with short rows / wide rows, a strided destination
+    rqs = [dict(resize="100,60"), dict(filters=["blur=1.5", "gamma=1.2"]), dict(crop="150px,100px,10px,5px"), dict(resize="64,64", filters=["blur=6", "kelvin=1"]),
+           dict(filters=["rotate=270"]), dict(resize="333,200,up", interp=1)]
+    imgs, plans, outs, refs = [], [], [], []
+    for i in range(23):
+        rq = rqs[i % len(rqs)]
+        h, w, c = 120 + 3 * i, 200 + 5 * i, 3 if i % 2 else 4
+        im = smooth_image(i, h, w, c)
+        if i % 3 == 0:
+            t = torch.from_numpy(im).pin_memory(); im = t.numpy(); imgs.append((im, t))
+        else:
+            imgs.append((im, None))
+        p = gpu.plan(w, h, c, api.Config(**kw), **rq)
+        plans.append(p)
+        o = np.zeros((p.out_h, p.out_w * p.out_c + (8 if i % 4 == 1 else 0)), np.uint8)
+        outs.append(o)
+        refs.append(_oracle(orc, im, rq, kw)[2])
+    api.run_host_batch(gpu, plans, [i[0] for i in imgs], outs, n_streams=3)
+    for p, o, r, rq in zip(plans, outs, refs, rqs * 4):
+        _same(o[:, :p.out_w * p.out_c].reshape(p.out_h, p.out_w, p.out_c), r, rq)
+    for p in plans:
+        p.close()
+    plan.close()
+
+
+def test_submit_wait_is_asynchronous_and_exact(gpu, orc):
+    kw = dict(max_w=0, max_h=0)
+    imgs = [smooth_image(i, 400, 600, 3) for i in range(12)]
+    rq = dict(resize="150,100", filters=["contrast=1.4"])
+    plan = gpu.plan(600, 400, 3, api.Config(**kw), **rq)
+    dsts = [np.zeros((plan.out_h, plan.out_w, 3), np.uint8) for _ in imgs]
+    jobs = api.HostJobs([plan] * len(imgs), imgs, dsts)
+    t1 = jobs.submit(gpu, n_streams=2)
+    dsts2 = [np.zeros_like(d) for d in dsts]
+    jobs2 = api.HostJobs([plan] * len(imgs), imgs, dsts2)
+    t2 = jobs2.submit(gpu, n_streams=2)                          # two batches in flight (they serialise on the lanes)
+    api.HostJobs.wait(gpu, t1)
+    api.HostJobs.wait(gpu, t2)
+    ref = [_oracle(orc, im, rq, kw)[2] for im in imgs]
+    for d, d2, r in zip(dsts, dsts2, ref):
+        _same(d, r); _same(d2, r)
+    plan.close()
+
+
+def test_farm_policies_match_single_runs(gpu, orc):
+    """imp_gpu_farm_run_host_policy on every GPU the box has (the driver's box has one; the 2+ GPU run is
+    test_farm_on_all_gpus): round-robin and size-aware assignments give the same bytes as single runs."""
+    kw = dict(max_w=0, max_h=0)
+    rng = np.random.default_rng(5)
+    imgs = [smooth_image(i, int(rng.integers(100, 500)), int(rng.integers(120, 700)), 3 if i % 4 else 4) for i in range(21)]
+    rq = dict(resize="96,96")
+    plans = [gpu.plan(im.shape[1], im.shape[0], im.shape[2], api.Config(**kw), **rq) for im in imgs]
+    ref = [p.run_host(im) for p, im in zip(plans, imgs)]
+    _same(ref[3], _oracle(orc, imgs[3], rq, kw)[2])
+    for n_gpus in sorted({1, gpu.device_count()}):
+        for policy in (api.FARM_ROUND_ROBIN, api.FARM_SIZE_AWARE):
+            dsts = [np.zeros_like(r) for r in ref]
+            api.run_host_batch(gpu, plans, imgs, dsts, n_streams=2, n_gpus=n_gpus, policy=policy)
+            for d, r in zip(dsts, ref):
+                _same(d, r, (n_gpus, policy))
+    for p in plans:
+        p.close()
+
+
+def test_farm_on_all_gpus(gpu, orc):
+    """Product-level multi-GPU test: skipped below 2 devices."""
+    n = gpu.device_count()
+    if n < 2:
+        pytest.skip("needs 2+ GPUs on the box")
+    kw = dict(max_w=0, max_h=0, watermark=rnd_image(9, 12, 12, 4), wm_gravity_x="r", wm_gravity_y="b", wm_offset_x=1, wm_offset_y=1)
+    imgs = [smooth_image(i, 300 + 11 * i, 500 + 7 * i, 3 if i % 3 else 4) for i in range(40)]
+    rq = dict(resize="128,128")
+    plans = [gpu.plan(im.shape[1], im.shape[0], im.shape[2], api.Config(**kw), **rq) for im in imgs]
+    ref = [p.run_host(im) for p, im in zip(plans, imgs)]
+    for policy in (api.FARM_ROUND_ROBIN, api.FARM_SIZE_AWARE):
+        dsts = [np.zeros_like(r) for r in ref]
+        api.run_host_batch(gpu, plans, imgs, dsts, n_streams=2, n_gpus=n, policy=policy)
+        for d, r in zip(dsts, ref):
+            _same(d, r, policy)
+    gpu.set_device(0)
+    for p in plans:
+        p.close()
+
+
+def test_rotated_three_byte_stores_do_not_outrun_the_ring(gpu, orc):
+    """Round-2 regression: with rotate=90/270 and 3-byte pixels the strip kernels' epilogue issues scattered byte stores;
+    the plain-gather consumers then released a ring stage with their own loads still queued, and the TMA refill of 8 tiles
+    later overtook them (tiles 5 .. n-9 of a column came out wrong, differently on every run). Needs >= 14 tile rows."""
+    for shape in [(256, 256, 3), (512, 384, 3), (300, 200, 1)]:
+        img = rnd_image(1, *shape)
+        for f in (["rotate=90"], ["rotate=270"], ["flip=01", "rotate=270"]):
+            for rq in (dict(filters=f), dict(resize=f"{shape[1] * 2},{shape[0] * 2},up", simple=True, filters=f), dict(resize=f"{shape[1] - 7},{shape[0] - 5}", interp=1, filters=f)):
+                ref = _oracle(orc, img, rq, dict(max_w=0, max_h=0))[2]
+                for rep in range(3):
+                    _same(gpu.run(img, api.Config(max_w=0, max_h=0), **rq), ref, (shape, rq, rep))

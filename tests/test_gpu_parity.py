@@ -440,6 +440,9 @@ def test_tile_kernels_orientations_sizes_and_packing(gpu, orc, c):
                 if (gi + oi) % 5 == 2: rq["flatten"] = True
                 code, _, out = _gpu_run(gpu, img, kw, rq)
                 c2, _, ref = _oracle(orc, img, rq, kw)
+                if "crop" in g and w < 66:
+                    assert code == c2 == 50, (rq, code, c2)        # the 61 px window at x = 5 does not fit the 33 px frame
+                    continue
                 assert code == c2 == 0, (rq, code, c2)
                 _assert_same(out, ref, ((h, w, c), rq), _has_vignette(rq))
                 n += 1
