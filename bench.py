@@ -116,6 +116,12 @@ def _cpu_worker(args):
     ref_ok = False
     if use_ref and O.Ref.available():
         ref_ok = O.Ref.use_cv2(True)
+    # output pixels per request, from the port, outside the timed region (a GIF-encoded answer is not decoded back)
+    pix = []
+    for (shape, rq, _), img in zip(picks, imgs):
+        code, step, out = O.run_chain(img, rq.get("crop"), None, rq.get("resize"), rq.get("filters", []), cfg, bool(rq.get("simple")))
+        assert code == 0
+        pix.append(out.shape[0] * out.shape[1])
     t0 = time.perf_counter()
     opix = 0
     for k in range(count):
@@ -130,7 +136,7 @@ def _cpu_worker(args):
         else:
             code, step, out = O.run_chain(img, rq.get("crop"), None, rq.get("resize"), rq.get("filters", []), cfg, bool(rq.get("simple")))
         assert code == 0
-        opix += out.shape[0] * out.shape[1]
+        opix += pix[k % len(picks)]
     return time.perf_counter() - t0, opix, ref_ok
 
 

@@ -201,17 +201,34 @@ int plan_wait_ready(imp_gpu_plan* plan, cudaStream_t st) {
     return IMP_OK;
 }
 
+// Device memory of plans that were destroyed (cache evictions, mostly): kernels on any stream may still be reading the
+// blobs, so the arenas are parked and released in batches behind ONE device synchronisation (caller holds g_mu).
+struct Parked { int dev; uint8_t* arena; };
+std::vector<Parked> g_parked;
+void parked_release(bool all) {
+    if (g_parked.empty() || (!all && g_parked.size() < 32)) return;
+    bool synced[MAX_DEV] = {false};
+    for (const Parked& p : g_parked) {
+        if (!g_dev[p.dev].ready || cudaSetDevice(p.dev) != cudaSuccess) continue;
+        if (!synced[p.dev]) { cudaDeviceSynchronize(); synced[p.dev] = true; }
+        cudaFreeAsync(p.arena, g_dev[p.dev].stream);     // back into the pool, no further synchronisation
+    }
+    g_parked.clear();
+    if (t_dev >= 0) cudaSetDevice(t_dev);
+}
+
 void plan_free_device(imp_gpu_plan* plan) {
     for (int d = 0; d < MAX_DEV; d++) {
         imp_gpu_plan::Dev& pd = plan->dev[d];
         if (!pd.ready) continue;
         if (g_dev[d].ready && cudaSetDevice(d) == cudaSuccess) {
-            if (pd.arena) cudaFree(pd.arena);            // synchronises: kernels that still read the blobs finish first
+            if (pd.arena) g_parked.push_back(Parked{d, pd.arena});
             if (pd.ready_ev) cudaEventDestroy(pd.ready_ev);
         }
         pd.arena = nullptr; pd.ready_ev = nullptr; pd.pass_blobs.clear();
         pd.ready = false;
     }
+    parked_release(false);
 }
 
 void plan_release(imp_gpu_plan* plan) {          // drops one reference
@@ -263,6 +280,8 @@ void cache_clear() {
         g_cache.lru.clear(); g_cache.map.clear();
     }
     for (imp_gpu_plan* p : drop) plan_release(p);
+    std::lock_guard<std::mutex> lk(g_mu);
+    parked_release(true);
 }
 
 int ops_smem(const ImpPass& h) { return std::max(16, h.nops * (int)sizeof(ImpOp) + h.lut_bytes); }
@@ -747,6 +766,10 @@ int imp_gpu_init(int device) {
             if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
                 unsigned long long keep = ~0ull;
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                // prime the pool: the first plans of a worker then sub-allocate instead of mapping fresh memory
+                void* prime = nullptr;
+                if (cudaMallocAsync(&prime, 32u << 20, c.stream) == cudaSuccess) cudaFreeAsync(prime, c.stream);
+                else cudaGetLastError();
             }
             CK(imp_upload_tables());
             c.ready = true;

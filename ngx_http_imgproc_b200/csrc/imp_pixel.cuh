@@ -370,6 +370,27 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
                     }
                 }
                 break;
+            case IMP_OP_LUT3: {
+                const uint8_t* t = lut + op.i[0];
+                const bool al = op.i[1] != 0 && oc == 4;
+#pragma unroll
+                for (int n = 0; n < N; n++) {
+                    ImpPx& p = px[n];
+                    p.b = t[p.b]; p.g = t[256 + p.g]; p.r = t[512 + p.r];
+                    if (al) p.a = t[768 + p.a];
+                }
+            } break;
+            case IMP_OP_MAXLUT3: {
+                const uint8_t* t = lut + op.i[0];
+                const bool al = op.i[1] != 0 && oc == 4;
+#pragma unroll
+                for (int n = 0; n < N; n++) {
+                    ImpPx& p = px[n];
+                    const int m = imp_max(p.b, imp_max(p.g, p.r));
+                    p.b = t[m]; p.g = t[256 + m]; p.r = t[512 + m];
+                    if (al) p.a = t[768 + p.a];
+                }
+            } break;
             case IMP_OP_PAPER:
                 if (oc == 4) {
 #pragma unroll

@@ -38,6 +38,11 @@ enum ImpOpKind : int {
     IMP_OP_SCANLINE,      // Scanline filters.c:405-455
     IMP_OP_WATERMARK,     // Watermark bridge.c:239-281 + AlphaBlendOver filters.c:619-662
     IMP_OP_PAPER,         // BlendWithPaper filters.c:666-687
+    // planner-made (imp_planner.cpp "fusion of channel-separable ops"): a run of AlphaBlendAddColor / ApplyGamma /
+    // BrightnessContrast / Lomo composed into one table per channel; i[0] = LUT offset of u8[3 or 4][256] (B,G,R[,A]),
+    // i[1] = 1 when the alpha table is present and to be applied
+    IMP_OP_LUT3,          // c = tab[c][c]
+    IMP_OP_MAXLUT3,       // c = tab[c][max(B,G,R)] (a saturation-0 ModulateHSV opened the run); alpha: tab[3][A]
 };
 
 // base-frame (x,y) -> coordinates in another frame of size w x h:

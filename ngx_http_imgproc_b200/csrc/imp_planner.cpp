@@ -15,6 +15,7 @@
 //   crop/gravity offsets that are negative or a gravity string with fewer than two tokens (OpenCV
 //   assert / strcmp(NULL)); resize to a zero-sized target (cvCreateImage error).
 #include "imp_internal.h"
+#include "imp_pixel.cuh"            // host instantiation of the per-pixel ops: composed LUTs are tabulated with the very code the kernels run
 #include <math.h>
 #include <float.h>
 #include <limits.h>
@@ -242,6 +243,43 @@ struct Lower {
     bool dry = false;               // validate only: no tables, LUTs or blobs
     double sigma = 0;
 
+    // ---- fusion of channel-separable ops ----------------------------------------------------------------------------
+    // AlphaBlendAddColor, ApplyGamma, BrightnessContrast and Lomo map every channel byte on its own (filters.c:549-616,
+    // 335-346), so a run of them — gotham is three in a row, kelvin and "sepia" end in one — composes into ONE 256-entry
+    // table per channel, tabulated here with the host instantiation of the kernels' own per-pixel functions: the same
+    // bytes, one shared-memory load per channel instead of the float sequence of every op. A modulate with saturation
+    // factor 0 (sepia) turns the pixel into (V,V,V) with V = scaled max(B,G,R): it OPENS such a run as a table over the
+    // maximum (IMP_OP_MAXLUT3). Geometry filters do not close a run (pointwise ops commute with index maps).
+    int fuse_mode = 0;              // 0 none, 1 per-channel tables of the channel's own value, 2 tables of max(B,G,R)
+    bool fuse_alpha = false;        // the alpha table is not the identity (gamma runs over alpha too, filters.c:554)
+    uint8_t fuse_tab[4][256];
+    void fuse_open(int mode) {
+        fuse_mode = mode; fuse_alpha = false;
+        if (!dry) for (int c = 0; c < 4; c++) for (int v = 0; v < 256; v++) fuse_tab[c][v] = (uint8_t)v;
+    }
+    // f(ImpPx&) is one separable op on a whole pixel; it is tabulated channel by channel through the running tables
+    template <class F> void fuse(F f, bool touches_alpha) {
+        if (!fuse_mode) fuse_open(1);
+        if (touches_alpha && hdr.oc == 4) fuse_alpha = true;
+        if (dry) return;
+        for (int v = 0; v < 256; v++) {
+            ImpPx p{fuse_tab[0][v], fuse_tab[1][v], fuse_tab[2][v], fuse_tab[3][v]};
+            f(p);
+            fuse_tab[0][v] = (uint8_t)p.b; fuse_tab[1][v] = (uint8_t)p.g; fuse_tab[2][v] = (uint8_t)p.r;
+            if (touches_alpha && hdr.oc == 4) fuse_tab[3][v] = (uint8_t)p.a;
+        }
+    }
+    void fuse_flush() {
+        if (!fuse_mode) return;
+        ImpOp o{}; o.kind = fuse_mode == 2 ? IMP_OP_MAXLUT3 : IMP_OP_LUT3;
+        o.i[1] = fuse_alpha ? 1 : 0;
+        if (!dry) o.i[0] = add_lut(&fuse_tab[0][0], fuse_alpha ? 1024 : 768);
+        fuse_mode = 0;
+        ops.push_back(o);
+    }
+    // every op that is not channel-separable closes the running table first
+    void push(const ImpOp& o) { fuse_flush(); ops.push_back(o); }
+
     void begin_pass(int kind, int in_w_, int in_h_, int in_c_) {
         memset(&hdr, 0, sizeof hdr);
         bb = BlobBuilder(); ops.clear(); luts.clear(); uses_wm = false; sigma = 0;
@@ -254,6 +292,7 @@ struct Lower {
     int add_lut(const uint8_t* p, int n) { int off = (int)luts.size(); luts.insert(luts.end(), p, p + n); return off; }
     int final_dc = 0;              // destination channels of the LAST pass when the encoder-side packing changes them
     void end_pass(const ImpFrameMap& out, int out_w, int out_h) {
+        fuse_flush();
         if (dry) return;
         hdr.nops = (int)ops.size();
         while (luts.size() % 16) luts.push_back(0);
@@ -278,6 +317,7 @@ struct Lower {
     }
     // A Gaussian blur: close the running pass (stored in base orientation) and open a stencil pass.
     void split_for_blur(double sg) {
+        fuse_flush();
         if (dry) {                                  // only what later validation depends on: a new pass starts an empty op list
             if (!(hdr.kind == IMP_G_COPY && ops.empty() && hdr.sc >= 3)) { ops.clear(); hdr.sc = hdr.oc; }
             hdr.kind = IMP_G_BLUR;
@@ -343,20 +383,34 @@ void gamma_lut(float gamma, uint8_t* lut) {          // filters.c:561-570, store
     for (int i = 0; i < 256; i++) lut[i] = (uint8_t)(unsigned)d2i_x86(pow(i / 255.0, inverse) * 255.0);
 }
 
-void push_modulate(Lower& L, int h, int s, int v) { ImpOp o{}; o.kind = IMP_OP_MODULATE; o.i[0] = h; o.i[1] = s; o.i[2] = v; L.ops.push_back(o); }
+void push_modulate(Lower& L, int h, int s, int v) {
+    if (s == 0) {
+        // S becomes 0 whatever it was and HSV2RGB's S == 0 branch (helpers.c:117) returns (V,V,V): the pixel only depends on
+        // max(B,G,R) from here on, so the op opens a table over that maximum and the separable ops after it fold in
+        L.fuse_flush();
+        L.fuse_open(2);
+        if (!L.dry) for (int m = 0; m < 256; m++) { ImpPx p{m, m, m, 255}; imp_op_modulate(p, h, 0, v); L.fuse_tab[0][m] = (uint8_t)p.b; L.fuse_tab[1][m] = (uint8_t)p.g; L.fuse_tab[2][m] = (uint8_t)p.r; }
+        return;
+    }
+    ImpOp o{}; o.kind = IMP_OP_MODULATE; o.i[0] = h; o.i[1] = s; o.i[2] = v; L.push(o);
+}
 void push_addcolor(Lower& L, const int* rgb, float alpha) {     // filters.c:608-616
     ImpOp o{}; o.kind = IMP_OP_ADDCOLOR;
     float beta = 1 - alpha;
     o.f[0] = beta; o.f[1] = (float)rgb[2] * alpha; o.f[2] = (float)rgb[1] * alpha; o.f[3] = (float)rgb[0] * alpha;
     o.i[0] = (beta >= 0 && o.f[1] >= 0 && o.f[2] >= 0 && o.f[3] >= 0) ? 1 : 0;     // enables the XU-free truncation path
-    L.ops.push_back(o);
+    const float f0 = o.f[0], f1 = o.f[1], f2 = o.f[2], f3 = o.f[3]; const bool nonneg = o.i[0] != 0;
+    L.fuse([=](ImpPx& p) { imp_op_addcolor(p, f0, f1, f2, f3, nonneg); }, false);
 }
 void push_gamma(Lower& L, float g) {
-    ImpOp o{}; o.kind = IMP_OP_LUT_ALL;
-    if (!L.dry) { uint8_t lut[256]; gamma_lut(g, lut); o.i[0] = L.add_lut(lut, 256); }
-    L.ops.push_back(o);
+    uint8_t lut[256];
+    if (!L.dry) gamma_lut(g, lut);
+    L.fuse([&](ImpPx& p) { p.b = lut[p.b]; p.g = lut[p.g]; p.r = lut[p.r]; p.a = lut[p.a]; }, true);     // every channel, alpha too (filters.c:554)
 }
-void push_contrast(Lower& L, float br, float ct) { ImpOp o{}; o.kind = IMP_OP_CONTRAST; o.f[0] = ct; o.f[1] = br * 255; L.ops.push_back(o); }
+void push_contrast(Lower& L, float br, float ct) {
+    const float f0 = ct, f1 = br * 255;
+    L.fuse([=](ImpPx& p) { p.b = imp_contrast1(p.b, f0, f1); p.g = imp_contrast1(p.g, f0, f1); p.r = imp_contrast1(p.r, f0, f1); }, false);
+}
 
 int hex2(const std::string& s, int i) { return (int)strtol(s.substr(i * 2, 2).c_str(), nullptr, 16); }
 
@@ -445,7 +499,7 @@ int lower_filter(Lower& L, const char* request, int allow) {
                     }
                 }
             }
-            ImpOp o{}; o.kind = IMP_OP_GRADMAP; o.i[0] = L.add_lut(lut, 768); L.ops.push_back(o);
+            ImpOp o{}; o.kind = IMP_OP_GRADMAP; L.fuse_flush(); o.i[0] = L.add_lut(lut, 768); L.ops.push_back(o);
             return IMP_OK;
         }
         case 8: {   // vignette filters.c:295-323; centre/maxr from helpers.c:46-66
@@ -466,7 +520,7 @@ int lower_filter(Lower& L, const char* request, int allow) {
                 long long entries = mx * mx + my * my + 1;
                 o.i[2] = entries <= (16ll << 20) ? (int)entries : 0;
             }
-            L.ops.push_back(o);
+            L.push(o);
             return IMP_OK;
         }
         case 9: {   // gotham filters.c:325-333
@@ -477,7 +531,9 @@ int lower_filter(Lower& L, const char* request, int allow) {
             push_contrast(L, (float)-0.07, (float)1.5);
             return IMP_OK;
         }
-        case 10: { ImpOp o{}; o.kind = IMP_OP_LOMO; L.ops.push_back(o); return IMP_OK; }   // filters.c:335-346
+        case 10:    // lomo filters.c:335-346
+            L.fuse([](ImpPx& p) { p.g = imp_lomo1(p.g); p.r = imp_lomo1(p.r); }, false);
+            return IMP_OK;
         case 11: {  // kelvin filters.c:348-354
             push_modulate(L, 120, 50, 100);
             int rgb[3] = {255, 153, 0};
@@ -488,7 +544,7 @@ int lower_filter(Lower& L, const char* request, int allow) {
             int sat;
             if (args == "full") sat = 255; else if (args == "mid") sat = 190; else if (args == "pale") sat = 120;
             else return IMP_ERROR_INVALID_ARGS;
-            ImpOp o{}; o.kind = IMP_OP_RAINBOW; o.i[0] = sat; L.ops.push_back(o);
+            ImpOp o{}; o.kind = IMP_OP_RAINBOW; o.i[0] = sat; L.push(o);
             return IMP_OK;
         }
         case 13: {  // scanline filters.c:405-455
@@ -506,7 +562,7 @@ int lower_filter(Lower& L, const char* request, int allow) {
             o.i[0] = freq + width + 1; o.i[1] = freq; o.i[2] = width;
             o.i[3] = f2i_x86(255 * opacity) & 255; o.i[4] = f2i_x86(255 * intensity) & 255;
             o.map = fr.map();
-            L.ops.push_back(o);
+            L.push(o);
             return IMP_OK;
         }
     }
@@ -728,7 +784,7 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
     for (int i = 0; i < req->filter_count; i++) {
         int code = lower_filter(L, req->filters[i] ? req->filters[i] : "", cfg ? cfg->allow_experiments : 0);
         if (code) return code;
-        if ((int)L.ops.size() > IMP_MAX_OPS) return IMP_ERROR_TOO_MUCH_FILTERS;
+        if ((int)L.ops.size() + (L.fuse_mode ? 1 : 0) > IMP_MAX_OPS) return IMP_ERROR_TOO_MUCH_FILTERS;
     }
 
     // a pass 0 that stayed a plain index map (crop / no resize) streams through the strip kernel as well
@@ -758,14 +814,15 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
         float opacity = (float)(wm->opacity / 100.0);
         o.f[0] = 1 - opacity;
         o.map = L.fr.map();
-        L.ops.push_back(o);
+        L.push(o);
         L.uses_wm = true;
         if (!dry) plan->wm = imp_wm_intern(wm);         // shared by content: PrepareWatermark decodes once (bridge.c:199-237)
         wm_bytes = (unsigned long long)ew * eh * wm->channels;
     }
 
     // flatten (bridge.c:642-656)
-    if (req->flatten && L.fr.c == 4) { ImpOp o{}; o.kind = IMP_OP_PAPER; L.ops.push_back(o); }
+    if (req->flatten && L.fr.c == 4) { ImpOp o{}; o.kind = IMP_OP_PAPER; L.push(o); }
+    L.fuse_flush();
     if ((int)L.ops.size() > IMP_MAX_OPS) return IMP_ERROR_TOO_MUCH_FILTERS;
 
     *step = IMP_STEP_ENCODE;

@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE — builds oracle/_ref/libimp_ref_gpu.so: the reference with INTEGRATION.md's edits applied.
 
-The reference's bridge.c is read where it lies (/root/reference), the handful of call-site edits that
-INTEGRATION.md §2 lists are applied IN MEMORY (regex substitutions keyed on the reference's own identifiers; no
-reference text is stored in this repo), the result is compiled from a temporary directory together with the
-reference's untouched filters.c / helpers.c / advancedio.c and the test stubs, linked against
-ngx_http_imgproc_b200/libimp_gpu.so, and the temporary source is deleted. Only the .so is kept (git-ignored,
+The reference's bridge.c and filters.c are read where they lie (/root/reference); the definitions that
+ngx_http_imgproc_b200/dropin/imp_dropin.c replaces under their own names are deleted IN MEMORY (brace-matched on the
+reference's own identifiers; no reference text is stored in this repo), RunJob gets INTEGRATION.md §2's one flush
+statement, and the result is compiled from a temporary directory together with imp_dropin.c, the reference's untouched
+helpers.c / advancedio.c and the test stubs, linked against ngx_http_imgproc_b200/libimp_gpu.so; the temporary sources are
+deleted. RunJob's operator call sites (Crop, Resize, Filter, Watermark, BlendWithPaper) are NOT edited. Only the .so is kept (git-ignored,
 travels to the GPU box). tests/test_gpu_parity.py then drives the reference's own RunJob through it on a B200 and
 compares with the unmodified CPU build (libimp_ref.so): that is the drop-in claim, executed.
 
@@ -23,35 +24,14 @@ ROOT = os.path.dirname(HERE)
 REF = os.environ.get("IMP_REFERENCE", "/root/reference")
 PKG = os.path.join(ROOT, "ngx_http_imgproc_b200")
 
-HELPERS = r'''
-#include "imp_ops.h"
-/* INTEGRATION.md §2: frames stay owned by the (stubbed) OpenCV allocator; Config -> imp_gpu_config */
-static IplImage* imp_create(int w, int h, int depth, int ch) { return cvCreateImage(cvSize(w, h), depth, ch); }
-static void imp_release(IplImage** im) { cvReleaseImage(im); }
-static void imp_config_from(const Config* c, imp_gpu_config* g, imp_gpu_watermark* w) {
-    g->max_target_w = c->MaxTargetDimensions->W;  g->max_target_h = c->MaxTargetDimensions->H;
-    g->max_filters = (int)c->MaxFiltersCount;     g->allow_experiments = (int)c->AllowExperiments;
-    g->watermark = NULL;
-    if (c->WatermarkInfo) {
-        w->pixels = c->WatermarkInfo->Pointer;    w->width = c->WatermarkInfo->Size.width;  w->height = c->WatermarkInfo->Size.height;
-        w->channels = c->WatermarkInfo->Channels; w->step = c->WatermarkInfo->Step;
-        w->gravity_x = c->WatermarkPosition->GravityX; w->gravity_y = c->WatermarkPosition->GravityY;
-        w->offset_x = c->WatermarkPosition->OffsetX;   w->offset_y = c->WatermarkPosition->OffsetY;
-        w->opacity = (int)c->WatermarkOpacity;
-        g->watermark = w;
-    }
-}
-'''
+DROPIN = os.path.join(PKG, "dropin", "imp_dropin.c")
 
-FLUSH = r'''
-	{   /* INTEGRATION.md §2: one fused GPU pass per frame, before anything reads pixels */
-		IplImage* imp_fr[album.Count > 0 ? album.Count : 1]; int imp_k;
-		for (imp_k = 0; imp_k < album.Count; imp_k++) imp_fr[imp_k] = album.Frames[imp_k].Image;
-		answer->Code = imp_FlushAll(imp_fr, album.Count);
-		for (imp_k = 0; imp_k < album.Count; imp_k++) album.Frames[imp_k].Image = imp_fr[imp_k];
-		if (answer->Code) { goto finalize; }
-	}
-'''
+# the definitions ngx_http_imgproc_b200/dropin/imp_dropin.c replaces (its header comment lists them with file:line)
+BRIDGE_REPLACED = ["OnEnvStart", "OnEnvDestroy", "Crop", "Resize", "Watermark"]
+FILTERS_REPLACED = ["Flip", "Rotate", "Modulate", "Colorize", "Blur", "Gamma", "Contrast", "Gradmap", "Vignette", "Gotham", "Lomo",
+                    "Kelvin", "Rainbow", "Scanline", "BlendWithPaper"]
+
+FLUSH = "\tanswer->Code = imp_FlushAlbum(&album); if (answer->Code) { goto finalize; }   /* INTEGRATION.md §2: the one added statement */\n"
 
 
 def sub_once(pattern, repl, text, what, flags=0):
@@ -61,19 +41,44 @@ def sub_once(pattern, repl, text, what, flags=0):
     return new
 
 
+def delete_function(text: str, name: str) -> str:
+    """Removes the top-level definition `<type> name(...) { ... }` (brace-matched; the reference's sources hold no braces
+    in strings or comments inside these bodies — the compile that follows would catch a wrong cut)."""
+    m = re.search(r'^(?:int|void)\s+' + re.escape(name) + r'\s*\([^;{]*\)\s*\{', text, flags=re.M)
+    if not m:
+        raise SystemExit(f"make_gpu_bridge: definition of {name} not found (reference layout changed?)")
+    depth, i = 1, m.end()
+    while depth and i < len(text):
+        depth += {'{': 1, '}': -1}.get(text[i], 0)
+        i += 1
+    if depth:
+        raise SystemExit(f"make_gpu_bridge: unbalanced braces after {name}")
+    return text[:m.start()] + f"/* {name}: provided by imp_dropin.c */\n" + text[i:]
+
+
 def patched_bridge(src: str) -> str:
+    """bridge.c with INTEGRATION.md §2 applied: five replaced definitions deleted, the gray->BGR block deleted, one flush
+    statement and one imp_Discard added. Every operator CALL SITE of RunJob stays as the reference wrote it."""
     s = src
-    s = sub_once(r'(#include "advancedio.h"\n)', lambda m: m.group(1) + HELPERS, s, "helpers")
-    s = sub_once(r'(void OnEnvStart\(\) \{\n)[^\n]*\n', lambda m: m.group(1) + "\timp_gpu_init(0); imp_ops_set_image_allocator(imp_create, imp_release);\n", s, "OnEnvStart")
-    s = sub_once(r'(\tanswer->Step = IMP_STEP_CROP;\n)', lambda m: "\timp_gpu_config gcfg; imp_gpu_watermark gwm; imp_config_from(config, &gcfg, &gwm);\n" + m.group(1), s, "config")
-    s = sub_once(r'answer->Code = Crop\(&image, crop, gravity\);', "answer->Code = imp_Crop(&image, crop, gravity);", s, "Crop")
-    s = sub_once(r'answer->Code = Resize\(&image, resize, config, simple\);', "answer->Code = imp_Resize(&image, resize, &gcfg, simple);", s, "Resize")
+    for name in BRIDGE_REPLACED:
+        s = delete_function(s, name)
+    s = sub_once(r'(#include "advancedio.h"\n)', lambda m: m.group(1) + '#include "imp_ops.h"\nint imp_FlushAlbum(Album* album);\n', s, "include")
     s = sub_once(r'\t\tif \(image->nChannels == 1\) \{\n(?:[^\n]*\n){4}\t\t\}\n', "", s, "gray->BGR block")
-    s = sub_once(r'answer->Code = Filter\(&image, filters\[i\], config->AllowExperiments\);', "answer->Code = imp_Filter(&image, filters[i], config->AllowExperiments);", s, "Filter")
-    s = sub_once(r'answer->Code = Watermark\(image, config\);', "answer->Code = imp_Watermark(image, &gcfg);", s, "Watermark")
-    s = sub_once(r'\t\t\tBlendWithPaper\(image\);', "\t\t\timp_BlendWithPaper(image);", s, "BlendWithPaper")
     s = sub_once(r'(\t// alternative exit points\n)', lambda m: FLUSH + m.group(1), s, "flush")
     s = sub_once(r'(finalize:.*?)\t\t\t\tcvReleaseImage\(&image\);', lambda m: m.group(1) + "\t\t\t\timp_Discard(image); cvReleaseImage(&image);", s, "finalize", flags=re.S)
+    for call in ("Crop(&image, crop, gravity)", "Resize(&image, resize, config, simple)", "Filter(&image, filters[i], config->AllowExperiments)",
+                 "Watermark(image, config)", "BlendWithPaper(image)"):
+        if "answer->Code = " + call not in s and "\t" + call + ";" not in s:
+            raise SystemExit(f"make_gpu_bridge: call site '{call}' is no longer in RunJob")
+    return s
+
+
+def patched_filters(src: str) -> str:
+    """filters.c without the 14 callbacks and BlendWithPaper; Filter, CallbackMap, CheckDestructive, ASCII,
+    CalcPerceivedBrightness and the pixel helpers stay as they are."""
+    s = src
+    for name in FILTERS_REPLACED:
+        s = delete_function(s, name)
     return s
 
 
@@ -88,15 +93,17 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     tmp = tempfile.mkdtemp(prefix="imp_gpu_bridge_")
     try:
-        with open(os.path.join(REF, "bridge.c")) as f:
-            patched = patched_bridge(f.read())
-        gen = os.path.join(tmp, "bridge_gpu.c")
-        with open(gen, "w") as f:
-            f.write(patched)
+        gen = {}
+        for name, fn in (("bridge.c", patched_bridge), ("filters.c", patched_filters)):
+            with open(os.path.join(REF, name)) as f:
+                text = fn(f.read())
+            gen[name] = os.path.join(tmp, name.replace(".c", "_gpu.c"))
+            with open(gen[name], "w") as f:
+                f.write(text)
         cmd = [os.environ.get("CC", "gcc"), "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w",
                "-I", os.path.join(HERE, "shim"), "-I", REF, "-I", os.path.join(ROOT, "include"),
                "-o", os.path.join(out_dir, "libimp_ref_gpu.so"),
-               os.path.join(REF, "filters.c"), os.path.join(REF, "helpers.c"), gen, os.path.join(REF, "advancedio.c"),
+               gen["filters.c"], os.path.join(REF, "helpers.c"), gen["bridge.c"], os.path.join(REF, "advancedio.c"), DROPIN,
                os.path.join(HERE, "ref_stubs.c"), os.path.join(HERE, "fake_freeimage.c"), os.path.join(HERE, "imp_oracle.c"),
                "-L", PKG, "-limp_gpu", "-Wl,-rpath,$ORIGIN/../../ngx_http_imgproc_b200", "-lm"]
         subprocess.check_call(cmd)

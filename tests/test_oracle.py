@@ -343,10 +343,12 @@ def test_runjob_on_gif_pages_vs_reference(orc):
 
 
 def test_integration_edits_apply_to_the_reference():
-    """INTEGRATION.md's call-site edits (oracle/make_gpu_bridge.py) still match the reference's bridge.c: every edit
-    applies exactly once and no direct call to the CPU operators is left inside RunJob."""
+    """INTEGRATION.md's edits (oracle/make_gpu_bridge.py) still match the reference: the definitions imp_dropin.c replaces
+    under their own names are cut out of bridge.c / filters.c, RunJob keeps every operator call site as the reference wrote
+    it, loses the gray->BGR block and gains exactly one flush statement and one imp_Discard."""
     import importlib.util
     import os
+    import re
     ref = "/root/reference/bridge.c"
     if not os.path.exists(ref):
         pytest.skip("reference sources not present on this box")
@@ -354,10 +356,26 @@ def test_integration_edits_apply_to_the_reference():
     spec = importlib.util.spec_from_file_location("make_gpu_bridge", os.path.join(here, "oracle", "make_gpu_bridge.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    out = mod.patched_bridge(open(ref).read())
+    src = open(ref).read()
+    out = mod.patched_bridge(src)
     run_job = out[out.index("JobResult* RunJob"):]
-    for gone in ("= Crop(&image", "= Resize(&image", "= Filter(&image", "= Watermark(image", "\tBlendWithPaper(image)", "CV_GRAY2BGR"):
-        assert gone not in run_job, gone
-    for once in ("imp_Crop(&image", "imp_Resize(&image", "imp_Filter(&image", "imp_Watermark(image", "imp_BlendWithPaper(image)", "imp_FlushAll(", "imp_Discard(image)"):
-        assert run_job.count(once) == 1, once
-    assert "imp_gpu_init(0)" in out
+    for kept in ("= Crop(&image, crop, gravity)", "= Resize(&image, resize, config, simple)", "= Filter(&image, filters[i], config->AllowExperiments)",
+                 "= Watermark(image, config)", "\tBlendWithPaper(image);"):
+        assert run_job.count(kept) == 1, kept                      # call sites untouched
+    assert "CV_GRAY2BGR" not in run_job
+    assert run_job.count("imp_FlushAlbum(&album)") == 1 and run_job.count("imp_Discard(image)") == 1
+    for name in mod.BRIDGE_REPLACED:
+        assert not re.search(r"^(?:int|void)\s+" + name + r"\s*\(", out, flags=re.M), name
+    # what is left of the diff: the deleted bodies, one include + prototype, one block deleted, two statements
+    removed = sum(1 for line in src.splitlines() if line.strip() and line not in out)
+    assert removed > 150                                              # Crop + Resize + Watermark bodies are gone
+    fsrc = open("/root/reference/filters.c").read()
+    fout = mod.patched_filters(fsrc)
+    for name in mod.FILTERS_REPLACED:
+        assert not re.search(r"^(?:int|void)\s+" + name + r"\s*\(", fout, flags=re.M), name
+    for kept in ("int Filter(", "int CheckDestructive(", "CallbackMap[]", "Memory ASCII", "float CalcPerceivedBrightness(", "void ModulateHSV("):
+        assert kept in fout, kept
+    # the shim defines exactly the symbols that were cut
+    shim = open(os.path.join(here, "ngx_http_imgproc_b200", "dropin", "imp_dropin.c")).read()
+    for name in mod.BRIDGE_REPLACED + mod.FILTERS_REPLACED:
+        assert re.search(r"^(?:int|void)\s+" + name + r"\s*\(", shim, flags=re.M), name
