@@ -12,7 +12,8 @@
 //      13 IMADs. Sums are exact u16 (<= 255*256) and are stored TRANSPOSED (row index contiguous).
 //   4. vertical pass with IDP.2A (u16 x u8 pairs): two vertically adjacent sums share a word, taps in two parity versions:
 //      R+1 instructions per output instead of 2R+1. (acc + 2^15) >> 16 is OpenCV's fixed-point rounding.
-//   5. op list on the blurred pixels (registers), results written to a shared-memory stage in destination orientation,
+//      A thread owns one column of the tile and a run of 8 rows for ALL channels, so the blurred pixels stay in registers:
+//   5. the op list runs on them right there, results are written to a shared-memory stage in destination orientation,
 //   6. copy-out: 16 bytes per thread, coalesced rows.
 // R is the tap radius padded to {3,6,9,12}; zero taps change nothing. Taps > 255 (a lone centre tap of 256) never get here.
 #pragma once
@@ -31,12 +32,11 @@ __device__ unsigned g_imp_dbg_flags;
 #endif
 
 template <int SC, int R>
-__global__ void __launch_bounds__(BLUR_THREADS, 4)
+__global__ void __launch_bounds__(BLUR_THREADS, 3)
 imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one) {
     using D = ImpBlurDims<R>;
     constexpr int SPANX = D::SPANX, SPANY = D::SPANY, NWH = D::NWH, NWIN = D::NWIN, PWW = D::PWW;
     constexpr int NDV = D::NDV, NWV = D::NWV, NV128 = D::NV128, HS = D::HS;
-    constexpr int SROW = BTW * SC + 4;                                  // blurred-byte stage row stride (25/33 words: odd)
     extern __shared__ __align__(128) uint8_t smem[];
     const int jn = blockIdx.y + blockIdx.z * 65535;
     if (jn >= count) return;
@@ -65,7 +65,6 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
     uint8_t* tile = s_ops + ((ops_bytes + 127) & ~127);                 // TMA box; later the destination-oriented out stage
     uint32_t* planar = reinterpret_cast<uint32_t*>(tile + ((rs * SPANY + 127) & ~127));     // [SC][SPANY][PWW] words; later the blurred-byte stage
     uint16_t* hbuf = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(planar) + ((SC * SPANY * PWW * 4 + 127) & ~127));   // [SC*BTW][HS]
-    uint8_t* stage = reinterpret_cast<uint8_t*>(planar);
     uint8_t* ostage = tile;
     const int tid = threadIdx.x;
     // box origin: source pixel (x0-R, y0-R); 16-byte aligned in x as TMA requires (coordinates may be negative)
@@ -156,7 +155,15 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
     }
     __syncthreads();
 
-    // ---- vertical pass (IDP.2A): item = (byte column, 8-row group), columns fastest ----
+    // ---- vertical pass (IDP.2A) fused with the op list: a thread owns column x of the tile and a run of 8 rows, all
+    // channels, so the blurred pixels never leave registers before the ops have run; results go to the out stage in
+    // destination orientation ----
+    static_assert(BTW == 32 && BTH == 64 && BLUR_THREADS == BTW * (BTH / 8), "one (column, 8-row run) per thread");
+    const int oc = P->oc, dc = P->dc;
+    // out-stage row stride: an ODD number of words, so that the 32 lanes of a warp — which own 32 different destination rows
+    // when the output is rotated — land in 32 different banks (a stride of 48 or 64 words put them into two)
+    const int OS = TWd * dc + 4;
+    const int tw = om.swap ? vh : vw, th = om.swap ? vw : vh;           // base-frame extent of the tile
     {
         uint32_t tv[2][NWV];
         const uint32_t* tapv = reinterpret_cast<const uint32_t*>(blob + P->tapv_off);
@@ -164,14 +171,15 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
         for (int m = 0; m < 2; m++)
 #pragma unroll
             for (int i = 0; i < NWV; i++) tv[m][i] = __ldg(tapv + m * NWV + i);
-        for (int item = tid; item < SC * BTW * (BTH / 8); item += BLUR_THREADS) {
-            const int col = item % (SC * BTW), g = item / (SC * BTW);
-            const uint4* hp = reinterpret_cast<const uint4*>(hbuf + col * HS + 8 * g);
+        const int x = tid & 31, g = tid >> 5;
+        uint32_t lo[SC], hi[SC];                                        // blurred bytes of rows 0-3 / 4-7 of the run, per channel
+#pragma unroll
+        for (int c = 0; c < SC; c++) {
+            const uint4* hp = reinterpret_cast<const uint4*>(hbuf + (c * BTW + x) * HS + 8 * g);
             uint32_t W[4 * NV128];
 #pragma unroll
             for (int i = 0; i < NV128; i++) { const uint4 q = hp[i]; W[4 * i] = q.x; W[4 * i + 1] = q.y; W[4 * i + 2] = q.z; W[4 * i + 3] = q.w; }
-            const int c = col / BTW, x = col - c * BTW;
-            uint8_t* sp = stage + (8 * g) * SROW + x * SC + c;
+            uint32_t r[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 unsigned acc = 32768u;
@@ -180,49 +188,44 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
                     const uint32_t a = W[(j >> 1) + t], b = tv[j & 1][t >> 1];
                     acc = (t & 1) ? __dp2a_hi(a, b, acc) : __dp2a_lo(a, b, acc);
                 }
-                sp[j * SROW] = (uint8_t)(acc >> 16);
+                r[j] = acc;                                             // the blurred byte is bits 16..23 (sum of taps = 256)
+            }
+            lo[c] = __byte_perm(__byte_perm(r[0], r[1], 0x0062), __byte_perm(r[2], r[3], 0x0062), 0x5410);
+            hi[c] = __byte_perm(__byte_perm(r[4], r[5], 0x0062), __byte_perm(r[6], r[7], 0x0062), 0x5410);
+        }
+        const int bx = x0 + x;
+        const int cbx = min(bx, w - 1);                                 // pixels of the tile beyond the frame: computed on a valid pixel, never stored
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            ImpPx px[4];
+            int bxs[4], bys[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int sh8 = 8 * k;
+                px[k].b = ((half ? hi[0] : lo[0]) >> sh8) & 255;
+                px[k].g = ((half ? hi[SC > 1 ? 1 : 0] : lo[SC > 1 ? 1 : 0]) >> sh8) & 255;
+                px[k].r = ((half ? hi[SC > 2 ? 2 : 0] : lo[SC > 2 ? 2 : 0]) >> sh8) & 255;
+                px[k].a = (SC == 4) ? (((half ? hi[SC - 1] : lo[SC - 1]) >> sh8) & 255) : 255;
+                bxs[k] = cbx; bys[k] = min(y0 + 8 * g + 4 * half + k, h - 1);
+            }
+            if (nops) imp_run_ops_n<4>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int ly = 8 * g + 4 * half + k, by = y0 + ly;
+                if (x >= tw || ly >= th) continue;                      // outside the tile's valid rectangle (frame edge)
+                int X, Y;
+                imp_map_xy(om, bx, by, X, Y);
+                IMP_DBG(X >= X0 && X < X0 + vw && Y >= Y0 && Y < Y0 + vh, 1);
+                uint8_t* d = ostage + (Y - Y0) * OS + (X - X0) * dc;
+                const ImpPx& p = px[k];
+                if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
+                else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
             }
         }
     }
     __syncthreads();
-
-    // ---- op list, written to the out stage in destination orientation (lanes run along destination x) ----
-    const int oc = P->oc, dc = P->dc;
-    const int OS = TWd * dc;                                            // out-stage row stride: 96..256, a multiple of 16
-    const int xsh = om.swap ? 6 : 5;                                    // log2(TWd)
-    static_assert(BTW == 32 && BTH == 64, "tile shifts below");
-#pragma unroll 1
-    for (int round = 0; round < (BTW * BTH) / (BLUR_THREADS * 4); round++) {
-        ImpPx px[4];
-        int bxs[4], bys[4], so[4];
-        bool live[4];
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int p = (round * 4 + it) * BLUR_THREADS + tid;
-            int Xl = p & (TWd - 1), Yl = p >> xsh;
-            live[it] = Xl < vw && Yl < vh;
-            Xl = min(Xl, vw - 1); Yl = min(Yl, vh - 1);                 // dead slots compute on a valid pixel, never stored
-            so[it] = Yl * OS + Xl * dc;
-            const int X = X0 + Xl, Y = Y0 + Yl;
-            const int u = om.flipx ? om.w - 1 - X : X, v = om.flipy ? om.h - 1 - Y : Y;
-            bxs[it] = om.swap ? v : u; bys[it] = om.swap ? u : v;
-            IMP_DBG(bxs[it] >= x0 && bxs[it] < x0 + BTW && bys[it] >= y0 && bys[it] < y0 + BTH && bxs[it] < w && bys[it] < h, 1);
-            const uint8_t* sp = stage + (bys[it] - y0) * SROW + (bxs[it] - x0) * SC;
-            px[it].b = sp[0]; px[it].g = sp[SC > 1 ? 1 : 0]; px[it].r = sp[SC > 2 ? 2 : 0]; px[it].a = (SC == 4) ? sp[SC - 1] : 255;
-        }
-        if (nops) imp_run_ops_n<4>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
-            if (!live[it]) continue;
-            uint8_t* d = ostage + so[it];
-            const ImpPx& p = px[it];
-            if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
-            else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
-        }
-    }
-    __syncthreads();
     // ---- copy-out: rows of the destination rectangle, 16 bytes per thread when the rows are 16-byte addressable ----
-    tile_copy_out(ostage, OS, job.dst + (size_t)Y0 * job.dst_pitch + (size_t)X0 * dc, job.dst_pitch, vw * dc, vh, tid, BLUR_THREADS);
+    tile_copy_out_w(ostage, OS, job.dst + (size_t)Y0 * job.dst_pitch + (size_t)X0 * dc, job.dst_pitch, vw * dc, vh, tid, BLUR_THREADS);
 }
 
 }  // namespace imp_tiles

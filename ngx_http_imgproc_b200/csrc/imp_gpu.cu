@@ -389,9 +389,11 @@ int pick_variant(const ImpPass& h, const ImpJob& j) {
     const uintptr_t img = (uintptr_t)j.src;
     const uintptr_t win = img + (size_t)h.sy0 * j.src_pitch + (size_t)h.sx0 * h.sc;
     if (img % 16 && win % 16) return fallback;
-    int variant = 1;                                                 // strip kernels: INTER_AREA, INTER_NN, INTER_LINEAR, index map
+    int variant = 1;                                                 // strip kernels: INTER_AREA (and INTER_LINEAR as an A/B candidate)
     if (h.kind == IMP_G_BLUR) variant = h.blur_r > 0 ? 2 : 0;        // fused blur tile kernel
     if (h.kind == IMP_G_CUBIC) variant = 4;                          // cubic tile kernel
+    if (h.gt > 0) variant = 5;                                       // gather tile kernel: index map, INTER_NN, INTER_LINEAR
+    else if (h.kind == IMP_G_COPY || h.kind == IMP_G_NN) return fallback;
     // the launch must fit the opt-in shared-memory limit the kernels are configured with (many LUT filters can push a
     // pass over it: ADVICE r1); the direct kernels stage only the ops
     if (variant && variant_smem(h, variant, variant_param(h, variant)) > kTileSmemLimit) return fallback;
@@ -418,9 +420,10 @@ int tile_smem_bytes(const ImpPass& h, int stages) {
     return 128 + ((ops + 127) & ~127) + stages * tile_stage_bytes(h) + 64;      // +64: padded taps past the last row
 }
 
-int variant_param(const ImpPass& h, int variant) { return variant == 1 ? tile_stages(h) : variant == 2 ? h.blur_r : 0; }
+int variant_param(const ImpPass& h, int variant) { return variant == 1 ? tile_stages(h) : variant == 2 ? h.blur_r : variant == 5 ? h.gt : 0; }
 int variant_smem(const ImpPass& h, int variant, int param) {
     if (variant == 4) return imp_cubic_dyn_smem(h.sc, (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15, h.tile_rs, h.tile_rows);
+    if (variant == 5) return imp_gather_dyn_smem(h.gt, (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15, h.tile_rs, h.tile_rows, h.dc);
     return variant == 1 ? tile_smem_bytes(h, param) : variant == 2 ? blur_smem_bytes(h) : ops_smem(h);
 }
 int variant_tiles(const ImpPass& h, int variant) {
@@ -428,6 +431,7 @@ int variant_tiles(const ImpPass& h, int variant) {
     if (variant == 2) return ((h.bw + IMP_BLUR_TW - 1) / IMP_BLUR_TW) * ((h.bh + IMP_BLUR_TH - 1) / IMP_BLUR_TH);   // same count in destination space
     if (variant == 3) return ((h.bw + 31) / 32) * ((h.bh + 8 * IMP_CUBIC_RUN - 1) / (8 * IMP_CUBIC_RUN));
     if (variant == 4) return ((h.bw + IMP_CUBIC_T - 1) / IMP_CUBIC_T) * ((h.bh + IMP_CUBIC_T - 1) / IMP_CUBIC_T);
+    if (variant == 5) return ((h.bw + h.gt - 1) / h.gt) * ((h.bh + h.gt - 1) / h.gt);                  // same count in destination space
     return pass_tiles(h);
 }
 
@@ -466,7 +470,7 @@ int batch_compile(imp_gpu_batch* b, cudaStream_t up) {
             const ImpHostPass& hp = it.plan->passes[k];
             ImpJob jb = make_job(it.plan, d, k, it.src, it.sp, it.dst, it.dp, b->scratch.p, off[i]);
             const int variant = pick_variant(hp.hdr, jb);
-            if (variant == 1 || variant == 2 || variant == 4) { int rc = encode_job_tmap(hp.hdr, jb, &b->tmaps); if (rc) return rc; }
+            if (variant == 1 || variant == 2 || variant == 4 || variant == 5) { int rc = encode_job_tmap(hp.hdr, jb, &b->tmaps); if (rc) return rc; }
             const int param = variant_param(hp.hdr, variant);
             pend.push_back(Pending{hp.hdr.kind, hp.hdr.sc, variant, param, occ_class(hp.hdr, variant, param), jb, hp.hdr, boff[i][k]});
         }
@@ -553,7 +557,7 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
         const ImpHostPass& hp = p->passes[k];
         ImpJob j = make_job(p, t_dev, k, src, sp, dst, dp, scratch, off);
         const int variant = pick_variant(hp.hdr, j);
-        if (variant == 1 || variant == 2 || variant == 4) { int rc = encode_job_tmap(hp.hdr, j, nullptr); if (rc) return rc; }
+        if (variant == 1 || variant == 2 || variant == 4 || variant == 5) { int rc = encode_job_tmap(hp.hdr, j, nullptr); if (rc) return rc; }
         if (hp.hdr.kind == IMP_G_BLUR && variant == 0) {
             CK(imp_launch_blur_generic(j, hp.hdr, (uint16_t*)(scratch + boff[k]), ops_smem(hp.hdr), st));
         } else {

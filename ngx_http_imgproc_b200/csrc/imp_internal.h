@@ -75,7 +75,17 @@ cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, cons
 // Two-kernel Gaussian through a u16 scratch (any sigma). One job, passed by value.
 cudaError_t imp_launch_blur_generic(const ImpJob& job, const ImpPass& hdr, uint16_t* d_scratch, int smem_bytes, cudaStream_t st);
 unsigned long long imp_launches();
+void imp_count_launches(int n);
 cudaError_t imp_upload_tables();
+// one translation unit per kernel family (each with its own copy of the per-byte division tables, imp_pixel.cuh)
+cudaError_t imp_upload_tables_strip();
+cudaError_t imp_upload_tables_blur();
+cudaError_t imp_upload_tables_cubic();
+cudaError_t imp_upload_tables_gather();
+cudaError_t imp_launch_strip(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st);        // imp_k_strip.cu
+cudaError_t imp_launch_blur_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st);    // imp_k_blur.cu
+cudaError_t imp_launch_cubic_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st);   // imp_k_cubic.cu
+cudaError_t imp_launch_gather_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st);  // imp_k_gather.cu
 // rows of `row_bytes` bytes from (src, sp) to (dst, dp); dst and dp are multiples of 4 (the library's own pitched buffers)
 cudaError_t imp_launch_repitch(const uint8_t* d_src, int sp, uint8_t* d_dst, int dp, int row_bytes, int rows, cudaStream_t st);
 cudaError_t imp_launch_gif_expand(const ImpGifFrame* d_frames, int n, int cw, int ch, int destructive, uint8_t* d_canvases, int cpitch, cudaStream_t st);

@@ -8,23 +8,20 @@
 #include "imp_internal.h"
 #include <algorithm>
 #include "imp_gather.cuh"
-#include "imp_tiles.cuh"
-#include "imp_blur.cuh"
-#include "imp_cubic.cuh"
 
 #include <atomic>
 static std::atomic<unsigned long long> g_imp_launches{0};
 unsigned long long imp_launches() { return g_imp_launches.load(); }
+void imp_count_launches(int n) { g_imp_launches += (unsigned long long)n; }
 
-__device__ float g_imp_div255[256];
-__device__ float g_imp_div30[256];
-
+// every kernel translation unit has its own copy of the per-byte division tables (imp_pixel.cuh)
 cudaError_t imp_upload_tables() {
-    float a[256], b[256];
-    for (int i = 0; i < 256; i++) { a[i] = (float)i / 255.0f; b[i] = (float)(i * 2) / 60.0f; }     // IEEE float division on the host
-    cudaError_t e = cudaMemcpyToSymbol(g_imp_div255, a, sizeof a);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(g_imp_div30, b, sizeof b);
+    cudaError_t e = imp_upload_tables_tu();
+    if (e == cudaSuccess) e = imp_upload_tables_strip();
+    if (e == cudaSuccess) e = imp_upload_tables_blur();
+    if (e == cudaSuccess) e = imp_upload_tables_cubic();
+    if (e == cudaSuccess) e = imp_upload_tables_gather();
+    return e;
 }
 
 // mask[d2] for d2 = 0..n-1: the per-pixel code of imp_vignette_mask evaluated at (dx, dy) = (d2's exact sqrt is not
@@ -493,68 +490,6 @@ cudaError_t launch_kind(const ImpLaunchGroup& g, const ImpJob* d_jobs, const Imp
 
 }  // namespace
 
-template <int SC, int MODE>
-cudaError_t launch_area_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
-    static std::atomic<bool> attr_set[16];                 // per device; setting the attribute twice is harmless
-    int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_strip_kernel<SC, MODE>;
-    if (!attr_set[dev & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set[dev & 15] = true;
-    }
-    dim3 block(imp_tiles::STRIP_THREADS);
-    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);      // max_tiles = strips (tile columns)
-    kern<<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o, g.tmax);
-    g_imp_launches++;
-    return cudaGetLastError();
-}
-
-template <int SC, int R>
-cudaError_t launch_blur_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
-    static std::atomic<bool> attr_set[16];                 // per device; setting the attribute twice is harmless
-    int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_blur_tile_kernel<SC, R>;
-    if (!attr_set[dev & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set[dev & 15] = true;
-    }
-    dim3 block(imp_tiles::BLUR_THREADS);
-    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);      // max_tiles = 32x64 tiles
-    kern<<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o);
-    g_imp_launches++;
-    return cudaGetLastError();
-}
-
-template <int SC>
-cudaError_t launch_blur_tile_r(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
-    switch (g.tmax) {
-        case 3:  return launch_blur_tile<SC, 3>(g, d_jobs, o, st);
-        case 6:  return launch_blur_tile<SC, 6>(g, d_jobs, o, st);
-        case 9:  return launch_blur_tile<SC, 9>(g, d_jobs, o, st);
-        case 12: return launch_blur_tile<SC, 12>(g, d_jobs, o, st);
-    }
-    return cudaErrorInvalidValue;
-}
-
-template <int SC>
-cudaError_t launch_cubic_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
-    static std::atomic<bool> attr_set[16];
-    int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_cubic_tile_kernel<SC>;
-    if (!attr_set[dev & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set[dev & 15] = true;
-    }
-    dim3 block(imp_tiles::CUBIC_THREADS);
-    dim3 grid(g.max_tiles, g.count < 65535 ? g.count : 65535, (g.count + 65534) / 65535);      // max_tiles = 32x32 output tiles
-    kern<<<grid, block, g.smem_bytes, st>>>(d_jobs, g.first, g.count, o);
-    g_imp_launches++;
-    return cudaGetLastError();
-}
-
 cudaError_t launch_cubic_run(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st) {
     const ImpJob dummy{};
     const ImpJob& o = one ? *one : dummy;
@@ -572,47 +507,10 @@ cudaError_t launch_cubic_run(const ImpLaunchGroup& g, const ImpJob* d_jobs, cons
 
 cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st) {
     if (g.variant == 3 && g.kind == IMP_G_CUBIC) return launch_cubic_run(g, d_jobs, one, st);
-    if (g.variant == 2 && g.kind == IMP_G_BLUR) {
-        const ImpJob dummy{};
-        const ImpJob& o = one ? *one : dummy;
-        if (g.sc == 3) return launch_blur_tile_r<3>(g, d_jobs, o, st);
-        if (g.sc == 4) return launch_blur_tile_r<4>(g, d_jobs, o, st);
-        return cudaErrorInvalidValue;
-    }
-    if (g.variant == 4 && g.kind == IMP_G_CUBIC) {
-        const ImpJob dummy{};
-        const ImpJob& o = one ? *one : dummy;
-        switch (g.sc) {
-            case 1: return launch_cubic_tile<1>(g, d_jobs, o, st);
-            case 3: return launch_cubic_tile<3>(g, d_jobs, o, st);
-            case 4: return launch_cubic_tile<4>(g, d_jobs, o, st);
-        }
-        return cudaErrorInvalidValue;
-    }
-    if (g.variant == 1) {
-        const ImpJob dummy{};
-        const ImpJob& o = one ? *one : dummy;
-        // strip kernel modes (imp_tiles.cuh): 0 fractional INTER_AREA, 1 integer INTER_AREA, 2 INTER_NN, 3 INTER_LINEAR, 4 index map
-        const int mode = g.kind == IMP_G_AREA_FRAC ? 0 : g.kind == IMP_G_AREA_INT ? 1 : g.kind == IMP_G_NN ? 2 : g.kind == IMP_G_LINEAR ? 3 : g.kind == IMP_G_COPY ? 4 : -1;
-        switch (mode * 8 + g.sc) {
-            case 0 * 8 + 1: return launch_area_tile<1, 0>(g, d_jobs, o, st);
-            case 0 * 8 + 3: return launch_area_tile<3, 0>(g, d_jobs, o, st);
-            case 0 * 8 + 4: return launch_area_tile<4, 0>(g, d_jobs, o, st);
-            case 1 * 8 + 1: return launch_area_tile<1, 1>(g, d_jobs, o, st);
-            case 1 * 8 + 3: return launch_area_tile<3, 1>(g, d_jobs, o, st);
-            case 1 * 8 + 4: return launch_area_tile<4, 1>(g, d_jobs, o, st);
-            case 2 * 8 + 1: return launch_area_tile<1, 2>(g, d_jobs, o, st);
-            case 2 * 8 + 3: return launch_area_tile<3, 2>(g, d_jobs, o, st);
-            case 2 * 8 + 4: return launch_area_tile<4, 2>(g, d_jobs, o, st);
-            case 3 * 8 + 1: return launch_area_tile<1, 3>(g, d_jobs, o, st);
-            case 3 * 8 + 3: return launch_area_tile<3, 3>(g, d_jobs, o, st);
-            case 3 * 8 + 4: return launch_area_tile<4, 3>(g, d_jobs, o, st);
-            case 4 * 8 + 1: return launch_area_tile<1, 4>(g, d_jobs, o, st);
-            case 4 * 8 + 3: return launch_area_tile<3, 4>(g, d_jobs, o, st);
-            case 4 * 8 + 4: return launch_area_tile<4, 4>(g, d_jobs, o, st);
-        }
-        return cudaErrorInvalidValue;
-    }
+    if (g.variant == 2 && g.kind == IMP_G_BLUR) return imp_launch_blur_tile(g, d_jobs, one, st);       // imp_k_blur.cu
+    if (g.variant == 4 && g.kind == IMP_G_CUBIC) return imp_launch_cubic_tile(g, d_jobs, one, st);     // imp_k_cubic.cu
+    if (g.variant == 5) return imp_launch_gather_tile(g, d_jobs, one, st);                             // imp_k_gather.cu
+    if (g.variant == 1) return imp_launch_strip(g, d_jobs, one, st);                                   // imp_k_strip.cu
     switch (g.kind) {
         case IMP_G_COPY:      return launch_kind<IMP_G_COPY>(g, d_jobs, one, st);
         case IMP_G_NN:        return launch_kind<IMP_G_NN>(g, d_jobs, one, st);

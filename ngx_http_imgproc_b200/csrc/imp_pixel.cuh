@@ -20,6 +20,18 @@
 #define IMP_HD inline
 #endif
 
+#if defined(__CUDACC__)
+// x/255.0f and (2x)/60.0f for every byte x, divided on the host with IEEE float division (imp_gpu_init). The library is
+// built without relocatable device code, so every kernel translation unit carries its own copy (2 KB) and exports an
+// uploader built from imp_upload_tables_tu(); imp_upload_tables() (imp_kernels.cu) calls them all.
+static __device__ float g_imp_div255[256];
+static __device__ float g_imp_div30[256];
+// ceil(2^31 / d) for d = 1..255 (0 for d = 0): floor(n / d) == umulhi(2n + 1, g_imp_recip31[d]) for 0 <= n < 2^16.
+// (2n+1) * (2^31/d + e) / 2^32 = (n + 1/2)/d + (2n+1)e/2^32 with 0 <= e < 1: the first term lies at least 1/(2d) >= 2^-9
+// below the next integer and never below floor(n/d); the second is < 2^-15.
+static __device__ unsigned g_imp_recip31[256];
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define IMP_FMUL(a, b) __fmul_rn((a), (b))
 #define IMP_FADD(a, b) __fadd_rn((a), (b))
@@ -40,19 +52,13 @@ struct ImpPx { int b, g, r, a; };
 // (16 lanes/clk/SM on sm_100 vs 64+ for the ALU/FMA pipes; the first ncu capture of the pass kernel showed
 // I2F alone at >100 % of the XU pipe). All of them are exact for the ranges stated.
 #if defined(__CUDA_ARCH__)
-// x/255.0f and (2x)/60.0f for every byte x, divided on the host with IEEE float division (imp_gpu_init).
-extern __device__ float g_imp_div255[256];
-extern __device__ float g_imp_div30[256];
 // 0 <= x < 2^23 -> float, exact (LOP3 + FADD)
 __device__ __forceinline__ float imp_u2f(int x) { return __fadd_rn(__uint_as_float(0x4B000000u | (unsigned)x), -8388608.0f); }
 // 0 <= x < 2^23 -> trunc(x) (FADD.RZ + LOP3); NaN -> 0x400000 (low byte 0, like x86's INT_MIN)
 __device__ __forceinline__ int imp_f2u(float x) { return __float_as_int(__fadd_rz(x, 8388608.0f)) & 0x7FFFFF; }
-// n / d for 0 <= n <= 65535, 1 <= d <= 255, exact: the approximate reciprocal is biased up by 2^-18, more than its
-// own error (2^-22) and less than the 1/d gap that separates a non-integer quotient from the next integer.
+// floor(n / d) for 0 <= n <= 65535, 0 <= d <= 255 (0 when d == 0), exact: one table load + LEA + IMAD.HI (see g_imp_recip31)
 __device__ __forceinline__ int imp_udiv16(int n, int d) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(imp_u2f(d)));
-    return imp_f2u(__fmul_rn(imp_u2f(n), __fmul_rn(r, 1.000003814697265625f)));
+    return (int)__umulhi(2u * (unsigned)n + 1u, __ldg(&g_imp_recip31[d]));
 }
 // |x| < 2^22 -> float, exact (IADD + FADD); float |x| < 2^22 -> round-half-even int (FADD + IADD)
 __device__ __forceinline__ float imp_i2f22(int x) { return __fadd_rn(__int_as_float(0x4B400000 + x), -12582912.0f); }
@@ -62,7 +68,7 @@ inline float imp_i2f22(int x) { return (float)x; }
 inline int imp_rint22(float x) { return (int)lrintf(x); }
 inline float imp_u2f(int x) { return (float)x; }
 inline int imp_f2u(float x) { return (x == x) ? (int)x : 0x400000; }
-inline int imp_udiv16(int n, int d) { return n / d; }
+inline int imp_udiv16(int n, int d) { return d ? n / d : 0; }
 #endif
 
 // x86 cvttss2si: truncate; NaN / out of range -> 0x80000000.
@@ -74,6 +80,20 @@ IMP_HD int imp_sat8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 IMP_HD int imp_min(int a, int b) { return a < b ? a : b; }
 IMP_HD int imp_max(int a, int b) { return a > b ? a : b; }
 
+#if defined(__CUDACC__)
+static inline cudaError_t imp_upload_tables_tu() {
+    float a[256], b[256];
+    for (int i = 0; i < 256; i++) { a[i] = (float)i / 255.0f; b[i] = (float)(i * 2) / 60.0f; }     // IEEE float division on the host
+    unsigned r[256];
+    r[0] = 0;
+    for (unsigned d = 1; d < 256; d++) r[d] = (unsigned)(((1ull << 31) + d - 1) / d);
+    cudaError_t e = cudaMemcpyToSymbol(g_imp_div255, a, sizeof a);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_imp_div30, b, sizeof b);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_imp_recip31, r, sizeof r);
+    return e;
+}
+#endif
+
 IMP_HD void imp_map_xy(const ImpFrameMap& m, int bx, int by, int& x, int& y) {
     int u = m.swap ? by : bx, v = m.swap ? bx : by;
     x = m.flipx ? m.w - 1 - u : u;
@@ -81,26 +101,28 @@ IMP_HD void imp_map_xy(const ImpFrameMap& m, int bx, int by, int& x, int& y) {
 }
 
 // helpers.c:70-107 RGB2HSV (integer; C division truncates toward zero).
+// Branch-free: the reference's `if (v != 0)` / `if (s != 0)` guards only skip work whose result is 0 anyway — v == 0
+// means delta == 0, and s == 0 <=> delta == 0 (255*delta >= v as soon as delta >= 1), where the first maximum is r and
+// num = g - b = 0 — and imp_udiv16 returns 0 for a zero divisor.
 IMP_HD void imp_rgb2hsv(int b, int g, int r, int& h, int& s, int& v) {
-    int mn = imp_min(b, imp_min(g, r)), mx = imp_max(b, imp_max(g, r));
-    int delta = mx - mn;
-    h = 0; s = 0; v = mx;
-    if (v != 0) s = imp_udiv16(255 * delta, v);
-    if (s != 0) {
-        int num, base;
-        if (mx == r)      { num = g - b; base = 0; }
-        else if (mx == g) { num = b - r; base = 60; }
-        else              { num = r - g; base = 120; }
-        const int q = imp_udiv16(30 * (num < 0 ? -num : num), delta);      // C division truncates toward zero
-        h = base + (num < 0 ? -q : q);
-    }
+    const int mn = imp_min(b, imp_min(g, r)), mx = imp_max(b, imp_max(g, r));
+    const int delta = mx - mn;
+    v = mx;
+    s = imp_udiv16(255 * delta, v);
+    const bool ir = mx == r, ig = mx == g;                                  // the reference tests r, then g, else b
+    const int num = ir ? g - b : (ig ? b - r : r - g);
+    const int base = ir ? 0 : (ig ? 60 : 120);
+    const int q = imp_udiv16(30 * (num < 0 ? -num : num), delta);          // C division truncates toward zero
+    h = base + (num < 0 ? -q : q);
     if (h < 0) h += 180;
 }
 
 // helpers.c:109-176 HSV2RGB (float32; `default:` also takes sector 6, i.e. H == 180).
 // Inputs are the BYTES the reference would have stored (0..255).
+// Branch-free: with S == 0 every product below is v * 1.0f, i.e. (V,V,V) like the reference's early return; of q and t only
+// the one the sector uses is evaluated (q in odd sectors and in `default`, t in even ones), by the expression the
+// reference evaluates; the sector switch is three selects.
 IMP_HD void imp_hsv2rgb(int H, int S, int V, int& b, int& g, int& r) {
-    if (S == 0) { r = g = b = V; return; }
     const float v = imp_u2f(V);
 #if defined(__CUDA_ARCH__)
     const float s = __ldg(&g_imp_div255[S]);
@@ -113,17 +135,14 @@ IMP_HD void imp_hsv2rgb(int H, int S, int V, int& b, int& g, int& r) {
     const float f = IMP_FSUB(h, imp_u2f(i));
     // v in [0,255], factors in [0,1]: plain truncation is in range
     const int p = imp_f2u(IMP_FMUL(v, IMP_FSUB(1.0f, s)));
-    const int q = imp_f2u(IMP_FMUL(v, IMP_FSUB(1.0f, IMP_FMUL(s, f))));
-    const int t = imp_f2u(IMP_FMUL(v, IMP_FSUB(1.0f, IMP_FMUL(s, IMP_FSUB(1.0f, f)))));
-    switch (i) {
-        case 0:  r = V; g = t; b = p; break;
-        case 1:  r = q; g = V; b = p; break;
-        case 2:  r = p; g = V; b = t; break;
-        case 3:  r = p; g = q; b = V; break;
-        case 4:  r = t; g = p; b = V; break;
-        default: r = V; g = p; b = q; break;
-    }
-    b &= 255; g &= 255; r &= 255;
+    const bool use_q = (i & 1) != 0 || i >= 5;
+    const float ff = use_q ? f : IMP_FSUB(1.0f, f);
+    const int x = imp_f2u(IMP_FMUL(v, IMP_FSUB(1.0f, IMP_FMUL(s, ff))));    // q = v(1 - s f) or t = v(1 - s(1 - f))
+    // sector:  0 (V,t,p)  1 (q,V,p)  2 (p,V,t)  3 (p,q,V)  4 (t,p,V)  default (V,p,q)      as (r,g,b)
+    r = (i == 0 || i >= 5) ? V : ((i == 1 || i == 4) ? x : p);
+    g = (i == 1 || i == 2) ? V : ((i == 0 || i == 3) ? x : p);
+    b = (i == 3 || i == 4) ? V : ((i == 2 || i >= 5) ? x : p);
+    // v in [0,255] and the factors in [0,1]: p, x are already bytes
 }
 
 // filters.c:524-547: (int)fmin(c*k/100.0, 255) stored through char == C-truncating (c*k)/100 capped at
@@ -209,7 +228,7 @@ IMP_HD void imp_op_scanline(ImpPx& p, int y, int period, int freq, int sbyte, in
 // the 4th power are double, then narrowed (libm vs CUDA may differ in the last double ulp, which the
 // float narrowing hides except with probability ~2^-29: tested as <= 1 LSB).
 #if defined(__CUDACC__)
-__host__ __device__ __noinline__            // double cos + its slow path: large and rare, keep one copy per kernel
+static __host__ __device__ __noinline__     // double cos + its slow path: large and rare, keep one copy per kernel
 #else
 inline
 #endif

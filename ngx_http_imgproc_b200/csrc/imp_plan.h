@@ -84,6 +84,7 @@ struct ImpPass {
     int tile_rs, tile_rows;   // tile kernels: shared-memory row stride (bytes) and max source rows per 32x8 tile
     int tile_smem;            // tile kernels: source-tile bytes (tile_rs*tile_rows); 0 = no tile variant for this pass
     int xtile_off, ytile_off; // tile kernels: int2 per tile column {first px, last px}; int4 per tile row {first src row, rows, first y tap, y taps}
+    int gt;                   // gather tile kernel (imp_gathertile.cuh; COPY / NN / LINEAR): destination tile edge, 64 or 32; 0 = none
     int tile_ytaps;           // strip kernel: y-tap entries staged per tile (max over tiles, incl. alignment slack)
     int yrow4_off;            // strip kernel: int4 per output row {byte offset of its first source row inside the tile, y taps, index of its first tap in the tile's staged taps, 0}
     int nops;
@@ -103,6 +104,10 @@ struct ImpPass {
     (((((tile_rs) * (tile_rows)) > IMP_CUBIC_T * IMP_CUBIC_T * 3 ? ((tile_rs) * (tile_rows)) : IMP_CUBIC_T * IMP_CUBIC_T * 3) + 127) & ~127)
 inline int imp_cubic_dyn_smem(int sc, int ops_bytes16, int tile_rs, int tile_rows) {
     return 128 + ((ops_bytes16 + 127) & ~127) + IMP_CUBIC_TILE_BYTES(tile_rs, tile_rows) + tile_rows * IMP_CUBIC_HRS(sc) * 4 + 64;
+}
+// imp_gathertile.cuh: [bar 128][ops][TMA box][6*T lookup words][T rows of T*3 bytes: out stage of 3-channel results]
+inline int imp_gather_dyn_smem(int gt, int ops_bytes16, int tile_rs, int tile_rows, int dc) {
+    return 128 + ((ops_bytes16 + 127) & ~127) + ((tile_rs * tile_rows + 127) & ~127) + 6 * gt * 4 + (dc == 4 ? 0 : gt * gt * 3) + 64;
 }
 #define IMP_BLUR_TW 32
 #define IMP_BLUR_TH 64

@@ -229,6 +229,26 @@ void gather_strip_tables(BlobBuilder& bb, ImpPass& P, int c, FXL x_lo, FXH x_hi,
     P.tile_smem = (P.tile_rs <= 2048 && rows <= 256 && (long long)P.tile_rs * rows <= 64 * 1024) ? P.tile_rs * rows : 0;
 }
 
+// Gather tile kernel (imp_gathertile.cuh; index map, NN, LINEAR): T x T tiles of the destination at ANY base origin (it
+// tiles in destination space, so flips move the origin). The TMA box is the largest source rectangle such a tile reads;
+// T = 64 when that box stays small (upscales, copies), 32 otherwise, none when even that is too large.
+// x_lo/x_hi(bx), y_lo/y_hi(by): clamped source coordinates a base column / row reads; non-decreasing in bx / by.
+template <class FXL, class FXH, class FYL, class FYH>
+void gather_tile_tables(ImpPass& P, int c, FXL x_lo, FXH x_hi, FYL y_lo, FYH y_hi) {
+    const int rw = P.bw, rh = P.bh;
+    for (int T : {64, 32}) {
+        int span = 0, rows = 0;
+        for (int x0 = 0; x0 < rw; x0++) span = std::max(span, x_hi(std::min(x0 + T, rw) - 1) - x_lo(x0) + 1);
+        for (int y0 = 0; y0 < rh; y0++) rows = std::max(rows, y_hi(std::min(y0 + T, rh) - 1) - y_lo(y0) + 1);
+        const int rs = (span * c + 15 + 15) & ~15;                  // +15 for the 16-byte alignment of the box origin
+        const long long bytes = (long long)rs * rows;
+        if (rs <= 2048 && rows <= 256 && bytes <= (T == 64 ? 24 : 40) * 1024) {
+            P.gt = T; P.tile_rs = rs; P.tile_rows = rows; P.tile_smem = (int)bytes;
+            return;
+        }
+    }
+}
+
 // ---- lowering state -----------------------------------------------------------------------------------
 struct Lower {
     imp_gpu_plan* plan;
@@ -287,7 +307,7 @@ struct Lower {
         hdr.sc = in_c_;
     }
     void copy_tables() {
-        gather_strip_tables(bb, hdr, hdr.sc, [](int x) { return x; }, [](int x) { return x; }, [](int y) { return y; }, [](int y) { return y; });
+        gather_tile_tables(hdr, hdr.sc, [](int x) { return x; }, [](int x) { return x; }, [](int y) { return y; }, [](int y) { return y; });
     }
     int add_lut(const uint8_t* p, int n) { int off = (int)luts.size(); luts.insert(luts.end(), p, p + n); return off; }
     int final_dc = 0;              // destination channels of the LAST pass when the encoder-side packing changes them
@@ -680,8 +700,11 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
             P.kind = IMP_G_NN;
             P.xofs_off = L.bb.add(xo.data(), xo.size() * 4);
             P.yofs_off = L.bb.add(yo.data(), yo.size() * 4);
-            gather_strip_tables(L.bb, P, c, [&](int x) { return xo[x]; }, [&](int x) { return xo[x]; },
-                                [&](int y) { return yo[y]; }, [&](int y) { return yo[y]; });
+            // staging pays while most staged rows are used: a nearest-neighbour shrink reads one row in scale_y, which the
+            // direct kernel fetches sector by sector instead
+            if (scale_y <= 1.5 && scale_x <= 2.0)
+                gather_tile_tables(P, c, [&](int x) { return xo[x]; }, [&](int x) { return xo[x]; },
+                                   [&](int y) { return yo[y]; }, [&](int y) { return yo[y]; });
         } else if (mode == 3 && scale_x >= 1 && scale_y >= 1) {
             {
                 // The strip kernel (imp_tiles.cuh) walks the same tap tables for both flavours; with integer scales
@@ -771,8 +794,18 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
                 P.tile_rows = rows;
                 P.tile_smem = (P.tile_rs <= 2048 && rows <= 96 && (long long)P.tile_rs * rows <= 48 * 1024) ? P.tile_rs * rows : 0;
             } else {
-                gather_strip_tables(L.bb, P, c, [&](int x) { return clampi(xo[x], 0, cw - 1); }, [&](int x) { return clampi(xo[x] + 1, 0, cw - 1); },
-                                    [&](int y) { return clampi(yo[y], 0, ch - 1); }, [&](int y) { return clampi(yo[y] + 1, 0, ch - 1); });
+                // two candidates (A/B with IMP_GPU_LINEAR=strip|tile): the persistent strip kernel's mode 3 and the gather tile kernel
+                // shrinking reads a large source rectangle per output tile: the persistent strip kernel streams it through its
+                // TMA ring (cfg1l: 0.36 ms against 0.56 ms for one box per tile); enlarging reads a small one and is bound by
+                // the stores, which the tile kernel issues 16 bytes at a time
+                static const int force = [] { const char* e = getenv("IMP_GPU_LINEAR"); return !e ? 0 : !strcmp(e, "strip") ? 1 : !strcmp(e, "tile") ? 2 : 0; }();
+                const bool strip = force ? force == 1 : (scale_x > 1.25 || scale_y > 1.25);
+                if (strip)
+                    gather_strip_tables(L.bb, P, c, [&](int x) { return clampi(xo[x], 0, cw - 1); }, [&](int x) { return clampi(xo[x] + 1, 0, cw - 1); },
+                                        [&](int y) { return clampi(yo[y], 0, ch - 1); }, [&](int y) { return clampi(yo[y] + 1, 0, ch - 1); });
+                else
+                    gather_tile_tables(P, c, [&](int x) { return clampi(xo[x], 0, cw - 1); }, [&](int x) { return clampi(xo[x] + 1, 0, cw - 1); },
+                                       [&](int y) { return clampi(yo[y], 0, ch - 1); }, [&](int y) { return clampi(yo[y] + 1, 0, ch - 1); });
             }
         }
     }

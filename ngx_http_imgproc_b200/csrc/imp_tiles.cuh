@@ -534,4 +534,37 @@ __device__ __forceinline__ void tile_copy_out(const uint8_t* s, int ss, uint8_t*
     }
 }
 
+// Same for a stage whose rows are only 4-byte aligned (row stride `ss` a multiple of 4, odd in words: see imp_blur.cuh):
+// a 16-byte global chunk is assembled from four 32-bit shared loads.
+__device__ __forceinline__ void tile_copy_out_w(const uint8_t* s, int ss, uint8_t* d, int dp, int row_bytes, int rows, int tid, int nt) {
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(d) | (unsigned)dp);
+    if ((mis & 15) == 0) {
+        const int nch = row_bytes >> 4, tail = row_bytes & 15;
+        for (int i = tid; i < rows * nch; i += nt) {
+            const int ry = i / nch, ch = i - ry * nch;
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(s + ry * ss + 16 * ch);
+            *reinterpret_cast<uint4*>(d + (size_t)ry * dp + 16 * ch) = make_uint4(q[0], q[1], q[2], q[3]);
+        }
+        for (int i = tid; i < rows * tail; i += nt) {
+            const int ry = i / tail, b = (nch << 4) + i - ry * tail;
+            d[(size_t)ry * dp + b] = s[ry * ss + b];
+        }
+    } else if ((mis & 3) == 0) {
+        const int nch = row_bytes >> 2, tail = row_bytes & 3;
+        for (int i = tid; i < rows * nch; i += nt) {
+            const int ry = i / nch, ch = i - ry * nch;
+            *reinterpret_cast<uint32_t*>(d + (size_t)ry * dp + 4 * ch) = *reinterpret_cast<const uint32_t*>(s + ry * ss + 4 * ch);
+        }
+        for (int i = tid; i < rows * tail; i += nt) {
+            const int ry = i / tail, b = (nch << 2) + i - ry * tail;
+            d[(size_t)ry * dp + b] = s[ry * ss + b];
+        }
+    } else {
+        for (int i = tid; i < rows * row_bytes; i += nt) {
+            const int ry = i / row_bytes, b = i - ry * row_bytes;
+            d[(size_t)ry * dp + b] = s[ry * ss + b];
+        }
+    }
+}
+
 }  // namespace imp_tiles
