@@ -161,7 +161,7 @@ int plan_to_device(imp_gpu_plan* plan) {
         const ImpPass& h = plan->passes[i].hdr;
         const ImpOp* ops = reinterpret_cast<const ImpOp*>(plan->passes[i].blob.data() + h.ops_off);
         for (int k = 0; k < h.nops; k++)
-            if (ops[k].kind == IMP_OP_VIGNETTE && ops[k].i[2] > 0) { tabs.push_back(Tab{i, (size_t)k, total}); total += align256((size_t)ops[k].i[2] * sizeof(float)); }
+            if (ops[k].kind == IMP_OP_VIGNETTE && ops[k].i[2] > 0) { tabs.push_back(Tab{i, (size_t)k, total}); total += align256((size_t)ops[k].i[2] * ops[k].i[3] * sizeof(float)); }
     }
     if (ctx.up_pending) { CK(cudaEventSynchronize(ctx.up_ev)); ctx.up_pending = false; }      // the staging buffer is free again
     int rc = ctx.h_up.grow(blob_total, true); if (rc) return rc;
@@ -175,7 +175,7 @@ int plan_to_device(imp_gpu_plan* plan) {
         const ImpPass& h = plan->passes[t.pass].hdr;
         ImpOp* op = reinterpret_cast<ImpOp*>(ctx.h_up.p + off[t.pass] + h.ops_off) + t.op;
         float* tab = reinterpret_cast<float*>(pd.arena + t.off);
-        CK(imp_build_vignette_table(tab, op->i[2], op->f[0], op->f[1], ctx.stream));
+        CK(imp_build_vignette_table(tab, op->i[2], op->i[3], op->f[0], op->f[1], ctx.stream));
         const unsigned long long v = (unsigned long long)(uintptr_t)tab;
         op->i[4] = (int)(unsigned)(v & 0xffffffffu); op->i[5] = (int)(unsigned)(v >> 32);
     }
@@ -392,7 +392,7 @@ int pick_variant(const ImpPass& h, const ImpJob& j) {
     int variant = 1;                                                 // strip kernels: INTER_AREA (and INTER_LINEAR as an A/B candidate)
     if (h.kind == IMP_G_BLUR) variant = h.blur_r > 0 ? 2 : 0;        // fused blur tile kernel
     if (h.kind == IMP_G_CUBIC) variant = 4;                          // cubic tile kernel
-    if (h.gt > 0) variant = 5;                                       // gather tile kernel: index map, INTER_NN, INTER_LINEAR
+    if (h.gt > 0 && h.kind != IMP_G_CUBIC) variant = 5;              // gather tile kernel: index map, INTER_NN, INTER_LINEAR
     else if (h.kind == IMP_G_COPY || h.kind == IMP_G_NN) return fallback;
     // the launch must fit the opt-in shared-memory limit the kernels are configured with (many LUT filters can push a
     // pass over it: ADVICE r1); the direct kernels stage only the ops
@@ -420,9 +420,9 @@ int tile_smem_bytes(const ImpPass& h, int stages) {
     return 128 + ((ops + 127) & ~127) + stages * tile_stage_bytes(h) + 64;      // +64: padded taps past the last row
 }
 
-int variant_param(const ImpPass& h, int variant) { return variant == 1 ? tile_stages(h) : variant == 2 ? h.blur_r : variant == 5 ? h.gt : 0; }
+int variant_param(const ImpPass& h, int variant) { return variant == 1 ? tile_stages(h) : variant == 2 ? h.blur_r : (variant == 5 || variant == 4) ? h.gt : 0; }
 int variant_smem(const ImpPass& h, int variant, int param) {
-    if (variant == 4) return imp_cubic_dyn_smem(h.sc, (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15, h.tile_rs, h.tile_rows);
+    if (variant == 4) return imp_cubic_dyn_smem(h.sc, (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15, h.tile_rs, h.tile_rows, h.gt, h.dc);
     if (variant == 5) return imp_gather_dyn_smem(h.gt, (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15, h.tile_rs, h.tile_rows, h.dc);
     return variant == 1 ? tile_smem_bytes(h, param) : variant == 2 ? blur_smem_bytes(h) : ops_smem(h);
 }
@@ -430,8 +430,7 @@ int variant_tiles(const ImpPass& h, int variant) {
     if (variant == 1) return (h.bw + 31) / 32;
     if (variant == 2) return ((h.bw + IMP_BLUR_TW - 1) / IMP_BLUR_TW) * ((h.bh + IMP_BLUR_TH - 1) / IMP_BLUR_TH);   // same count in destination space
     if (variant == 3) return ((h.bw + 31) / 32) * ((h.bh + 8 * IMP_CUBIC_RUN - 1) / (8 * IMP_CUBIC_RUN));
-    if (variant == 4) return ((h.bw + IMP_CUBIC_T - 1) / IMP_CUBIC_T) * ((h.bh + IMP_CUBIC_T - 1) / IMP_CUBIC_T);
-    if (variant == 5) return ((h.bw + h.gt - 1) / h.gt) * ((h.bh + h.gt - 1) / h.gt);                  // same count in destination space
+    if (variant == 4 || variant == 5) return ((h.bw + h.gt - 1) / h.gt) * ((h.bh + h.gt - 1) / h.gt);                  // same count in destination space
     return pass_tiles(h);
 }
 

@@ -91,4 +91,4 @@ cudaError_t imp_launch_repitch(const uint8_t* d_src, int sp, uint8_t* d_dst, int
 cudaError_t imp_launch_gif_expand(const ImpGifFrame* d_frames, int n, int cw, int ch, int destructive, uint8_t* d_canvases, int cpitch, cudaStream_t st);
 cudaError_t imp_launch_ascii(const uint8_t* d_img, int pitch, int w, int h, int c, const uint8_t* d_lut, uint8_t* d_out, cudaStream_t st);
 cudaError_t imp_launch_brightness(const uint8_t* d_img, int pitch, int w, int h, int c, double* d_acc, cudaStream_t st);
-cudaError_t imp_build_vignette_table(float* d_tab, int n, float maxr, float intensity, cudaStream_t st);          // per-device constant tables of imp_pixel.cuh
+cudaError_t imp_build_vignette_table(float* d_tab, int nx, int ny, float maxr, float intensity, cudaStream_t st);          // per-device constant tables of imp_pixel.cuh

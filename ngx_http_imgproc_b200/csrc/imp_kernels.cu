@@ -24,20 +24,20 @@ cudaError_t imp_upload_tables() {
     return e;
 }
 
-// mask[d2] for d2 = 0..n-1: the per-pixel code of imp_vignette_mask evaluated at (dx, dy) = (d2's exact sqrt is not
-// needed: the mask only sees sqrt(dx*dx+dy*dy) = sqrt(d2)), i.e. at x = cx - 0 ... expressed through d2 directly.
-__global__ void imp_vignette_table_kernel(float* __restrict__ tab, int n, float maxr, float intensity) {
-    const int d2 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d2 >= n) return;
-    const float distance = (float)sqrt((double)d2);
+// mask[j][i] for |dx| = i < nx, |dy| = j < ny: the per-pixel code of imp_vignette_mask, which sees the pixel only through
+// sqrt(dx*dx + dy*dy).
+__global__ void imp_vignette_table_kernel(float* __restrict__ tab, int nx, int ny, float maxr, float intensity) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nx || j >= ny) return;
+    const float distance = (float)sqrt((double)i * (double)i + (double)j * (double)j);
     const float raw = __fmul_rn(__fdiv_rn(distance, maxr), intensity);
     const double c = cos((double)raw);
     const double c2 = c * c;
-    tab[d2] = (float)(c2 * c2);
+    tab[(size_t)j * nx + i] = (float)(c2 * c2);
 }
 
-cudaError_t imp_build_vignette_table(float* d_tab, int n, float maxr, float intensity, cudaStream_t st) {
-    imp_vignette_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_tab, n, maxr, intensity);
+cudaError_t imp_build_vignette_table(float* d_tab, int nx, int ny, float maxr, float intensity, cudaStream_t st) {
+    imp_vignette_table_kernel<<<dim3((nx + 255) / 256, ny), 256, 0, st>>>(d_tab, nx, ny, maxr, intensity);
     g_imp_launches++;
     return cudaGetLastError();
 }

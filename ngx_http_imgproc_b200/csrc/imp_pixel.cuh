@@ -346,14 +346,17 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
             case IMP_OP_VIGNETTE: {
 #if defined(__CUDA_ARCH__)
                 const float* tab = reinterpret_cast<const float*>(((unsigned long long)(unsigned)op.i[5] << 32) | (unsigned)op.i[4]);
-                if (tab) {           // mask[d2], tabulated per plan by imp_vignette_table_kernel with the code of imp_vignette_mask
-                    const int cx = op.i[0], cy = op.i[1];
+                if (tab) {           // mask[|dy|][|dx|], tabulated per plan by imp_vignette_table_kernel with the code of imp_vignette_mask
+                    const int cx = op.i[0], cy = op.i[1], stride = op.i[2];
+                    float mask[N];
 #pragma unroll
                     for (int n = 0; n < N; n++) {
                         int x, y; imp_map_xy(op.map, bx[n], by[n], x, y);
                         const int dx = cx - x, dy = cy - y;
-                        imp_op_vignette_masked(px[n], __ldg(tab + (dx * dx + dy * dy)));
+                        mask[n] = __ldg(tab + (dy < 0 ? -dy : dy) * stride + (dx < 0 ? -dx : dx));
                     }
+#pragma unroll
+                    for (int n = 0; n < N; n++) imp_op_vignette_masked(px[n], mask[n]);
                     break;
                 }
 #endif

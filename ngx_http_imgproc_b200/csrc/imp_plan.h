@@ -97,13 +97,16 @@ struct ImpPass {
 
 // Geometry of the fused blur tile kernel (imp_blur.cuh), shared with the planner (tap tables, TMA box) and the runtime
 // (shared-memory size). A CTA blurs a BTW x BTH tile of the base frame with taps padded to radius R.
-#define IMP_CUBIC_T 32        // imp_cubic.cuh: output tile edge
-#define IMP_CUBIC_HRS(sc) ((sc) == 4 ? IMP_CUBIC_T * 4 + 4 : IMP_CUBIC_T * (sc) + 1)     // floats per row of its horizontal-pass buffer
-// the TMA box region doubles as the 32 x 32 x 3-byte out stage of 3-channel results
-#define IMP_CUBIC_TILE_BYTES(tile_rs, tile_rows) \
-    (((((tile_rs) * (tile_rows)) > IMP_CUBIC_T * IMP_CUBIC_T * 3 ? ((tile_rs) * (tile_rows)) : IMP_CUBIC_T * IMP_CUBIC_T * 3) + 127) & ~127)
-inline int imp_cubic_dyn_smem(int sc, int ops_bytes16, int tile_rs, int tile_rows) {
-    return 128 + ((ops_bytes16 + 127) & ~127) + IMP_CUBIC_TILE_BYTES(tile_rs, tile_rows) + tile_rows * IMP_CUBIC_HRS(sc) * 4 + 64;
+// imp_cubic.cuh: floats per row of the horizontal-pass buffer of a T-wide tile (+4 / +1: bank spread), and the launch's
+// dynamic shared memory: [bar 128][ops][TMA box][hbuf rows x HRS floats][T x {int4, float4} row lookups][T x T*3 out stage]
+// Columns are stored group-transposed — column lx at position (lx & 3) * (T/4 + 1) + (lx >> 2) — so that the vertical pass,
+// where a thread owns columns 4t .. 4t+3, reads consecutive positions across a warp (conflict-free), hence T + 4 positions
+// per row; the row stride is 4 mod 32 words (float4 rows of 8 lanes spread over all banks) or odd.
+#define IMP_CUBIC_HRS(sc, T) ((sc) == 4 ? ((T) + 4) * 4 + 20 : ((T) + 4) * (sc) + 1)
+#define IMP_CUBIC_POS(lx, T) (((lx) & 3) * ((T) / 4 + 1) + ((lx) >> 2))
+inline int imp_cubic_dyn_smem(int sc, int ops_bytes16, int tile_rs, int tile_rows, int T, int dc) {
+    return 128 + ((ops_bytes16 + 127) & ~127) + ((tile_rs * tile_rows + 127) & ~127) + ((tile_rows * IMP_CUBIC_HRS(sc, T) * 4 + 15) & ~15) + T * 32 +
+           (dc == 4 ? 0 : T * T * 3) + 64;
 }
 // imp_gathertile.cuh: [bar 128][ops][TMA box][6*T lookup words][T rows of T*3 bytes: out stage of 3-channel results]
 inline int imp_gather_dyn_smem(int gt, int ops_bytes16, int tile_rs, int tile_rows, int dc) {

@@ -533,12 +533,14 @@ int lower_filter(Lower& L, const char* request, int allow) {
                 if (maxd < d) maxd = d;
             }
             ImpOp o{}; o.kind = IMP_OP_VIGNETTE; o.i[0] = cx; o.i[1] = cy; o.f[0] = radius * maxd; o.f[1] = intensity; o.map = fr.map();
-            // The mask depends on the pixel only through d2 = dx*dx + dy*dy, an integer: the runtime tabulates it once per
-            // plan and device (same double-precision code as the per-pixel path) when the table stays below 64 MB.
+            // The mask depends on the pixel only through (|dx|, |dy|): the runtime tabulates it once per plan and device as
+            // mask[|dy|][|dx|] (same double-precision code as the per-pixel path) when the table stays below 64 MB. Indexed
+            // by d2 = dx*dx + dy*dy it was half the entries, but the 32 lanes of a warp then hit 32 different sectors of
+            // it; row-major in |dx| they read one or two.
             {
                 long long mx = std::max(cx, w - 1 - cx), my = std::max(cy, h - 1 - cy);
-                long long entries = mx * mx + my * my + 1;
-                o.i[2] = entries <= (16ll << 20) ? (int)entries : 0;
+                long long entries = (mx + 1) * (my + 1);
+                if (entries <= (16ll << 20)) { o.i[2] = (int)(mx + 1); o.i[3] = (int)(my + 1); }
             }
             L.push(o);
             return IMP_OK;
@@ -779,20 +781,26 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
                 std::vector<float> ybf(yb.size());
                 for (size_t i = 0; i < yb.size(); i++) ybf[i] = (float)yb[i] * (1.0f / 4194304.0f);
                 P.taps_off = L.bb.add(ybf.data(), ybf.size() * 4);
-                // tile kernel (imp_cubic.cuh): 32 x 32 output tiles at ANY origin (it tiles in destination space); the TMA
-                // box is the largest source rectangle such a tile's clamped 4x4 footprints span
-                int span = 0, rows = 0;
-                for (int x0 = 0; x0 < rw; x0++) {
-                    const int x1 = std::min(x0 + IMP_CUBIC_T, rw) - 1;
-                    span = std::max(span, clampi(xo[x1] + 2, 0, cw - 1) - clampi(xo[x0] - 1, 0, cw - 1) + 1);
+                // tile kernel (imp_cubic.cuh): T x T output tiles at ANY origin (it tiles in destination space); the TMA box is
+                // the largest source rectangle such a tile's clamped 4x4 footprints span. T = 64 while the box and the
+                // horizontal-pass buffer stay within ~52 KB (four CTAs per SM), else 32, else the column-run kernel.
+                for (int T : {64, 32}) {
+                    int span = 0, rows = 0;
+                    for (int x0 = 0; x0 < rw; x0++) {
+                        const int x1 = std::min(x0 + T, rw) - 1;
+                        span = std::max(span, clampi(xo[x1] + 2, 0, cw - 1) - clampi(xo[x0] - 1, 0, cw - 1) + 1);
+                    }
+                    for (int y0 = 0; y0 < rh; y0++) {
+                        const int y1 = std::min(y0 + T, rh) - 1;
+                        rows = std::max(rows, clampi(yo[y1] + 2, 0, ch - 1) - clampi(yo[y0] - 1, 0, ch - 1) + 1);
+                    }
+                    const int rs = (span * c + 15 + 15) & ~15;
+                    const long long bytes = (long long)rs * rows + (long long)rows * IMP_CUBIC_HRS(c, T) * 4;
+                    if (rs <= 2048 && rows <= 160 && bytes <= 52 * 1024) {
+                        P.gt = T; P.tile_rs = rs; P.tile_rows = rows; P.tile_smem = rs * rows;
+                        break;
+                    }
                 }
-                for (int y0 = 0; y0 < rh; y0++) {
-                    const int y1 = std::min(y0 + IMP_CUBIC_T, rh) - 1;
-                    rows = std::max(rows, clampi(yo[y1] + 2, 0, ch - 1) - clampi(yo[y0] - 1, 0, ch - 1) + 1);
-                }
-                P.tile_rs = (span * c + 15 + 15) & ~15;
-                P.tile_rows = rows;
-                P.tile_smem = (P.tile_rs <= 2048 && rows <= 96 && (long long)P.tile_rs * rows <= 48 * 1024) ? P.tile_rs * rows : 0;
             } else {
                 // two candidates (A/B with IMP_GPU_LINEAR=strip|tile): the persistent strip kernel's mode 3 and the gather tile kernel
                 // shrinking reads a large source rectangle per output tile: the persistent strip kernel streams it through its

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 TAG=${TAG:-r02}
 for c in ${CONFIGS:-cfg3 cfg3nn cfg4}; do
   python bench.py --config $c --scale ${SCALE:-4} --steps 3 --e2e-steps 0 --no-cpu --extras none > gpurun_out/prof_$c.plain.log 2>&1 || { echo "$c plain run failed"; tail -5 gpurun_out/prof_$c.plain.log; continue; }
-  ncu --set full --clock-control none --import-source on -k regex:'imp_(strip|blur_tile|cubic_tile|cubic_run|pass)_kernel' -s 2 -c 1 -f -o /tmp/${TAG}_$c \
+  ncu --set full --clock-control none --import-source on -k regex:'imp_(strip|blur_tile|cubic_tile|cubic_run|pass|gather_tile)_kernel' -s 2 -c 1 -f -o /tmp/${TAG}_$c \
       python bench.py --config $c --scale ${SCALE:-4} --steps 3 --e2e-steps 0 --no-cpu --extras none > gpurun_out/prof_$c.ncu.log 2>&1
   R=/tmp/${TAG}_$c.ncu-rep
   [ -f $R ] || { echo "$c: no report"; tail -5 gpurun_out/prof_$c.ncu.log; continue; }
