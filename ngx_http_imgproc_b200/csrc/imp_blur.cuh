@@ -50,7 +50,8 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
     const ImpFrameMap om = P->out;
     // ---- this CTA's tile, chosen in destination space ----
     const int TWd = om.swap ? BTH : BTW, THd = om.swap ? BTW : BTH;
-    const int tiles_xd = (om.w + TWd - 1) / TWd, tiles_yd = (om.h + THd - 1) / THd;
+    const int xsh = om.swap ? 6 : 5, ysh = om.swap ? 5 : 6;             // log2 of the destination tile edges
+    const int tiles_xd = (om.w + TWd - 1) >> xsh, tiles_yd = (om.h + THd - 1) >> ysh;
     if ((int)blockIdx.x >= tiles_xd * tiles_yd) return;
     const int X0 = ((int)blockIdx.x % tiles_xd) * TWd, Y0 = ((int)blockIdx.x / tiles_xd) * THd;
     const int vw = min(TWd, om.w - X0), vh = min(THd, om.h - Y0);       // valid destination rectangle
@@ -195,6 +196,15 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
         }
         const int bx = x0 + x;
         const int cbx = min(bx, w - 1);                                 // pixels of the tile beyond the frame: computed on a valid pixel, never stored
+        // the out-stage address of base pixel (bx, by) is affine in by for this thread's column (cf. StripStore)
+        int so0, sstep;
+        {
+            int Xa, Ya, Xb, Yb;
+            imp_map_xy(om, bx, y0, Xa, Ya);
+            imp_map_xy(om, bx, y0 + 1, Xb, Yb);
+            so0 = (Ya - Y0) * OS + (Xa - X0) * dc;
+            sstep = (Yb - Ya) * OS + (Xb - Xa) * dc;
+        }
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             ImpPx px[4];
@@ -211,12 +221,10 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
             if (nops) imp_run_ops_n<4>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int ly = 8 * g + 4 * half + k, by = y0 + ly;
+                const int ly = 8 * g + 4 * half + k;
                 if (x >= tw || ly >= th) continue;                      // outside the tile's valid rectangle (frame edge)
-                int X, Y;
-                imp_map_xy(om, bx, by, X, Y);
-                IMP_DBG(X >= X0 && X < X0 + vw && Y >= Y0 && Y < Y0 + vh, 1);
-                uint8_t* d = ostage + (Y - Y0) * OS + (X - X0) * dc;
+                uint8_t* d = ostage + so0 + ly * sstep;
+                IMP_DBG(d >= ostage && d + dc <= ostage + OS * THd, 1);
                 const ImpPx& p = px[k];
                 if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
                 else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }

@@ -21,6 +21,10 @@ namespace imp_tiles {
 
 constexpr int CUBIC_THREADS = 256;
 
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (lo) / b.byte2, b.byte3 (hi); a signed (coefficients), b unsigned (pixel bytes)
+__device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+
 __device__ __forceinline__ int rint_sat_u8(float x) {      // sat_u8(rint(x)), round-half-even, one F2I
     unsigned r;
     asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -43,7 +47,8 @@ imp_cubic_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
     const int HRS = IMP_CUBIC_HRS(SC, T);                               // floats per row of the horizontal-pass buffer
     const int bw = P->bw, sw = P->sw, sh = P->sh;
     const ImpFrameMap om = P->out;
-    const int tiles_xd = (om.w + T - 1) / T, tiles_yd = (om.h + T - 1) / T;
+    const int tsh = T == 64 ? 6 : 5;                                    // T is 64 or 32
+    const int tiles_xd = (om.w + T - 1) >> tsh, tiles_yd = (om.h + T - 1) >> tsh;
     if ((int)blockIdx.x >= tiles_xd * tiles_yd) return;
     const int X0 = ((int)blockIdx.x % tiles_xd) * T, Y0 = ((int)blockIdx.x / tiles_xd) * T;
     const int vw = min(T, om.w - X0), vh = min(T, om.h - Y0);           // valid destination rectangle
@@ -111,9 +116,13 @@ imp_cubic_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
             if (SC == 4) {
                 const uint32_t p0 = *reinterpret_cast<const uint32_t*>(row + so[0]), p1 = *reinterpret_cast<const uint32_t*>(row + so[1]);
                 const uint32_t p2 = *reinterpret_cast<const uint32_t*>(row + so[2]), p3 = *reinterpret_cast<const uint32_t*>(row + so[3]);
-#pragma unroll
-                for (int c = 0; c < SC; c++)
-                    hsum[c] = (int)((p0 >> (8 * c)) & 255) * a0 + (int)((p1 >> (8 * c)) & 255) * a1 + (int)((p2 >> (8 * c)) & 255) * a2 + (int)((p3 >> (8 * c)) & 255) * a3;
+                // byte-transpose pixel pairs (4 PRMT), then each channel is two mixed-sign dp2a: 12 instructions for the 16 MACs
+                const unsigned t01 = __byte_perm(p0, p1, 0x5140), u01 = __byte_perm(p0, p1, 0x7362);     // {c0:p0,p1 | c1:p0,p1}, {c2 | c3}
+                const unsigned t23 = __byte_perm(p2, p3, 0x5140), u23 = __byte_perm(p2, p3, 0x7362);
+                hsum[0] = dp2a_lo_su(av.x, t01, dp2a_lo_su(av.y, t23, 0));
+                hsum[SC > 1 ? 1 : 0] = dp2a_hi_su(av.x, t01, dp2a_hi_su(av.y, t23, 0));
+                hsum[SC > 2 ? 2 : 0] = dp2a_lo_su(av.x, u01, dp2a_lo_su(av.y, u23, 0));
+                hsum[SC > 3 ? 3 : 0] = dp2a_hi_su(av.x, u01, dp2a_hi_su(av.y, u23, 0));
             } else {
 #pragma unroll
                 for (int c = 0; c < SC; c++)
@@ -133,10 +142,10 @@ imp_cubic_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
     const short* __restrict__ yb = reinterpret_cast<const short*>(blob + P->ycoef_off);
     const int oc = P->oc, dc = P->dc, simd_end = P->simd_end;
     const int OS = T * 3;                                               // out-stage row stride (3-channel results)
-    const int qpr = T >> 2;                                             // 4-pixel groups per tile row
+    const int qsh = tsh - 2;                                            // log2 of the 4-pixel groups per tile row
     const bool vec16 = dc == 4 && ((reinterpret_cast<uintptr_t>(job.dst) | (unsigned)job.dst_pitch) & 15) == 0;
-    for (int item = tid; item < qpr * T; item += CUBIC_THREADS) {
-        const int Yl = item / qpr, Xq = (item - Yl * qpr) * 4;
+    for (int item = tid; item < (T << qsh); item += CUBIC_THREADS) {
+        const int Yl = item >> qsh, Xq = (item & ((1 << qsh) - 1)) * 4;
         if (Yl >= vh || Xq >= vw) continue;
         ImpPx px[4];
         int bxs[4], bys[4];
@@ -186,7 +195,8 @@ imp_cubic_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
         if (nops) imp_run_ops_n<4>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
         uint32_t w[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) w[k] = (uint32_t)(px[k].b & 255) | ((uint32_t)(px[k].g & 255) << 8) | ((uint32_t)(px[k].r & 255) << 16) | ((uint32_t)px[k].a << 24);
+        for (int k = 0; k < 4; k++)         // the low bytes of b, g, r, a: three PRMTs
+            w[k] = __byte_perm(__byte_perm((unsigned)px[k].b, (unsigned)px[k].g, 0x0040), __byte_perm((unsigned)px[k].r, (unsigned)px[k].a, 0x0040), 0x5410);
         if (dc == 4) {
             uint8_t* d = job.dst + (size_t)(Y0 + Yl) * job.dst_pitch + (size_t)(X0 + Xq) * 4;
             if (vec16 && Xq + 4 <= vw) *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -36,7 +36,8 @@ imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, co
     const int T = P->gt;
     const int sw = P->sw, sh = P->sh;
     const ImpFrameMap om = P->out;
-    const int tiles_xd = (om.w + T - 1) / T, tiles_yd = (om.h + T - 1) / T;
+    const int tsh = T == 64 ? 6 : 5;                                    // T is 64 or 32
+    const int tiles_xd = (om.w + T - 1) >> tsh, tiles_yd = (om.h + T - 1) >> tsh;
     if ((int)blockIdx.x >= tiles_xd * tiles_yd) return;
     const int X0 = ((int)blockIdx.x % tiles_xd) * T, Y0 = ((int)blockIdx.x / tiles_xd) * T;
     const int vw = min(T, om.w - X0), vh = min(T, om.h - Y0);           // valid destination rectangle
@@ -101,10 +102,10 @@ imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, co
 
     const int oc = P->oc, dc = P->dc;
     const int OS = T * 3;                                               // out-stage row stride (3-channel results)
-    const int qpr = T >> 2;                                             // 4-pixel groups per tile row
+    const int qsh = tsh - 2;                                            // log2 of the 4-pixel groups per tile row
     const bool vec16 = dc == 4 && ((reinterpret_cast<uintptr_t>(job.dst) | (unsigned)job.dst_pitch) & 15) == 0;
-    for (int item = tid; item < qpr * T; item += GATHER_THREADS) {
-        const int Yl = item / qpr, Xq = (item - Yl * qpr) * 4;
+    for (int item = tid; item < (T << qsh); item += GATHER_THREADS) {
+        const int Yl = item >> qsh, Xq = (item & ((1 << qsh) - 1)) * 4;
         if (Yl >= vh || Xq >= vw) continue;
         ImpPx px[4];
         int bxs[4], bys[4];
@@ -142,7 +143,7 @@ imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, co
                 const uint8_t* q = tile + ry0[ly] + cx0[lx];
                 if (SC == 4) {
                     const uint32_t w = *reinterpret_cast<const uint32_t*>(q);
-                    v4[0] = w & 255; v4[1] = (w >> 8) & 255; v4[2] = (w >> 16) & 255; v4[3] = w >> 24;
+                    v4[0] = __byte_perm(w, 0, 0x4440); v4[1] = __byte_perm(w, 0, 0x4441); v4[2] = __byte_perm(w, 0, 0x4442); v4[3] = w >> 24;
                 } else {
 #pragma unroll
                     for (int c = 0; c < SC; c++) v4[c] = q[c];
@@ -154,7 +155,8 @@ imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, co
         if (nops) imp_run_ops_n<4>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
         uint32_t w[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) w[k] = (uint32_t)(px[k].b & 255) | ((uint32_t)(px[k].g & 255) << 8) | ((uint32_t)(px[k].r & 255) << 16) | ((uint32_t)px[k].a << 24);
+        for (int k = 0; k < 4; k++)         // the low bytes of b, g, r, a: three PRMTs
+            w[k] = __byte_perm(__byte_perm((unsigned)px[k].b, (unsigned)px[k].g, 0x0040), __byte_perm((unsigned)px[k].r, (unsigned)px[k].a, 0x0040), 0x5410);
         if (dc == 4) {
             uint8_t* d = job.dst + (size_t)(Y0 + Yl) * job.dst_pitch + (size_t)(X0 + Xq) * 4;
             if (vec16 && Xq + 4 <= vw) *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -12,6 +12,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 #include "imp_plan.h"
 
 #if defined(__CUDACC__)
@@ -30,6 +31,11 @@ static __device__ float g_imp_div30[256];
 // (2n+1) * (2^31/d + e) / 2^32 = (n + 1/2)/d + (2n+1)e/2^32 with 0 <= e < 1: the first term lies at least 1/(2d) >= 2^-9
 // below the next integer and never below floor(n/d); the second is < 2^-15.
 static __device__ unsigned g_imp_recip31[256];
+// HSV2RGB per hue byte H (helpers.c:109-176): h = 2H/60, sector i = floor(h), f = h - i. Of q = v(1 - s f) and
+// t = v(1 - s(1 - f)) a sector uses exactly one: .x = the float bits of the factor it needs (f in odd sectors and in
+// `default`, 1 - f in even ones, computed on the host in the reference's float order), .y = the PRMT selector that places
+// {V, that value, p} into (b, g, r) for the sector.
+static __device__ int2 g_imp_hsv[256];
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -87,9 +93,22 @@ static inline cudaError_t imp_upload_tables_tu() {
     unsigned r[256];
     r[0] = 0;
     for (unsigned d = 1; d < 256; d++) r[d] = (unsigned)(((1ull << 31) + d - 1) / d);
+    int2 hs[256];
+    for (int H = 0; H < 256; H++) {
+        const float h = b[H];
+        const int i = (int)h;
+        const float f = h - (float)i;
+        const bool use_q = (i & 1) != 0 || i >= 5;
+        const float ff = use_q ? f : 1.0f - f;
+        // source bytes of the packed word: 0 = V, 1 = q|t, 2 = p; result bytes: 0 = b, 1 = g, 2 = r, 3 = 0
+        static const int sel[6] = {0x4012, 0x4102, 0x4201, 0x4210, 0x4120, 0x4021};     // sectors 0..4, default
+        memcpy(&hs[H].x, &ff, 4);
+        hs[H].y = sel[i < 5 ? i : 5];
+    }
     cudaError_t e = cudaMemcpyToSymbol(g_imp_div255, a, sizeof a);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_imp_div30, b, sizeof b);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_imp_recip31, r, sizeof r);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_imp_hsv, hs, sizeof hs);
     return e;
 }
 #endif
@@ -125,12 +144,16 @@ IMP_HD void imp_rgb2hsv(int b, int g, int r, int& h, int& s, int& v) {
 IMP_HD void imp_hsv2rgb(int H, int S, int V, int& b, int& g, int& r) {
     const float v = imp_u2f(V);
 #if defined(__CUDA_ARCH__)
+    // device: the effective fraction and the sector's byte placement come from one 8-byte table entry (see g_imp_hsv)
     const float s = __ldg(&g_imp_div255[S]);
-    const float h = __ldg(&g_imp_div30[H]);
+    const int2 e = __ldg(&g_imp_hsv[H]);
+    const int p = imp_f2u(IMP_FMUL(v, IMP_FSUB(1.0f, s)));
+    const int x = imp_f2u(IMP_FMUL(v, IMP_FSUB(1.0f, IMP_FMUL(s, __int_as_float(e.x)))));
+    const unsigned o = __byte_perm((unsigned)V | ((unsigned)x << 8) | ((unsigned)p << 16), 0u, (unsigned)e.y);
+    b = o & 255; g = (o >> 8) & 255; r = o >> 16;
 #else
     const float s = IMP_FDIV((float)S, 255.0f);
     const float h = IMP_FDIV((float)(H * 2), 60.0f);
-#endif
     const int i = imp_f2u(h);                                               // h >= 0: floor == trunc
     const float f = IMP_FSUB(h, imp_u2f(i));
     // v in [0,255], factors in [0,1]: plain truncation is in range
@@ -143,6 +166,7 @@ IMP_HD void imp_hsv2rgb(int H, int S, int V, int& b, int& g, int& r) {
     g = (i == 1 || i == 2) ? V : ((i == 0 || i == 3) ? x : p);
     b = (i == 3 || i == 4) ? V : ((i == 2 || i >= 5) ? x : p);
     // v in [0,255] and the factors in [0,1]: p, x are already bytes
+#endif
 }
 
 // filters.c:524-547: (int)fmin(c*k/100.0, 255) stored through char == C-truncating (c*k)/100 capped at
@@ -347,12 +371,16 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
 #if defined(__CUDA_ARCH__)
                 const float* tab = reinterpret_cast<const float*>(((unsigned long long)(unsigned)op.i[5] << 32) | (unsigned)op.i[4]);
                 if (tab) {           // mask[|dy|][|dx|], tabulated per plan by imp_vignette_table_kernel with the code of imp_vignette_mask
-                    const int cx = op.i[0], cy = op.i[1], stride = op.i[2];
+                    const int stride = op.i[2];
+                    // dx = cx - x with x = flipx ? w-1-u : u, i.e. an affine function of the base coordinate: hoisted out of the pixel loop
+                    const int swap = op.map.swap;
+                    const int sx = op.map.flipx ? 1 : -1, ox = op.i[0] - (op.map.flipx ? op.map.w - 1 : 0);
+                    const int sy = op.map.flipy ? 1 : -1, oy = op.i[1] - (op.map.flipy ? op.map.h - 1 : 0);
                     float mask[N];
 #pragma unroll
                     for (int n = 0; n < N; n++) {
-                        int x, y; imp_map_xy(op.map, bx[n], by[n], x, y);
-                        const int dx = cx - x, dy = cy - y;
+                        const int u = swap ? by[n] : bx[n], v = swap ? bx[n] : by[n];
+                        const int dx = ox + sx * u, dy = oy + sy * v;
                         mask[n] = __ldg(tab + (dy < 0 ? -dy : dy) * stride + (dx < 0 ? -dx : dx));
                     }
 #pragma unroll

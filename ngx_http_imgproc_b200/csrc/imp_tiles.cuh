@@ -506,13 +506,16 @@ imp_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __
 // buffers always are), 4 bytes or single bytes otherwise. Consecutive threads write consecutive chunks of a row.
 __device__ __forceinline__ void tile_copy_out(const uint8_t* s, int ss, uint8_t* d, int dp, int row_bytes, int rows, int tid, int nt) {
     const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(d) | (unsigned)dp);
-    if ((mis & 15) == 0) {
+    if ((mis & 15) == 0 && row_bytes <= 256) {
+        // rows of up to 16 chunks: chunk slots padded to a power of two, so (row, chunk) come from a shift and a mask
         const int nch = row_bytes >> 4, tail = row_bytes & 15;
-        for (int i = tid; i < rows * nch; i += nt) {
-            const int ry = i / nch, ch = i - ry * nch;
+        const int sl = nch <= 2 ? 1 : nch <= 4 ? 2 : nch <= 8 ? 3 : 4;
+        for (int i = tid; i < (rows << sl); i += nt) {
+            const int ry = i >> sl, ch = i & ((1 << sl) - 1);
+            if (ch >= nch) continue;
             *reinterpret_cast<uint4*>(d + (size_t)ry * dp + 16 * ch) = *reinterpret_cast<const uint4*>(s + ry * ss + 16 * ch);
         }
-        for (int i = tid; i < rows * tail; i += nt) {
+        if (tail) for (int i = tid; i < rows * tail; i += nt) {
             const int ry = i / tail, b = (nch << 4) + i - ry * tail;
             d[(size_t)ry * dp + b] = s[ry * ss + b];
         }
@@ -538,14 +541,17 @@ __device__ __forceinline__ void tile_copy_out(const uint8_t* s, int ss, uint8_t*
 // a 16-byte global chunk is assembled from four 32-bit shared loads.
 __device__ __forceinline__ void tile_copy_out_w(const uint8_t* s, int ss, uint8_t* d, int dp, int row_bytes, int rows, int tid, int nt) {
     const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(d) | (unsigned)dp);
-    if ((mis & 15) == 0) {
+    if ((mis & 15) == 0 && row_bytes <= 256) {
+        // rows of up to 16 chunks: chunk slots padded to a power of two, so (row, chunk) come from a shift and a mask
         const int nch = row_bytes >> 4, tail = row_bytes & 15;
-        for (int i = tid; i < rows * nch; i += nt) {
-            const int ry = i / nch, ch = i - ry * nch;
+        const int sl = nch <= 2 ? 1 : nch <= 4 ? 2 : nch <= 8 ? 3 : 4;
+        for (int i = tid; i < (rows << sl); i += nt) {
+            const int ry = i >> sl, ch = i & ((1 << sl) - 1);
+            if (ch >= nch) continue;
             const uint32_t* q = reinterpret_cast<const uint32_t*>(s + ry * ss + 16 * ch);
             *reinterpret_cast<uint4*>(d + (size_t)ry * dp + 16 * ch) = make_uint4(q[0], q[1], q[2], q[3]);
         }
-        for (int i = tid; i < rows * tail; i += nt) {
+        if (tail) for (int i = tid; i < rows * tail; i += nt) {
             const int ry = i / tail, b = (nch << 4) + i - ry * tail;
             d[(size_t)ry * dp + b] = s[ry * ss + b];
         }
