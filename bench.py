@@ -431,6 +431,10 @@ def request_latency(cx: Ctx, name: str):
         ts = sorted(ts[skip:])
         return {"p50": ts[len(ts) // 2], "min": ts[0], "max": ts[-1], "n": len(ts)}
     warm = timed(lambda k: plan.run_host(frames[k % 4], out), 40, 8)
+    torch = cx.torch
+    pin = [torch.from_numpy(f).pin_memory() for f in frames]
+    pout = torch.empty((plan.out_h, plan.out_w, plan.out_c), dtype=torch.uint8).pin_memory()
+    warm_pinned = timed(lambda k: plan.run_host(pin[k % 4].numpy(), pout.numpy()), 40, 8)
     ops = api.OpsLayer(L)
     kw = dict(crop=rq.get("crop"), resize=rq.get("resize"), filters=rq.get("filters", []), simple=bool(rq.get("simple")))
     def seq(k, rq_kw):
@@ -445,7 +449,7 @@ def request_latency(cx: Ctx, name: str):
     cold_t = timed(cold, 12, 2)
     plan.close()
     return {"what": "pageable host frame in, host frame out, one request at a time (ms)",
-            "run_host_warm_plan": warm, "ops_sequence_repeat": repeat, "ops_sequence_cold_geometry": cold_t,
+            "run_host_warm_plan": warm, "run_host_warm_plan_pinned_frames": warm_pinned, "ops_sequence_repeat": repeat, "ops_sequence_cold_geometry": cold_t,
             "cold_over_repeat": cold_t["p50"] / repeat["p50"]}
 
 

@@ -183,6 +183,8 @@ int  imp_gpu_batch_wait(imp_gpu_ticket* ticket);
  * initialised on demand. imp_gpu_farm_run_host is round-robin (job i -> GPU i mod n_gpus). */
 #define IMP_FARM_ROUND_ROBIN 0
 #define IMP_FARM_SIZE_AWARE  1   /* largest job first onto the GPU with the fewest algorithmic bytes so far (mixed sizes) */
+/* The assignment itself (pure host logic, needs no device): owner[i] = the GPU job i runs on under `policy`. */
+int  imp_gpu_farm_assign(int n, imp_gpu_plan* const* plans, int n_gpus, int policy, int* owner);
 int  imp_gpu_farm_run_host(int n, imp_gpu_plan* const* plans, const unsigned char* const* srcs,
                            const int* src_steps, unsigned char* const* dsts, const int* dst_steps,
                            int n_gpus, int n_streams);

@@ -332,6 +332,16 @@ class HostJobs:
         lib.check(lib.lib.imp_gpu_batch_wait(ticket))
 
 
+def farm_assign(lib: Library, plans: List[Plan], n_gpus: int, policy=FARM_ROUND_ROBIN) -> List[int]:
+    """imp_gpu_farm_assign: the GPU each job would run on (host logic only; works without a device)."""
+    n = len(plans)
+    P = (C.c_void_p * max(n, 1))(*[p.h for p in plans])
+    owner = (C.c_int * max(n, 1))()
+    lib.lib.imp_gpu_farm_assign.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.check(lib.lib.imp_gpu_farm_assign(n, P, n_gpus, policy, owner))
+    return list(owner[:n])
+
+
 def run_host_batch(lib: Library, plans: List[Plan], srcs: List[np.ndarray], dsts: List[np.ndarray], n_streams=4, n_gpus=0, policy=FARM_ROUND_ROBIN):
     """imp_gpu_batch_run_host / imp_gpu_farm_run_host[_policy] over numpy (or pinned) buffers."""
     HostJobs(plans, srcs, dsts).run(lib, n_streams, n_gpus, policy)

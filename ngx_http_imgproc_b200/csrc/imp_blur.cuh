@@ -32,7 +32,7 @@ __device__ unsigned g_imp_dbg_flags;
 #endif
 
 template <int SC, int R>
-__global__ void __launch_bounds__(BLUR_THREADS, 3)
+__global__ void __launch_bounds__(BLUR_THREADS, 4)
 imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one) {
     using D = ImpBlurDims<R>;
     constexpr int SPANX = D::SPANX, SPANY = D::SPANY, NWH = D::NWH, NWIN = D::NWIN, PWW = D::PWW;

@@ -1024,6 +1024,27 @@ int imp_gpu_batch_wait(imp_gpu_ticket* ticket) {
     return rc;
 }
 
+// Which GPU runs which job (pure host logic: no device is touched). Round-robin: job i -> GPU i mod n_gpus. Size-aware:
+// largest job first onto the GPU with the least algorithmic bytes so far (ties: lowest GPU index; equal sizes keep
+// request order), the assignment SURVEY 8e asks for on mixed-size farms.
+int imp_gpu_farm_assign(int n, imp_gpu_plan* const* plans, int n_gpus, int policy, int* owner) {
+    if (n < 0 || n_gpus <= 0 || !owner || (n > 0 && !plans)) return IMP_ERROR_INVALID_ARGS;
+    if (policy != IMP_FARM_ROUND_ROBIN && policy != IMP_FARM_SIZE_AWARE) return IMP_ERROR_INVALID_ARGS;
+    try {
+        if (policy == IMP_FARM_ROUND_ROBIN) { for (int i = 0; i < n; i++) owner[i] = i % n_gpus; return IMP_OK; }
+        std::vector<int> order(n);
+        for (int i = 0; i < n; i++) { if (!plans[i]) return IMP_ERROR_INVALID_ARGS; order[i] = i; }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return plans[a]->algo_bytes > plans[b]->algo_bytes; });
+        std::vector<unsigned long long> load(n_gpus, 0);
+        for (int i : order) {
+            int g = 0;
+            for (int k = 1; k < n_gpus; k++) if (load[k] < load[g]) g = k;
+            load[g] += plans[i]->algo_bytes; owner[i] = g;
+        }
+    } catch (const std::bad_alloc&) { return IMP_ERROR_MALLOC_FAILED; }
+    return IMP_OK;
+}
+
 // Independent frames over the GPUs of one box, one host thread per GPU, no inter-GPU traffic.
 // IMP_FARM_ROUND_ROBIN: job i -> GPU i mod n_gpus. IMP_FARM_SIZE_AWARE: largest job first onto the GPU with the least
 // algorithmic bytes so far (mixed-size farms: evens out the bytes per GPU).
@@ -1036,20 +1057,10 @@ int imp_gpu_farm_run_host_policy(int n, imp_gpu_plan* const* plans, const unsign
     if (n_gpus > avail || n_gpus > MAX_DEV) return fail_msg("imp_gpu_farm_run_host: more GPUs requested than present");
     std::vector<std::vector<int>> share(n_gpus);
     try {
-        if (policy == IMP_FARM_SIZE_AWARE) {
-            std::vector<int> order(n);
-            for (int i = 0; i < n; i++) { if (!plans[i]) return IMP_ERROR_INVALID_ARGS; order[i] = i; }
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return plans[a]->algo_bytes > plans[b]->algo_bytes; });
-            std::vector<unsigned long long> load(n_gpus, 0);
-            for (int i : order) {
-                int g = 0;
-                for (int k = 1; k < n_gpus; k++) if (load[k] < load[g]) g = k;
-                load[g] += plans[i]->algo_bytes; share[g].push_back(i);
-            }
-            for (auto& s : share) std::sort(s.begin(), s.end());           // each GPU walks its jobs in request order
-        } else {
-            for (int i = 0; i < n; i++) share[i % n_gpus].push_back(i);
-        }
+        std::vector<int> owner(std::max(n, 1));
+        int rc = imp_gpu_farm_assign(n, plans, n_gpus, policy, owner.data());
+        if (rc) return rc;
+        for (int i = 0; i < n; i++) share[owner[i]].push_back(i);          // each GPU walks its jobs in request order
     } catch (const std::bad_alloc&) { return IMP_ERROR_MALLOC_FAILED; }
     std::vector<int> rcs(n_gpus, IMP_OK);
     std::vector<std::string> errs(n_gpus);

@@ -293,12 +293,25 @@ struct Lower {
         if (!fuse_mode) return;
         ImpOp o{}; o.kind = fuse_mode == 2 ? IMP_OP_MAXLUT3 : IMP_OP_LUT3;
         o.i[1] = fuse_alpha ? 1 : 0;
-        if (!dry) o.i[0] = add_lut(&fuse_tab[0][0], fuse_alpha ? 1024 : 768);
         fuse_mode = 0;
+        reserve_op();
+        if (!dry) o.i[0] = add_lut(&fuse_tab[0][0], fuse_alpha ? 1024 : 768);
         ops.push_back(o);
     }
     // every op that is not channel-separable closes the running table first
-    void push(const ImpOp& o) { fuse_flush(); ops.push_back(o); }
+    void push(const ImpOp& o) { fuse_flush(); reserve_op(); ops.push_back(o); }
+    // The reference takes as many filters as imgproc_max_filters_count allows (bridge.c:360-363). A pass holds IMP_MAX_OPS ops
+    // and ~30 KB of tables (shared memory of the kernels): when the next op would not fit, the running pass is stored in base
+    // orientation and an index-map pass continues the chain — same pixels, one more round trip through the L2-resident scratch.
+    void reserve_op() {
+        if ((int)ops.size() < IMP_MAX_OPS && luts.size() <= 30 * 1024) return;
+        ImpFrameMap ident{0, 0, 0, hdr.bw, hdr.bh};
+        const int bw = hdr.bw, bh = hdr.bh, oc = hdr.oc;
+        if (hdr.kind == IMP_G_COPY && !dry) copy_tables();
+        end_pass(ident, bw, bh);
+        begin_pass(IMP_G_COPY, bw, bh, oc);
+        hdr.oc = oc; hdr.sx0 = hdr.sy0 = 0; hdr.sw = hdr.bw = bw; hdr.sh = hdr.bh = bh;
+    }
 
     void begin_pass(int kind, int in_w_, int in_h_, int in_c_) {
         memset(&hdr, 0, sizeof hdr);
@@ -519,7 +532,7 @@ int lower_filter(Lower& L, const char* request, int allow) {
                     }
                 }
             }
-            ImpOp o{}; o.kind = IMP_OP_GRADMAP; L.fuse_flush(); o.i[0] = L.add_lut(lut, 768); L.ops.push_back(o);
+            ImpOp o{}; o.kind = IMP_OP_GRADMAP; L.fuse_flush(); L.reserve_op(); o.i[0] = L.add_lut(lut, 768); L.ops.push_back(o);
             return IMP_OK;
         }
         case 8: {   // vignette filters.c:295-323; centre/maxr from helpers.c:46-66
@@ -825,7 +838,6 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
     for (int i = 0; i < req->filter_count; i++) {
         int code = lower_filter(L, req->filters[i] ? req->filters[i] : "", cfg ? cfg->allow_experiments : 0);
         if (code) return code;
-        if ((int)L.ops.size() + (L.fuse_mode ? 1 : 0) > IMP_MAX_OPS) return IMP_ERROR_TOO_MUCH_FILTERS;
     }
 
     // a pass 0 that stayed a plain index map (crop / no resize) streams through the strip kernel as well
@@ -864,7 +876,6 @@ int imp_build_plan(const imp_gpu_request* req, const imp_gpu_config* cfg, int w,
     // flatten (bridge.c:642-656)
     if (req->flatten && L.fr.c == 4) { ImpOp o{}; o.kind = IMP_OP_PAPER; L.push(o); }
     L.fuse_flush();
-    if ((int)L.ops.size() > IMP_MAX_OPS) return IMP_ERROR_TOO_MUCH_FILTERS;
 
     *step = IMP_STEP_ENCODE;
     // encoder-side pixel prep (advancedio.c:65-101 IplToFI32 / IplToFI24): FreeImage bitmaps are bottom-up, 32-bit ones

@@ -511,3 +511,20 @@ def test_reference_runjob_with_the_gpu_path_dropped_in(gpu, orc):
             assert len(raw) > 12 and orc.RefGpu.last_raw == raw, q
         checked += 1
     assert checked > 150
+
+
+def test_long_filter_lists_split_into_passes(gpu, orc):
+    """More ops than one pass holds (48) or more tables than its shared memory takes: the chain continues in an index-map
+    pass (gather tile kernel over the L2-resident scratch) instead of failing with TOO_MUCH_FILTERS."""
+    img = smooth_image(4, 140, 256, 4)
+    kw = dict(allow_experiments=True, max_filters=200, max_w=0, max_h=0)
+    chains = [["modulate=10,90,100", "rainbow=pale"] * 30,
+              ["gotham=1"] * 20 + ["rotate=90"] + ["kelvin=1"] * 15 + ["scanline=0.5,0.25,1,1"] * 20,
+              ["blur=1"] + ["lomo=1", "gamma=1.1", "vignette=0.6"] * 25 + ["blur=0.5"],
+              ["gradmap=306090,eecc00", "gamma=1.1"] * 45]
+    for f in chains:
+        for rq in (dict(resize="130,70", filters=f), dict(filters=f, flatten=True)):
+            code, _, out = _gpu_run(gpu, img, kw, rq)
+            c2, _, ref = _oracle(orc, img, rq, kw)
+            assert code == c2 == 0, (code, c2, gpu.last_error())
+            _assert_same(out, ref, f[:3], _has_vignette(rq))

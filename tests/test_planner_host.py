@@ -84,6 +84,45 @@ def test_watermark_off_image_is_invalid_args(hostsim, orc):
     assert _oracle(orc, img, {}, kw)[:2] == (50, 6)
 
 
+def test_long_filter_lists_split_into_passes_and_validate_mode_agrees(hostsim, orc):
+    """the reference takes as many filters as imgproc_max_filters_count allows; a pass holds 48 ops, so a longer
+    chain continues in an index-map pass instead of failing with 55. Channel-separable runs (gotham's colorize + gamma +
+    contrast, a sepia's modulate(s=0) + colorize) are one fused table op each. The validate-only mode of the planner (what
+    every recorded operator of the imp_ops layer runs) returns the same code and geometry as the full lowering."""
+    import ctypes as C
+    img = smooth_image(4, 40, 56, 4)
+    kw = dict(allow_experiments=True, max_filters=200, max_w=0, max_h=0)
+    chains = [["modulate=10,90,100", "rainbow=pale"] * 30,                              # 60 ops that cannot fuse: two passes
+              ["gotham=1"] * 20 + ["rotate=90"] + ["kelvin=1"] * 15 + ["scanline=0.5,0.25,1,1"] * 20,
+              ["blur=1"] + ["lomo=1", "gamma=1.1", "vignette=0.6"] * 25 + ["blur=0.5"],
+              ["gradmap=306090,eecc00", "gamma=1.1"] * 45]                              # 45 tables: the table area splits it too
+    for f in chains:
+        rq = dict(resize="30,20", filters=f)
+        code, step, out, info = hostsim.run(img, api.Config(**kw), want_info=True, **rq)
+        c2, s2, ref = _oracle(orc, img, rq, kw)
+        assert code == c2 == 0
+        tol = 1 if any("vignette" in x for x in f) else 0
+        assert np.abs(out.astype(int) - ref.astype(int)).max() <= tol
+    assert hostsim.run(img, api.Config(**kw), want_info=True, filters=chains[0])[3]["passes"] == 2
+    one = hostsim.run(img, api.Config(**kw), want_info=True, filters=["gotham=1", "modulate=0,0,100", "colorize=704214,0.6", "contrast=1.2"])[3]
+    assert one["passes"] == 1
+    # validate-only mode == full mode on the whole request matrix's codes and geometry
+    hostsim.lib.hostsim_plan_validate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    n = 0
+    for rq in REQS + [dict(filters=c) for c in chains]:
+        for shape in [(60, 80, 3), (33, 47, 1), (45, 64, 4)]:
+            cfg = api.Config(**(kw if "filters" in rq and len(rq["filters"]) > 8 else dict(allow_experiments=True, max_filters=8)))
+            ccfg, k1 = cfg.to_c(); creq, k2 = api.make_request(**rq)
+            step, out3 = C.c_int(-1), (C.c_int * 3)()
+            rc = hostsim.lib.hostsim_plan_validate(C.byref(creq), C.byref(ccfg), shape[1], shape[0], shape[2], C.byref(step), out3)
+            full = hostsim.run(np.zeros(shape, np.uint8), cfg, **rq)
+            assert rc == full[0] and (rc == 0 or step.value == full[1]), (rq, shape, rc, full[:2])
+            if rc == 0:
+                assert tuple(out3) == (full[2].shape[1], full[2].shape[0], full[2].shape[2]), (rq, shape)
+            n += 1
+    assert n > 90
+
+
 def test_plan_structure_and_algorithmic_bytes(hostsim):
     """One pass unless a blur splits the chain; SURVEY §8d byte counts for the five BASELINE configs."""
     img = np.zeros((108, 192, 3), np.uint8)
