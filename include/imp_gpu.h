@@ -110,6 +110,11 @@ int  imp_gpu_device_count(void);
 /* Selects which initialised device subsequent calls from THIS thread use. */
 int  imp_gpu_set_device(int device);
 const char* imp_gpu_last_error(void);          /* thread-local text of the last IMP_ERROR_GPU */
+/* Diagnostics: bounds assertions violated by the tile kernels on the current device since start-up, as a bit set. Always 0
+ * for the release build; the debug build (python -m ngx_http_imgproc_b200.build --debug -> libimp_gpu_dbg.so, compiled
+ * with -DIMP_DEBUG_BOUNDS) checks every staged-tile, lookup, out-stage and destination address the tile kernels form —
+ * the stand-in for compute-sanitizer, which the GPU pool does not offer. Synchronises the device. */
+unsigned imp_gpu_debug_flags(void);
 /* Pixel-stage kernels launched by this library since process start (all devices). The host paths' window
  * re-pitch copy (short rows travel as one linear H2D copy and are laid out on the device) is not counted. */
 unsigned long long imp_gpu_launch_count(void);

@@ -7,7 +7,9 @@
  * reference does) and fix up the IplImage header (width/height/nChannels/widthStep/imageSize) so the next
  * operator sees the geometry it expects. imp_Flush() then runs everything recorded for that frame as ONE
  * fused GPU plan (one H2D of the crop window, one kernel unless a blur splits the chain, one D2H) and
- * replaces the frame. INTEGRATION.md shows the exact edits to bridge.c.
+ * replaces the frame. ngx_http_imgproc_b200/dropin/imp_dropin.c wraps these under the reference's exact names and
+ * prototypes (Crop, Resize(…, Config*, …), the 14 filter callbacks, Watermark, BlendWithPaper) for a module that is
+ * compiled against its own required.h; INTEGRATION.md shows what changes in bridge.c / filters.c (call sites: nothing).
  *
  *   reference (file:line)                                replacement
  *   int Crop(IplImage**, char*, char*)       bridge.c:18   imp_Crop

@@ -50,8 +50,15 @@ def stale() -> bool:
     return _newer(LIB, [d for s in SOURCES for d in _deps(s)])
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """One object per source (compiled in parallel, only when its source or a header changed), then one link."""
+LIB_DBG = os.path.join(HERE, "libimp_gpu_dbg.so")
+
+
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """One object per source (compiled in parallel, only when its source or a header changed), then one link.
+    debug=True: the same sources with -DIMP_DEBUG_BOUNDS (imp_tiles.cuh) -> libimp_gpu_dbg.so, for the bounds-check test."""
+    global OBJ
+    if debug:
+        return _build_debug(force)
     if not force and not stale():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
@@ -74,6 +81,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def _build_debug(force: bool) -> str:
+    deps = [d for s in SOURCES for d in _deps(s)]
+    if not force and not _newer(LIB_DBG, deps):
+        return LIB_DBG
+    obj = os.path.join(HERE, "build", "dbg")
+    os.makedirs(obj, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    procs = []
+    for s in srcs:
+        o = os.path.join(obj, os.path.splitext(s)[0] + ".o")
+        procs.append((s, o, subprocess.Popen([nvcc()] + COMPILE_FLAGS + ["-DIMP_DEBUG_BOUNDS", "-c", "-o", o, os.path.join(CSRC, s)],
+                                             cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for s, o, pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc (debug) failed on {s}:\n" + out + err)
+    link = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-o", LIB_DBG] + [o for _, o, _ in procs]
+    res = subprocess.run(link, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link (debug) failed:\n" + res.stdout + res.stderr)
+    return LIB_DBG
+
+
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

@@ -24,12 +24,6 @@ namespace imp_tiles {
 constexpr int BTW = IMP_BLUR_TW, BTH = IMP_BLUR_TH;         // base-frame tile (imp_plan.h)
 constexpr int BLUR_THREADS = 256;
 
-#if defined(IMP_DEBUG_BOUNDS)
-__device__ unsigned g_imp_dbg_flags;
-#define IMP_DBG(cond, bit) do { if (!(cond)) atomicOr(&g_imp_dbg_flags, 1u << (bit)); } while (0)
-#else
-#define IMP_DBG(cond, bit) do { } while (0)
-#endif
 
 template <int SC, int R>
 __global__ void __launch_bounds__(BLUR_THREADS, 4)

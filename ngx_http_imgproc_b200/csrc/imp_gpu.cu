@@ -817,6 +817,11 @@ void imp_gpu_shutdown(void) {
 }
 
 const char* imp_gpu_last_error(void) { return t_err; }
+unsigned imp_gpu_debug_flags(void) {
+    if (bind() != IMP_OK) return 0;
+    cudaDeviceSynchronize();
+    return imp_debug_flags_strip() | imp_debug_flags_blur() | imp_debug_flags_cubic() | imp_debug_flags_gather();
+}
 unsigned long long imp_gpu_launch_count(void) { return imp_launches(); }
 
 // ---- overlays -------------------------------------------------------------------------------------------

@@ -82,6 +82,7 @@ cudaError_t imp_upload_tables_strip();
 cudaError_t imp_upload_tables_blur();
 cudaError_t imp_upload_tables_cubic();
 cudaError_t imp_upload_tables_gather();
+unsigned imp_debug_flags_strip(); unsigned imp_debug_flags_blur(); unsigned imp_debug_flags_cubic(); unsigned imp_debug_flags_gather();
 cudaError_t imp_launch_strip(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st);        // imp_k_strip.cu
 cudaError_t imp_launch_blur_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st);    // imp_k_blur.cu
 cudaError_t imp_launch_cubic_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st);   // imp_k_cubic.cu

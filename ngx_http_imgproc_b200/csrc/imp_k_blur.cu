@@ -4,6 +4,7 @@
 #include "imp_blur.cuh"
 
 cudaError_t imp_upload_tables_blur() { return imp_upload_tables_tu(); }
+unsigned imp_debug_flags_blur() { return imp_debug_flags_tu(); }
 
 template <int SC, int R>
 static cudaError_t launch_blur_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {

@@ -4,6 +4,7 @@
 #include "imp_cubic.cuh"
 
 cudaError_t imp_upload_tables_cubic() { return imp_upload_tables_tu(); }
+unsigned imp_debug_flags_cubic() { return imp_debug_flags_tu(); }
 
 template <int SC>
 static cudaError_t launch_cubic_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {

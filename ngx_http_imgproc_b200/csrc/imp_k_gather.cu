@@ -4,6 +4,7 @@
 #include "imp_gathertile.cuh"
 
 cudaError_t imp_upload_tables_gather() { return imp_upload_tables_tu(); }
+unsigned imp_debug_flags_gather() { return imp_debug_flags_tu(); }
 
 template <int SC, int KIND>
 static cudaError_t launch_gather_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {

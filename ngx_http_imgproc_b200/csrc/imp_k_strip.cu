@@ -4,6 +4,7 @@
 #include "imp_tiles.cuh"
 
 cudaError_t imp_upload_tables_strip() { return imp_upload_tables_tu(); }
+unsigned imp_debug_flags_strip() { return imp_debug_flags_tu(); }
 
 template <int SC, int MODE>
 static cudaError_t launch_strip(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {

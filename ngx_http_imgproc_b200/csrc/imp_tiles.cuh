@@ -8,6 +8,20 @@
 #pragma once
 #include "imp_gather.cuh"
 
+// ---- debug build (-DIMP_DEBUG_BOUNDS; ngx_http_imgproc_b200/build.py --debug -> libimp_gpu_dbg.so) -----------------------
+// compute-sanitizer is not available on the GPU pool, so the tile kernels carry their own bounds assertions on every
+// staged-tile, lookup-table, out-stage and destination address they form; a violated one sets a bit that
+// imp_gpu_debug_flags() reads back (tests/test_gpu_host_path.py runs the request fuzz over the debug build). Bits:
+// 0-1 blur (border fill, out stage), 2-3 cubic, 4-6 gather tile, 8-11 strip kernels (tile reads, taps, destination).
+#if defined(IMP_DEBUG_BOUNDS)
+static __device__ unsigned g_imp_dbg_flags;
+#define IMP_DBG(cond, bit) do { if (!(cond)) atomicOr(&g_imp_dbg_flags, 1u << (bit)); } while (0)
+static inline unsigned imp_debug_flags_tu() { unsigned v = 0; cudaMemcpyFromSymbol(&v, g_imp_dbg_flags, sizeof v); return v; }
+#else
+#define IMP_DBG(cond, bit) do { } while (0)
+static inline unsigned imp_debug_flags_tu() { return 0; }
+#endif
+
 namespace imp_tiles {
 
 // ---- PTX: mbarrier + 1-D bulk async copy (TMA, SASS UBLKCP) ---------------------------------------------
@@ -183,7 +197,7 @@ __device__ __forceinline__ void fence_generic_to_async_smem() {
 // The destination address of base pixel (bx, by) is affine in by for a fixed bx under all eight output orientations
 // (dst + Y*pitch + X*dc with (X,Y) = imp_map_xy): a thread of a strip owns one bx, so it keeps {address of (bx,0), step
 // per by} instead of re-evaluating the frame map from the pass header for every pixel.
-struct StripStore { uint8_t* base; int step; };
+struct StripStore { uint8_t* base; int step; int rows; };
 __device__ __forceinline__ StripStore strip_store_line(const ImpFrameMap& om, uint8_t* dst, int pitch, int dc, int bx) {
     int X0, Y0, X1, Y1;
     imp_map_xy(om, bx, 0, X0, Y0);
@@ -191,6 +205,7 @@ __device__ __forceinline__ StripStore strip_store_line(const ImpFrameMap& om, ui
     StripStore s;
     s.base = dst + (ptrdiff_t)Y0 * pitch + (ptrdiff_t)X0 * dc;
     s.step = (Y1 - Y0) * pitch + (X1 - X0) * dc;
+    s.rows = om.h;
     return s;
 }
 
@@ -223,6 +238,7 @@ __device__ __forceinline__ void strip_epilogue(const ImpJob& job, int oc, int dc
     else { p.b = v[0]; p.g = v[SC > 1 ? 1 : 0]; p.r = v[SC > 2 ? 2 : 0]; p.a = (SC == 4) ? v[SC - 1] : 255; }
     if (by >= orows.y0 && by <= orows.y1) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
     uint8_t* d = st.base + (ptrdiff_t)by * st.step;
+    IMP_DBG(d >= job.dst && d + dc <= job.dst + (size_t)st.rows * job.dst_pitch, 11);
     if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
     else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
 }
@@ -267,6 +283,9 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
         int v[SC];
         if (MODE == 0) {
             float sum[SC];
+            // rows [yrow.x/rs, +yrow.y) of the box, NT taps (the zero-weight padded ones included, +4 for the aligned word loads)
+            IMP_DBG(my_off >= 0 && yrow.x >= 0 && yrow.x + (yrow.y - 1) * rs + my_off + NT * SC + (SC == 4 ? 0 : 4) <= box_bytes + (SC == 4 ? 0 : 4) && my_off + NT * SC <= rs + 4, 8);
+            IMP_DBG(yrow.z >= 0 && (yrow.z + yrow.y) * 8 <= ytap_bytes, 9);
             area_rows<SC, (MODE == 0 ? NT : 1)>(sbase + my_off + yrow.x, rs, s_yt + yrow.z, yrow.y, a, na, sum);
 #pragma unroll
             for (int c = 0; c < SC; c++) v[c] = min(rint_pos(sum[c]), 255);          // sums are >= 0
@@ -304,6 +323,7 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
         const bool in_y = t * TH + warp < bh;
         mbar_wait(full + stage, phase);
         int v[SC];
+        IMP_DBG(my_off >= 0 && my_off + NT * SC <= rs + 4 && (by * ny - t * TH * ny) >= 0 && (by * ny - t * TH * ny + ny) <= P->tile_rows, 8);
         area_int_rows<SC, NT>(tile0 + (stage * stage_bytes + my_off + (by * ny - t * TH * ny) * rs), rs, ny, v);
 #pragma unroll
         for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
@@ -355,6 +375,7 @@ __device__ __forceinline__ void gather_strip_consume(const ImpJob& job, const Im
         mbar_wait(full + stage, phase);
         const uint8_t* sbase = tile0 + stage * stage_bytes;
         int v[SC];
+        IMP_DBG(r0 >= 0 && r0 < P->tile_rows && xo0 >= 0 && xo0 + SC <= rs && (MODE != 3 || (r1 >= 0 && r1 < P->tile_rows && xo1 >= 0 && xo1 + SC <= rs)), 10);
         if (MODE == 3) {
             const uint8_t* q0 = sbase + r0 * rs; const uint8_t* q1 = sbase + r1 * rs;
             int p00[SC], p01[SC], p10[SC], p11[SC];

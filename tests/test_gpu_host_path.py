@@ -186,3 +186,63 @@ def test_rotated_three_byte_stores_do_not_outrun_the_ring(gpu, orc):
                 ref = _oracle(orc, img, rq, dict(max_w=0, max_h=0))[2]
                 for rep in range(3):
                     _same(gpu.run(img, api.Config(max_w=0, max_h=0), **rq), ref, (shape, rq, rep))
+
+
+def test_bounds_assertions_stay_silent_under_the_fuzz(orc):
+    """compute-sanitizer is closed on the pool, so the tile kernels carry their own bounds assertions
+    (-DIMP_DEBUG_BOUNDS, libimp_gpu_dbg.so built by __graft_entry__.build()): the request matrix, the resize fuzz, odd sizes
+    under all orientations and the BASELINE shapes run over the debug build in a child process; no assertion may fire and
+    the results still equal the oracle's."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dbg = os.path.join(root, "ngx_http_imgproc_b200", "libimp_gpu_dbg.so")
+    if not os.path.exists(dbg):
+        pytest.skip("debug library not built (python -m ngx_http_imgproc_b200.build --debug)")
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import ctypes as C
+import ngx_http_imgproc_b200 as M
+from ngx_http_imgproc_b200 import api
+from oracle import oracle as O
+from conftest import rnd_image, smooth_image
+from test_planner_host import REQS, _oracle
+L = M.library(); L.init(0)
+L.lib.imp_gpu_debug_flags.restype = C.c_uint
+wm = rnd_image(7, 12, 20, 4)
+kw = dict(allow_experiments=True, max_filters=8, max_w=0, max_h=0, watermark=wm, wm_gravity_x="r", wm_gravity_y="b", wm_offset_x=3, wm_offset_y=2, wm_opacity=60)
+n = 0
+def check(img, rq, kwx=kw):
+    global n
+    code, step, p = L.try_plan(img.shape[1], img.shape[0], img.shape[2], api.Config(**kwx), **rq)
+    c2, s2, ref = _oracle(O, img, rq, kwx)
+    assert code == c2, (rq, code, c2)
+    if code: return
+    out = p.run_host(img); p.close()
+    d = np.abs(out.astype(int) - ref.astype(int)).max()
+    assert d <= (1 if any("vignette" in f for f in rq.get("filters", [])) else 0), (rq, int(d))
+    n += 1
+for (h, w, c) in [(60, 80, 3), (45, 64, 4), (33, 47, 1), (97, 33, 3), (131, 259, 4)]:
+    img = smooth_image(h + w, h, w, c)
+    for rq in REQS:
+        check(img, rq)
+orient = [[], ["flip=10"], ["rotate=90"], ["rotate=270"], ["flip=01", "rotate=270"]]
+rng = np.random.default_rng(3)
+for it in range(120):
+    sw, sh, c = int(rng.integers(1, 300)), int(rng.integers(1, 200)), int(rng.choice([1, 3, 4]))
+    dw, dh = int(rng.integers(1, 400)), int(rng.integers(1, 300))
+    img = rnd_image(it, sh, sw, c)
+    fl = orient[it % len(orient)] + (["blur=%.1f" % (0.5 + (it % 7) * 0.6)] if it % 4 == 0 and c > 1 else [])
+    check(img, dict(resize=f"{dw},{dh},up", filters=fl, simple=bool(it % 5 == 0), interp=int(it % 3 == 1)), dict(max_w=0, max_h=0))
+check(smooth_image(1, 1080, 1920, 3), dict(resize="640,360"))
+check(smooth_image(2, 2160, 3840, 4), dict(crop="3600px,2025px,c,c", resize="800,450"))
+check(smooth_image(3, 270, 480, 4), dict(resize="960,540,up", filters=["modulate=0,0,100", "colorize=704214,0.6"]))
+check(smooth_image(4, 750, 1000, 3), dict(filters=["blur=2.3", "vignette=0.8", "rotate=90"]))
+flags = L.lib.imp_gpu_debug_flags()
+print("BOUNDS", n, hex(flags))
+assert flags == 0, hex(flags)
+"""
+    env = dict(os.environ, IMP_GPU_LIB=dbg)
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "BOUNDS" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    assert int(r.stdout.split("BOUNDS")[1].split()[0]) > 300
