@@ -73,7 +73,8 @@ __device__ __forceinline__ void load_bytes(const uint8_t* p, uint32_t (&w)[(NB +
     constexpr int NW = (NB + 3) / 4;
     // plain pointer arithmetic (no integer round trip), so the compiler still knows these are shared-memory loads (LDS,
     // 32-bit addresses) — through uintptr_t they became generic LD.E with 64-bit address maths
-    const unsigned mis = smem_u32(p) & 3u;
+    // the low address bits are the same in the generic and the shared window: no cvta (10 % of the cfg1 kernel's instructions)
+    const unsigned mis = (unsigned)reinterpret_cast<uintptr_t>(p) & 3u;
     const uint32_t* base = reinterpret_cast<const uint32_t*>(p - mis);
     const unsigned sh = mis * 8;
     uint32_t raw[NW + 1];
