@@ -3,7 +3,7 @@
 // shared-memory tile kernels, and can be instantiated on the host for the CPU unit test.
 //
 // Arithmetic follows SURVEY Appendix A (OpenCV's algorithms as the reference's cvResize call,
-// bridge.c:191, executes them); tables are built on the host by imp_tables.cpp with the same double
+// bridge.c:191, executes them); tables are built on the host by imp_planner.cpp with the same double
 // maths OpenCV uses.
 #pragma once
 #include "imp_pixel.cuh"

@@ -14,6 +14,11 @@
 //   C-10 scanline with no argument token          (NULL dereference)
 //   crop/gravity offsets that are negative or a gravity string with fewer than two tokens (OpenCV
 //   assert / strcmp(NULL)); resize to a zero-sized target (cvCreateImage error).
+// Two more differences from "same code at the same step", both on purpose:
+//   * Crop tokenises `gravity` in place (bridge.c:73): frames 2.. of a multi-frame GIF then see a string of <= 2 characters
+//     and fail with INVALID_ARGS at the crop step. Here every frame of a job sees the same string and succeeds.
+//   * no cap on the op count of a pass surfaces as an error: a chain longer than IMP_MAX_OPS (or with more tables than a
+//     pass's shared memory takes) continues in an index-map pass (Lower::reserve_op), as the reference would accept it.
 #include "imp_internal.h"
 #include "imp_pixel.cuh"            // host instantiation of the per-pixel ops: composed LUTs are tabulated with the very code the kernels run
 #include <math.h>

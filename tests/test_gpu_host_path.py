@@ -246,3 +246,45 @@ assert flags == 0, hex(flags)
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "BOUNDS" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
     assert int(r.stdout.split("BOUNDS")[1].split()[0]) > 300
+
+
+def test_workers_forked_before_cuda_init(orc):
+    """nginx forks its workers after the configuration (and the module's shared library) is loaded, and OnEnvStart runs in
+    each worker (module.c:100-107): libimp_gpu.so must tolerate being loaded — but not initialised — before fork(), and
+    every child must be able to create its own CUDA context, serve requests and shut down. (A CUDA context itself can not
+    cross fork(), which is why imp_gpu_init is not called at load time.)"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import os, sys, numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import ngx_http_imgproc_b200 as M
+from ngx_http_imgproc_b200 import api
+from oracle import oracle as O
+from conftest import smooth_image
+L = M.library()                                   # master process: library loaded, plans validated, NO imp_gpu_init
+cfg = api.Config(max_w=0, max_h=0, watermark=smooth_image(9, 8, 12, 4), wm_gravity_x="r", wm_gravity_y="b", wm_opacity=70)
+assert L.try_plan(64, 48, 3, cfg, resize="0,0")[0] == 50
+img = smooth_image(1, 240, 320, 4)
+rq = dict(crop="300px,200px,c,c", resize="150,100", filters=["gamma=1.2"])
+ref = O.run_chain(img, rq["crop"], None, rq["resize"], rq["filters"], O.OracleConfig(max_w=0, max_h=0, watermark=cfg.watermark, wm_gravity_x="r", wm_gravity_y="b", wm_opacity=70))[2]
+pids = []
+for w in range(3):                                # three "worker processes"
+    pid = os.fork()
+    if pid == 0:
+        try:
+            L.init(0)                             # OnEnvStart
+            for k in range(3):
+                out = L.run(img, cfg, **rq)
+                assert np.array_equal(out, ref)
+            L.shutdown()                          # OnEnvDestroy
+            os._exit(0)
+        except BaseException as e:
+            sys.stderr.write("worker %d: %r\n" % (w, e)); os._exit(1)
+    pids.append(pid)
+bad = [os.waitpid(p, 0)[1] for p in pids]
+assert all(os.WIFEXITED(s) and os.WEXITSTATUS(s) == 0 for s in bad), bad
+print("FORK OK")
+"""
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FORK OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
