@@ -17,6 +17,7 @@
 namespace imp_tiles {
 
 constexpr int GATHER_THREADS = 256;
+// (IMP_GATHER_TPC, imp_plan.h: tiles a CTA walks)
 
 // shared-memory words the lookups take: per column and per row {offset 0, offset 1, coefficients}
 __host__ __device__ constexpr int gather_table_words(int T) { return 6 * T; }
@@ -38,12 +39,10 @@ imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, co
     const ImpFrameMap om = P->out;
     const int tsh = T == 64 ? 6 : 5;                                    // T is 64 or 32
     const int tiles_xd = (om.w + T - 1) >> tsh, tiles_yd = (om.h + T - 1) >> tsh;
-    if ((int)blockIdx.x >= tiles_xd * tiles_yd) return;
-    const int X0 = ((int)blockIdx.x % tiles_xd) * T, Y0 = ((int)blockIdx.x / tiles_xd) * T;
-    const int vw = min(T, om.w - X0), vh = min(T, om.h - Y0);           // valid destination rectangle
-    const int ulo = om.flipx ? om.w - X0 - vw : X0, vlo = om.flipy ? om.h - Y0 - vh : Y0;
-    const int x0 = om.swap ? vlo : ulo, y0 = om.swap ? ulo : vlo;       // base-frame origin of the tile
-    const int tw = om.swap ? vh : vw, th = om.swap ? vw : vh;           // base-frame extent of the tile
+    // a CTA walks IMP_GATHER_TPC consecutive tiles: the job / pass / op-list prologue is paid once, and the TMA box of tile
+    // i+1 is in flight while tile i is processed (two boxes, two mbarriers)
+    const int t_begin = (int)blockIdx.x * IMP_GATHER_TPC, t_end = min(t_begin + IMP_GATHER_TPC, tiles_xd * tiles_yd);
+    if (t_begin >= t_end) return;
 
     const int* __restrict__ xofs = reinterpret_cast<const int*>(blob + P->xofs_off);
     const int* __restrict__ yofs = reinterpret_cast<const int*>(blob + P->yofs_off);
@@ -52,30 +51,61 @@ imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, co
     auto xs1 = [&](int bx) { return min(max(__ldg(xofs + bx) + 1, 0), sw - 1); };
     auto ys0 = [&](int by) { return KIND == IMP_G_COPY ? by : KIND == IMP_G_NN ? __ldg(yofs + by) : min(max(__ldg(yofs + by), 0), sh - 1); };
     auto ys1 = [&](int by) { return min(max(__ldg(yofs + by) + 1, 0), sh - 1); };
-    const int sx_first = xs0(x0), sy_first = ys0(y0);                   // the tables are non-decreasing
 
     const int rs = P->tile_rs;
     const int nops = P->nops;
     const int ops_bytes = (nops * (int)sizeof(ImpOp) + P->lut_bytes + 15) & ~15;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const int box_bytes = (rs * P->tile_rows + 127) & ~127;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);                  // [2]
     uint8_t* s_ops = smem + 128;
-    uint8_t* tile = s_ops + ((ops_bytes + 127) & ~127);                 // TMA box
-    int* tab = reinterpret_cast<int*>(tile + ((rs * P->tile_rows + 127) & ~127));
+    uint8_t* box0 = s_ops + ((ops_bytes + 127) & ~127);                 // two TMA boxes
+    int* tab = reinterpret_cast<int*>(box0 + 2 * box_bytes);
     int* cx0 = tab, * cx1 = tab + T, * cxa = tab + 2 * T, * ry0 = tab + 3 * T, * ry1 = tab + 4 * T, * ryb = tab + 5 * T;
     uint8_t* ostage = reinterpret_cast<uint8_t*>(tab + gather_table_words(T));      // T rows of T*3 bytes (3-channel results)
     const int tid = threadIdx.x;
-    const int xbyte = job.tm_x0 + sx_first * SC;
-    const int c0 = (xbyte >> 4) << 1;
-    const int col_off = xbyte - c0 * 8;                                 // tile byte offset of source pixel sx_first
+    const int oc = P->oc, dc = P->dc;
+    const int OS = T * 3;                                               // out-stage row stride (3-channel results)
+    const int qsh = tsh - 2;                                            // log2 of the 4-pixel groups per tile row
+    const bool vec16 = dc == 4 && ((reinterpret_cast<uintptr_t>(job.dst) | (unsigned)job.dst_pitch) & 15) == 0;
+
+    // geometry of tile t: destination rectangle, base-frame origin and extent, first source pixel / row of its box
+    struct Geo { int X0, Y0, vw, vh, x0, y0, tw, th, sx_first, sy_first; };
+    auto geometry = [&](int t) {
+        Geo g;
+        const int ty = t / tiles_xd;
+        g.X0 = (t - ty * tiles_xd) << tsh; g.Y0 = ty << tsh;
+        g.vw = min(T, om.w - g.X0); g.vh = min(T, om.h - g.Y0);         // valid destination rectangle
+        const int ulo = om.flipx ? om.w - g.X0 - g.vw : g.X0, vlo = om.flipy ? om.h - g.Y0 - g.vh : g.Y0;
+        g.x0 = om.swap ? vlo : ulo; g.y0 = om.swap ? ulo : vlo;         // base-frame origin of the tile
+        g.tw = om.swap ? g.vh : g.vw; g.th = om.swap ? g.vw : g.vh;     // base-frame extent of the tile
+        g.sx_first = xs0(g.x0); g.sy_first = ys0(g.y0);                 // the tables are non-decreasing
+        return g;
+    };
+    auto issue = [&](const Geo& g, int buf) {                           // one thread: box of tile g into buffer buf
+        const int xbyte = job.tm_x0 + g.sx_first * SC;
+        mbar_expect_tx(bar + buf, (uint32_t)(rs * P->tile_rows));
+        tma_load_2d(box0 + buf * box_bytes, jp->tmap, (xbyte >> 4) << 1, g.sy_first, bar + buf);
+    };
+    Geo g = geometry(t_begin);
     if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, (uint32_t)(rs * P->tile_rows));
-        tma_load_2d(tile, jp->tmap, c0, sy_first, bar);
+        mbar_init(bar, 1); mbar_init(bar + 1, 1);
+        issue(g, 0);
     }
     {
         const uint4* gsrc = reinterpret_cast<const uint4*>(blob + P->ops_off);
         uint4* sdst = reinterpret_cast<uint4*>(s_ops);
         for (int i = tid; i < ops_bytes / 16; i += GATHER_THREADS) sdst[i] = __ldg(gsrc + i);
+    }
+    for (int t = t_begin, it = 0; t < t_end; t++, it++) {
+    const int buf = it & 1;
+    const uint8_t* tile = box0 + buf * box_bytes;
+    const int X0 = g.X0, Y0 = g.Y0, vw = g.vw, vh = g.vh, x0 = g.x0, y0 = g.y0, tw = g.tw, th = g.th, sx_first = g.sx_first, sy_first = g.sy_first;
+    const int xbyte = job.tm_x0 + sx_first * SC;
+    const int col_off = xbyte - ((xbyte >> 4) << 4);                    // tile byte offset of source pixel sx_first
+    if (it > 0) __syncthreads();                                        // the previous tile's lookups (and its box) are no longer read
+    if (t + 1 < t_end) {
+        g = geometry(t + 1);
+        if (tid == 0) { fence_generic_to_async_smem(); issue(g, buf ^ 1); }     // that buffer was read two tiles ago, behind the barrier above
     }
     // the tile's lookups, resolved once: byte offset of each base column inside a tile row, of each base row inside the tile
     if (tid < tw) {
@@ -98,12 +128,8 @@ imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, co
         IMP_DBG(ry0[i] >= 0 && ry0[i] < rs * P->tile_rows, 5);
     }
     __syncthreads();
-    mbar_wait(bar, 0);
+    mbar_wait(bar + buf, (it >> 1) & 1);
 
-    const int oc = P->oc, dc = P->dc;
-    const int OS = T * 3;                                               // out-stage row stride (3-channel results)
-    const int qsh = tsh - 2;                                            // log2 of the 4-pixel groups per tile row
-    const bool vec16 = dc == 4 && ((reinterpret_cast<uintptr_t>(job.dst) | (unsigned)job.dst_pitch) & 15) == 0;
     for (int item = tid; item < (T << qsh); item += GATHER_THREADS) {
         const int Yl = item >> qsh, Xq = (item & ((1 << qsh) - 1)) * 4;
         if (Yl >= vh || Xq >= vw) continue;
@@ -177,6 +203,7 @@ imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, co
         __syncthreads();
         tile_copy_out(ostage, OS, job.dst + (size_t)Y0 * job.dst_pitch + (size_t)X0 * 3, job.dst_pitch, vw * 3, vh, tid, GATHER_THREADS);
     }
+    }   // tiles of this CTA
 }
 
 }  // namespace imp_tiles

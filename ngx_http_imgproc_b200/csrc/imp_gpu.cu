@@ -430,7 +430,8 @@ int variant_tiles(const ImpPass& h, int variant) {
     if (variant == 1) return (h.bw + 31) / 32;
     if (variant == 2) return ((h.bw + IMP_BLUR_TW - 1) / IMP_BLUR_TW) * ((h.bh + IMP_BLUR_TH - 1) / IMP_BLUR_TH);   // same count in destination space
     if (variant == 3) return ((h.bw + 31) / 32) * ((h.bh + 8 * IMP_CUBIC_RUN - 1) / (8 * IMP_CUBIC_RUN));
-    if (variant == 4 || variant == 5) return ((h.bw + h.gt - 1) / h.gt) * ((h.bh + h.gt - 1) / h.gt);                  // same count in destination space
+    if (variant == 5) return (((h.bw + h.gt - 1) / h.gt) * ((h.bh + h.gt - 1) / h.gt) + IMP_GATHER_TPC - 1) / IMP_GATHER_TPC;     // CTAs: IMP_GATHER_TPC tiles each
+    if (variant == 4) return ((h.bw + h.gt - 1) / h.gt) * ((h.bh + h.gt - 1) / h.gt);                  // same count in destination space
     return pass_tiles(h);
 }
 

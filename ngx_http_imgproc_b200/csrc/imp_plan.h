@@ -109,8 +109,9 @@ inline int imp_cubic_dyn_smem(int sc, int ops_bytes16, int tile_rs, int tile_row
            (dc == 4 ? 0 : T * T * 3) + 64;
 }
 // imp_gathertile.cuh: [bar 128][ops][TMA box][6*T lookup words][T rows of T*3 bytes: out stage of 3-channel results]
+#define IMP_GATHER_TPC 4      // consecutive tiles one CTA walks (two TMA boxes: the next tile's is in flight)
 inline int imp_gather_dyn_smem(int gt, int ops_bytes16, int tile_rs, int tile_rows, int dc) {
-    return 128 + ((ops_bytes16 + 127) & ~127) + ((tile_rs * tile_rows + 127) & ~127) + 6 * gt * 4 + (dc == 4 ? 0 : gt * gt * 3) + 64;
+    return 128 + ((ops_bytes16 + 127) & ~127) + 2 * ((tile_rs * tile_rows + 127) & ~127) + 6 * gt * 4 + (dc == 4 ? 0 : gt * gt * 3) + 64;
 }
 #define IMP_BLUR_TW 32
 #define IMP_BLUR_TH 64
