@@ -595,11 +595,31 @@ int lane_finish(Lane& L, const HostJobs& J) {
     if (L.pend.empty()) return IMP_OK;
     cudaError_t e = cudaStreamSynchronize(L.st);
     if (e == cudaSuccess) {
-        for (const Lane::Out& o : L.pend) {
-            if (o.staged_off < 0) continue;
-            const imp_gpu_plan* p = J.plans[o.job];
-            const size_t row = (size_t)p->out_w * p->out_c;
-            for (int y = 0; y < p->out_h; y++) memcpy(J.dsts[o.job] + (size_t)y * J.dst_steps[o.job], L.h_out.p + o.staged_off + (size_t)y * row, row);
+        // results for pageable destinations (the frames cvCreateImage hands out) leave the pinned staging here; a 200-frame GIF
+        // is 400 MB of it, so chunks of 8 MB and more are split over up to four threads, whole frames each
+        size_t staged = 0;
+        for (const Lane::Out& o : L.pend) if (o.staged_off >= 0) staged += (size_t)J.plans[o.job]->out_w * J.plans[o.job]->out_c * J.plans[o.job]->out_h;
+        const int parts = staged >= (32u << 20) ? 4 : staged >= (8u << 20) ? 2 : 1;
+        const Lane::Out* pend = L.pend.data(); const int np = (int)L.pend.size();
+        const uint8_t* h_out = L.h_out.p;
+        auto unstage = [=, &J](int k0, int k1) {
+            for (int k = k0; k < k1; k++) {
+                const Lane::Out& o = pend[k];
+                if (o.staged_off < 0) continue;
+                const imp_gpu_plan* p = J.plans[o.job];
+                const size_t row = (size_t)p->out_w * p->out_c;
+                for (int y = 0; y < p->out_h; y++) memcpy(J.dsts[o.job] + (size_t)y * J.dst_steps[o.job], h_out + o.staged_off + (size_t)y * row, row);
+            }
+        };
+        if (parts == 1 || np < parts) unstage(0, np);
+        else {
+            std::thread helpers[3];
+            for (int t = 1; t < parts; t++) {
+                const int k0 = (int)((long long)np * t / parts), k1 = (int)((long long)np * (t + 1) / parts);
+                try { helpers[t - 1] = std::thread(unstage, k0, k1); } catch (...) { unstage(k0, k1); }
+            }
+            unstage(0, np / parts);
+            for (int t = 1; t < parts; t++) if (helpers[t - 1].joinable()) helpers[t - 1].join();
         }
     }
     L.pend.clear();
@@ -652,9 +672,27 @@ int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
         uint8_t* d_in = L.d_in.p + l.in_off;
         const uint8_t* win = J.srcs[i] + (size_t)p->win_y * J.src_steps[i] + (size_t)p->win_x * sc;
         if (!l.src_pinned) {
+            // a pageable frame (what cvDecodeImage hands RunJob) goes through the lane's pinned staging, laid out with the
+            // device pitch. One core moves ~10 GB/s, a fifth of the link: windows of 4 MB and more are split over up to four
+            // threads (cfg2's 29 MB window: 2.9 ms -> 0.8 ms before the copy engine even starts)
             uint8_t* h = L.h_in.p + l.hin_off;
-            if ((size_t)J.src_steps[i] == (size_t)l.in_pitch && in_row == (size_t)l.in_pitch) memcpy(h, win, (size_t)l.in_pitch * p->win_h);
-            else for (int y = 0; y < p->win_h; y++) memcpy(h + (size_t)y * l.in_pitch, win + (size_t)y * J.src_steps[i], in_row);
+            const int step = J.src_steps[i], pitch = l.in_pitch;
+            auto stage_rows = [=](int y0, int y1) {
+                if ((size_t)step == (size_t)pitch && in_row == (size_t)pitch) memcpy(h + (size_t)y0 * pitch, win + (size_t)y0 * step, (size_t)pitch * (y1 - y0));
+                else for (int y = y0; y < y1; y++) memcpy(h + (size_t)y * pitch, win + (size_t)y * step, in_row);
+            };
+            const size_t bytes = in_row * p->win_h;
+            const int parts = bytes >= (16u << 20) ? 4 : bytes >= (4u << 20) ? 2 : 1;
+            if (parts == 1) stage_rows(0, p->win_h);
+            else {
+                std::thread helpers[3];
+                for (int t = 1; t < parts; t++) {
+                    const int y0 = (int)((long long)p->win_h * t / parts), y1 = (int)((long long)p->win_h * (t + 1) / parts);
+                    try { helpers[t - 1] = std::thread(stage_rows, y0, y1); } catch (...) { stage_rows(y0, y1); }     // no thread to be had: inline
+                }
+                stage_rows(0, (int)((long long)p->win_h / parts));
+                for (int t = 1; t < parts; t++) if (helpers[t - 1].joinable()) helpers[t - 1].join();
+            }
             CK(cudaMemcpyAsync(d_in, h, (size_t)l.in_pitch * p->win_h, cudaMemcpyHostToDevice, L.st));    // already in the device layout
         } else if (l.linear) {
             const uint8_t* h_lin = J.srcs[i] + (size_t)p->win_y * J.src_steps[i];
