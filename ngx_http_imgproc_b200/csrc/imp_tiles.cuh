@@ -43,6 +43,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// The same on a 32-bit shared-window address: the ring loops convert their barrier arrays ONCE (the generic->shared cvta per
+// poll was 5-9 % of the strip kernels' instructions in the round-2 captures).
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
 // global -> shared, 16-byte aligned on both sides, size a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -273,10 +287,11 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
     const StripStore st = strip_store_line(P->out, job.dst, job.dst_pitch, dc, bx);
     const StripOpsRows orows = strip_ops_rows(s_ops, nops, bx);
     int stage = 0, phase = 0;
+    const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
     for (int t = 0; t < tiles_y; t++) {
         const int by = min(t * TH + warp, bh - 1);
         const bool in_y = t * TH + warp < bh;
-        mbar_wait(full + stage, phase);
+        mbar_wait_a(full_a + stage * 8, phase);
         const uint8_t* sbase = tile0 + stage * stage_bytes;
         const ImpAreaTap* s_yt = reinterpret_cast<const ImpAreaTap*>(sbase + box_bytes);              // the tile's y taps
         // {byte offset of my first source row in the tile, taps, first tap}: one 16-byte load starts the row
@@ -296,7 +311,7 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
             for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
+        if (lane == 0) mbar_arrive_a(empty_a + stage * 8);             // this warp is done with the stage
         if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
@@ -319,17 +334,18 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
     const StripStore st = strip_store_line(P->out, job.dst, job.dst_pitch, dc, bx);
     const StripOpsRows orows = strip_ops_rows(s_ops, nops, bx);
     int stage = 0, phase = 0;
+    const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
     for (int t = 0; t < tiles_y; t++) {
         const int by = min(t * TH + warp, bh - 1);
         const bool in_y = t * TH + warp < bh;
-        mbar_wait(full + stage, phase);
+        mbar_wait_a(full_a + stage * 8, phase);
         int v[SC];
         IMP_DBG(my_off >= 0 && my_off + NT * SC <= rs + 4 && (by * ny - t * TH * ny) >= 0 && (by * ny - t * TH * ny + ny) <= P->tile_rows, 8);
         area_int_rows<SC, NT>(tile0 + (stage * stage_bytes + my_off + (by * ny - t * TH * ny) * rs), rs, ny, v);
 #pragma unroll
         for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
+        if (lane == 0) mbar_arrive_a(empty_a + stage * 8);             // this warp is done with the stage
         if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
@@ -360,6 +376,7 @@ __device__ __forceinline__ void gather_strip_consume(const ImpJob& job, const Im
     const StripStore st = strip_store_line(P->out, job.dst, job.dst_pitch, dc, bx);
     const StripOpsRows orows = strip_ops_rows(s_ops, nops, bx);
     int stage = 0, phase = 0;
+    const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
     for (int t = 0; t < tiles_y; t++) {
         const int by = min(t * TH + warp, bh - 1);
         const bool in_y = t * TH + warp < bh;
@@ -373,7 +390,7 @@ __device__ __forceinline__ void gather_strip_consume(const ImpJob& job, const Im
             const short* yb = reinterpret_cast<const short*>(blob + P->ycoef_off);
             b0 = __ldg(yb + by * 2); b1 = __ldg(yb + by * 2 + 1);
         }
-        mbar_wait(full + stage, phase);
+        mbar_wait_a(full_a + stage * 8, phase);
         const uint8_t* sbase = tile0 + stage * stage_bytes;
         int v[SC];
         IMP_DBG(r0 >= 0 && r0 < P->tile_rows && xo0 >= 0 && xo0 + SC <= rs && (MODE != 3 || (r1 >= 0 && r1 < P->tile_rows && xo1 >= 0 && xo1 + SC <= rs)), 10);
@@ -408,7 +425,7 @@ __device__ __forceinline__ void gather_strip_consume(const ImpJob& job, const Im
         // every lane's loads must have been performed before lane 0 hands the stage back to the TMA producer
         fence_generic_to_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty + stage);                     // this warp is done with the stage
+        if (lane == 0) mbar_arrive_a(empty_a + stage * 8);             // this warp is done with the stage
         if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
