@@ -213,15 +213,21 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
                 bxs[k] = cbx; bys[k] = min(y0 + 8 * g + 4 * half + k, h - 1);
             }
             if (nops) imp_run_ops_n<4>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+            const int ly0 = 8 * g + 4 * half;
+            if (x >= tw || ly0 >= th) continue;                         // outside the tile's valid rectangle (frame edge)
+            const int nk = min(4, th - ly0);                            // 4 except in the last rows of a frame
+            uint8_t* d = ostage + so0 + ly0 * sstep;
+            IMP_DBG(d >= ostage && d + dc <= ostage + OS * THd && d + (nk - 1) * sstep >= ostage && d + (nk - 1) * sstep + dc <= ostage + OS * THd, 1);
+            if (dc == 4) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int ly = 8 * g + 4 * half + k;
-                if (x >= tw || ly >= th) continue;                      // outside the tile's valid rectangle (frame edge)
-                uint8_t* d = ostage + so0 + ly * sstep;
-                IMP_DBG(d >= ostage && d + dc <= ostage + OS * THd, 1);
-                const ImpPx& p = px[k];
-                if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
-                else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
+                for (int k = 0; k < 4; k++) {
+                    if (k < nk) *reinterpret_cast<uchar4*>(d + k * sstep) = make_uchar4((unsigned char)px[k].b, (unsigned char)px[k].g, (unsigned char)px[k].r, (unsigned char)px[k].a);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k < nk) { uint8_t* e = d + k * sstep; e[0] = (unsigned char)px[k].b; e[1] = (unsigned char)px[k].g; e[2] = (unsigned char)px[k].r; }
+                }
             }
         }
     }
