@@ -288,3 +288,33 @@ print("FORK OK")
 """
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "FORK OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_large_frames_and_many_tiny_jobs(gpu):
+    """Maximum-size edge of the path: frames of 100-200 MP through every tile kernel (byte offsets beyond 2^31 in the
+    destination, thousands of tiles per job), checked against size-independent properties (numpy index maps, flat fields),
+    and a 3000-job host batch of tiny mixed shapes (more live plans than the plan cache holds)."""
+    cfg = api.Config(max_w=0, max_h=0, max_filters=8, allow_experiments=True)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (12000, 16000, 3), dtype=np.uint8)
+    assert np.array_equal(gpu.run(img, cfg, filters=["rotate=90"]), np.rot90(img, -1))
+    assert np.array_equal(gpu.run(img, cfg, filters=["flip=11"]), img[::-1, ::-1])
+    assert np.array_equal(gpu.run(img, cfg, crop="15000px,11000px,777px,555px"), img[555:11555, 777:15777])
+    small = np.ascontiguousarray(img[:3000, :4000])
+    assert np.array_equal(gpu.run(small, cfg, resize="8000,6000,up", simple=True), np.repeat(np.repeat(small, 2, 0), 2, 1))
+    del img
+    flat = np.full((12000, 18000, 4), 93, np.uint8)
+    out = gpu.run(flat, cfg, resize="1800,1200")
+    assert out.shape == (1200, 1800, 4) and (out == 93).all()
+    assert (gpu.run(np.ascontiguousarray(flat[:9000, :9000]), cfg, filters=["blur=3"]) == 93).all()
+    out = gpu.run(np.ascontiguousarray(flat[:4000, :6000]), cfg, resize="12000,8000,up")
+    assert out.shape == (8000, 12000, 4) and (out == 93).all()
+    del flat, out
+    imgs = [rng.integers(0, 256, (17 + i % 13, 23 + i % 7, 3 + (i % 2)), dtype=np.uint8) for i in range(3000)]
+    plans = [gpu.plan(im.shape[1], im.shape[0], im.shape[2], cfg, resize="9,7") for im in imgs]
+    dsts = [np.zeros((p.out_h, p.out_w, p.out_c), np.uint8) for p in plans]
+    api.run_host_batch(gpu, plans, imgs, dsts, n_streams=4)
+    for d, p, im in list(zip(dsts, plans, imgs))[::97]:
+        assert np.array_equal(d, p.run_host(im))
+    for p in plans:
+        p.close()
