@@ -130,17 +130,25 @@ imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, co
     __syncthreads();
     mbar_wait(bar + buf, (it >> 1) & 1);
 
+    const int dstep = om.flipx ? -1 : 1, dbx = om.swap ? 0 : dstep, dby = om.swap ? dstep : 0;
     for (int item = tid; item < (T << qsh); item += GATHER_THREADS) {
         const int Yl = item >> qsh, Xq = (item & ((1 << qsh) - 1)) * 4;
         if (Yl >= vh || Xq >= vw) continue;
         ImpPx px[4];
         int bxs[4], bys[4];
+        // base-frame coordinates of the group's first pixel; the next ones are one step along the base x or y axis
+        // (destination x runs along base x, or along base y when the output is transposed; backwards when flipped)
+        int bx0, by0;
+        {
+            const int X = X0 + Xq, Y = Y0 + Yl;
+            const int u = om.flipx ? om.w - 1 - X : X, v = om.flipy ? om.h - 1 - Y : Y;
+            bx0 = om.swap ? v : u; by0 = om.swap ? u : v;
+        }
+        const int kmax = vw - 1 - Xq;                                   // dead slots (k > kmax) compute on the last valid pixel, never stored
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int Xl = min(Xq + k, vw - 1);                         // dead slots compute on a valid pixel, never stored
-            const int X = X0 + Xl, Y = Y0 + Yl;
-            const int u = om.flipx ? om.w - 1 - X : X, v = om.flipy ? om.h - 1 - Y : Y;
-            const int bx = om.swap ? v : u, by = om.swap ? u : v;
+            const int kk = min(k, kmax);
+            const int bx = bx0 + kk * dbx, by = by0 + kk * dby;
             bxs[k] = bx; bys[k] = by;
             const int lx = bx - x0, ly = by - y0;
             IMP_DBG(lx >= 0 && lx < tw && ly >= 0 && ly < th, 6);
