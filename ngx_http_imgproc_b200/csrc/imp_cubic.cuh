@@ -31,8 +31,8 @@ __device__ __forceinline__ int rint_sat_u8(float x) {      // sat_u8(rint(x)), r
     return (int)r;
 }
 
-template <int SC>
-__global__ void __launch_bounds__(CUBIC_THREADS, 3)
+template <int SC, bool LIGHT>
+__global__ void __launch_bounds__(CUBIC_THREADS, LIGHT ? 4 : 3)
 imp_cubic_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int jn = blockIdx.y + blockIdx.z * 65535;
@@ -200,7 +200,7 @@ imp_cubic_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, con
             if (SC == 1) { px[k].b = px[k].g = px[k].r = v4[0]; px[k].a = 255; }
             else { px[k].b = v4[0]; px[k].g = v4[1]; px[k].r = v4[2]; px[k].a = (SC == 4) ? v4[3] : 255; }
         }
-        if (nops) imp_run_ops_n<4>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+        if (nops) imp_run_ops_n<4, LIGHT>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
         uint32_t w[4];
 #pragma unroll
         for (int k = 0; k < 4; k++)         // the low bytes of b, g, r, a: three PRMTs

@@ -22,8 +22,8 @@ constexpr int GATHER_THREADS = 256;
 // shared-memory words the lookups take: per column and per row {offset 0, offset 1, coefficients}
 __host__ __device__ constexpr int gather_table_words(int T) { return 6 * T; }
 
-template <int SC, int KIND>
-__global__ void __launch_bounds__(GATHER_THREADS, 3)
+template <int SC, int KIND, bool LIGHT>
+__global__ void __launch_bounds__(GATHER_THREADS, LIGHT ? 4 : 3)
 imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int jn = blockIdx.y + blockIdx.z * 65535;
@@ -186,7 +186,7 @@ imp_gather_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, co
             if (SC == 1) { px[k].b = px[k].g = px[k].r = v4[0]; px[k].a = 255; }
             else { px[k].b = v4[0]; px[k].g = v4[1]; px[k].r = v4[2]; px[k].a = (SC == 4) ? v4[3] : 255; }
         }
-        if (nops) imp_run_ops_n<4>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+        if (nops) imp_run_ops_n<4, LIGHT>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
         uint32_t w[4];
 #pragma unroll
         for (int k = 0; k < 4; k++)         // the low bytes of b, g, r, a: three PRMTs

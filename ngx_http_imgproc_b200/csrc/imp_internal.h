@@ -69,6 +69,7 @@ struct ImpLaunchGroup {
     int smem_bytes;              // ops + LUT staging (+ source tile for tile variants)
     int variant;                 // 0 = direct-from-global kernel, 1 = shared-memory tile kernel (imp_tiles.cuh)
     int tmax;                    // tile variant: number of ring stages (2..8)
+    int light;                   // gather / cubic tile kernels: the table-ops-only instantiation (ImpPass::light of every job)
 };
 // d_jobs == nullptr: a single job passed by value (`one`), no device job table needed.
 cudaError_t imp_launch_group(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob* one, cudaStream_t st);

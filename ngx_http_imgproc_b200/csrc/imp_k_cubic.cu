@@ -6,11 +6,11 @@
 cudaError_t imp_upload_tables_cubic() { return imp_upload_tables_tu(); }
 unsigned imp_debug_flags_cubic() { return imp_debug_flags_tu(); }
 
-template <int SC>
+template <int SC, bool LIGHT>
 static cudaError_t launch_cubic_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
     static std::atomic<bool> attr_set[16];
     int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_cubic_tile_kernel<SC>;
+    auto kern = imp_tiles::imp_cubic_tile_kernel<SC, LIGHT>;
     if (!attr_set[dev & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
@@ -27,9 +27,9 @@ cudaError_t imp_launch_cubic_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs,
     const ImpJob dummy{};
     const ImpJob& o = one ? *one : dummy;
     switch (g.sc) {
-        case 1: return launch_cubic_tile<1>(g, d_jobs, o, st);
-        case 3: return launch_cubic_tile<3>(g, d_jobs, o, st);
-        case 4: return launch_cubic_tile<4>(g, d_jobs, o, st);
+        case 1: return g.light ? launch_cubic_tile<1, true>(g, d_jobs, o, st) : launch_cubic_tile<1, false>(g, d_jobs, o, st);
+        case 3: return g.light ? launch_cubic_tile<3, true>(g, d_jobs, o, st) : launch_cubic_tile<3, false>(g, d_jobs, o, st);
+        case 4: return g.light ? launch_cubic_tile<4, true>(g, d_jobs, o, st) : launch_cubic_tile<4, false>(g, d_jobs, o, st);
     }
     return cudaErrorInvalidValue;
 }

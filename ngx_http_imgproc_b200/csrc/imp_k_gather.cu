@@ -6,11 +6,11 @@
 cudaError_t imp_upload_tables_gather() { return imp_upload_tables_tu(); }
 unsigned imp_debug_flags_gather() { return imp_debug_flags_tu(); }
 
-template <int SC, int KIND>
+template <int SC, int KIND, bool LIGHT>
 static cudaError_t launch_gather_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
     static std::atomic<bool> attr_set[16];
     int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_gather_tile_kernel<SC, KIND>;
+    auto kern = imp_tiles::imp_gather_tile_kernel<SC, KIND, LIGHT>;
     if (!attr_set[dev & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
@@ -26,9 +26,9 @@ static cudaError_t launch_gather_tile(const ImpLaunchGroup& g, const ImpJob* d_j
 template <int KIND>
 static cudaError_t launch_gather_sc(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
     switch (g.sc) {
-        case 1: return launch_gather_tile<1, KIND>(g, d_jobs, o, st);
-        case 3: return launch_gather_tile<3, KIND>(g, d_jobs, o, st);
-        case 4: return launch_gather_tile<4, KIND>(g, d_jobs, o, st);
+        case 1: return g.light ? launch_gather_tile<1, KIND, true>(g, d_jobs, o, st) : launch_gather_tile<1, KIND, false>(g, d_jobs, o, st);
+        case 3: return g.light ? launch_gather_tile<3, KIND, true>(g, d_jobs, o, st) : launch_gather_tile<3, KIND, false>(g, d_jobs, o, st);
+        case 4: return g.light ? launch_gather_tile<4, KIND, true>(g, d_jobs, o, st) : launch_gather_tile<4, KIND, false>(g, d_jobs, o, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -322,9 +322,26 @@ IMP_HD void imp_op_paper(ImpPx& p) {
 // Runs the op list of a pass on N pixels at base coordinates (bx[n],by[n]): the op loop is the outer one, so an op's
 // parameters and its dispatch are paid once per N pixels and the N bodies are independent instruction streams.
 // lut: the pass's LUT area; wm*: this job's watermark.
-template <int N>
+// LIGHT: the pass holds nothing but fused tables (ImpPass::light): the interpreter then knows only IMP_OP_LUT3 / IMP_OP_MAXLUT3,
+// which keeps the HSV / watermark / vignette code and its registers out of the kernel instantiation.
+template <int N, bool LIGHT = false>
 IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int (&by)[N], const ImpOp* ops, int nops, const uint8_t* lut,
                           const uint8_t* wm, int wm_pitch, int wm_c) {
+    if (LIGHT) {
+        for (int k = 0; k < nops; k++) {
+            const ImpOp& op = ops[k];
+            const uint8_t* t = lut + op.i[0];
+            const bool al = op.i[1] != 0 && oc == 4, mx = op.kind == IMP_OP_MAXLUT3;
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                ImpPx& p = px[n];
+                const int m = imp_max(p.b, imp_max(p.g, p.r));
+                p.b = t[mx ? m : p.b]; p.g = t[256 + (mx ? m : p.g)]; p.r = t[512 + (mx ? m : p.r)];
+                if (al) p.a = t[768 + p.a];
+            }
+        }
+        return;
+    }
     for (int k = 0; k < nops; k++) {
         const ImpOp& op = ops[k];
         switch (op.kind) {

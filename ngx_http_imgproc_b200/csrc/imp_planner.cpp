@@ -343,6 +343,8 @@ struct Lower {
         hdr.lut_bytes = (int)luts.size();
         hdr.out = out;
         hdr.dc = final_dc ? final_dc : hdr.oc;
+        hdr.light = 1;
+        for (const ImpOp& o : ops) if (o.kind != IMP_OP_LUT3 && o.kind != IMP_OP_MAXLUT3) hdr.light = 0;
         bb.b.resize(((bb.b.size() + 15) & ~size_t(15)) + 64, 0);     // tail slack: the strip kernels' 16/64-byte table copies may over-read
         hdr.blob_bytes = (int)bb.b.size();
         memcpy(bb.b.data(), &hdr, sizeof hdr);
