@@ -413,7 +413,9 @@ int tile_stage_bytes(const ImpPass& h) {
 int tile_stages(const ImpPass& h) {
     static const int forced = [] { const char* e = getenv("IMP_GPU_STAGES"); return e ? atoi(e) : 0; }();     // tuning knob
     if (forced >= 2 && forced <= 8) return forced;
-    return std::max(2, std::min(8, (72 * 1024) / tile_stage_bytes(h)));
+    // the table-ops-only instantiation runs four CTAs per SM (56 registers): 54 KB of ring each instead of 72
+    const bool four = h.light && h.kind != IMP_G_AREA_FRAC;
+    return std::max(2, std::min(8, ((four ? 54 : 72) * 1024) / tile_stage_bytes(h)));
 }
 int tile_smem_bytes(const ImpPass& h, int stages) {
     const int ops = (h.nops * (int)sizeof(ImpOp) + h.lut_bytes + 15) & ~15;
@@ -461,7 +463,8 @@ int batch_compile(imp_gpu_batch* b, cudaStream_t up) {
     auto occ_class = [](const ImpPass& h, int variant, int param) {
         if (variant == 4 || variant == 5) return h.light ? 1 : 0;      // these two group by the op-interpreter flavour instead
         if (variant != 1) return 0;
-        return std::max(1, std::min(3, (227 * 1024) / (variant_smem(h, variant, param) + 1024)));
+        const bool four = h.light && h.kind != IMP_G_AREA_FRAC;
+        return std::max(1, std::min(four ? 4 : 3, (227 * 1024) / (variant_smem(h, variant, param) + 1024))) + (h.light ? 8 : 0);
     };
     for (int k = 0; k < max_passes; k++) {
         std::vector<Pending> pend;
@@ -498,7 +501,7 @@ int batch_compile(imp_gpu_batch* b, cudaStream_t up) {
                 st.generic_blur = false;
                 st.g.kind = pend[s].kind; st.g.sc = pend[s].sc; st.g.first = (int)b->h_jobs.size(); st.g.count = (int)(e - s);
                 st.g.max_tiles = 0; st.g.smem_bytes = 16; st.g.variant = pend[s].variant; st.g.tmax = pend[s].tmax;
-                st.g.light = (pend[s].variant == 4 || pend[s].variant == 5) ? pend[s].occ : 0;
+                st.g.light = (pend[s].variant == 4 || pend[s].variant == 5) ? pend[s].occ : (pend[s].variant == 1 ? (pend[s].occ >= 8 ? 1 : 0) : 0);
                 for (size_t j = s; j < e; j++) {
                     st.g.max_tiles = std::max(st.g.max_tiles, variant_tiles(pend[j].hdr, pend[s].variant));
                     st.g.smem_bytes = std::max(st.g.smem_bytes, variant_smem(pend[j].hdr, pend[s].variant, pend[s].tmax));

@@ -246,19 +246,24 @@ __device__ __forceinline__ StripOpsRows strip_ops_rows(const uint8_t* s_ops, int
 
 // Shared epilogue of the strip kernels: op list + store of one pixel. Inlined: an out-of-line call (v[] through
 // local memory + call/return) measured 12-20 % slower on cfg1/cfg2 than the larger code.
-template <int SC>
+template <int SC, bool LIGHT>
 __device__ __forceinline__ void strip_epilogue(const ImpJob& job, int oc, int dc, const StripStore& st, const StripOpsRows& orows, const uint8_t* s_ops, int nops, int bx, int by, const int* v) {
     ImpPx p;
     if (SC == 1) { p.b = p.g = p.r = v[0]; p.a = 255; }
     else { p.b = v[0]; p.g = v[SC > 1 ? 1 : 0]; p.r = v[SC > 2 ? 2 : 0]; p.a = (SC == 4) ? v[SC - 1] : 255; }
-    if (by >= orows.y0 && by <= orows.y1) imp_run_ops(p, oc, bx, by, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+    if (by >= orows.y0 && by <= orows.y1) {
+        ImpPx px[1] = {p};
+        const int xs[1] = {bx}, ys[1] = {by};
+        imp_run_ops_n<1, LIGHT>(px, oc, xs, ys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+        p = px[0];
+    }
     uint8_t* d = st.base + (ptrdiff_t)by * st.step;
     IMP_DBG(d >= job.dst && d + dc <= job.dst + (size_t)st.rows * job.dst_pitch, 11);
     if (dc == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4((unsigned char)p.b, (unsigned char)p.g, (unsigned char)p.r, (unsigned char)p.a);
     else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
 }
 
-template <int SC, int NT, int MODE>
+template <int SC, int NT, int MODE, bool LIGHT>
 __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* __restrict__ blob,
                                                    const uint8_t* tile0, int stage_bytes, uint64_t* full, uint64_t* empty,
                                                    const uint8_t* s_ops, int nops, int bx0, int col_off, int tiles_y, int NSTAGE) {
@@ -312,7 +317,7 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_a(empty_a + stage * 8);             // this warp is done with the stage
-        if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
+        if (in_x && in_y) strip_epilogue<SC, LIGHT>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
@@ -320,7 +325,7 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
 // Integer-scale consumer (INTER_AREA NxM): no tap tables at all — output row y reads source rows y*ny .. y*ny+ny-1 and
 // output column x reads source pixels x*nx .. — and the store map is hoisted (registers are plentiful here).
 // Kept separate from the fractional consumer: sharing one body cost that one 4 % (register allocation).
-template <int SC, int NT>
+template <int SC, int NT, bool LIGHT>
 __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* tile0, int stage_bytes,
                                                        uint64_t* full, uint64_t* empty, const uint8_t* s_ops, int nops, int bx0, int col_off,
                                                        int tiles_y, int NSTAGE) {
@@ -346,7 +351,7 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
         for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
         __syncwarp();
         if (lane == 0) mbar_arrive_a(empty_a + stage * 8);             // this warp is done with the stage
-        if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
+        if (in_x && in_y) strip_epilogue<SC, LIGHT>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
@@ -354,7 +359,7 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
 // Plain-gather consumers of the strip kernel (modes 2 = INTER_NN, 3 = INTER_LINEAR, 4 = index map / crop): the same TMA ring,
 // one output row per warp, but the pixel comes from one (NN, COPY) or 2x2 (LINEAR) staged source pixels. The per-column
 // part of the gather (source offset, x coefficients) is loaded once per strip.
-template <int SC, int MODE>
+template <int SC, int MODE, bool LIGHT>
 __device__ __forceinline__ void gather_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* __restrict__ blob,
                                                      const uint8_t* tile0, int stage_bytes, uint64_t* full, uint64_t* empty,
                                                      const uint8_t* s_ops, int nops, int bx0, int col_off, int tiles_y, int NSTAGE) {
@@ -426,13 +431,15 @@ __device__ __forceinline__ void gather_strip_consume(const ImpJob& job, const Im
         fence_generic_to_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_a(empty_a + stage * 8);             // this warp is done with the stage
-        if (in_x && in_y) strip_epilogue<SC>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
+        if (in_x && in_y) strip_epilogue<SC, LIGHT>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
 
-template <int SC, int MODE>
-__global__ void __launch_bounds__(STRIP_THREADS, 3)
+// LIGHT: the pass has no ops or only fused tables (ImpPass::light — every plain resize): the instantiation without the general
+// op interpreter fits 56 registers, so four CTAs share an SM instead of three.
+template <int SC, int MODE, bool LIGHT>
+__global__ void __launch_bounds__(STRIP_THREADS, (LIGHT && MODE != 0) ? 4 : 3)      // the fractional mode keeps 12 x weights in registers: 72
 imp_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one, const int NSTAGE) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int jn = blockIdx.y + blockIdx.z * 65535;
@@ -506,36 +513,36 @@ imp_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __
     const int col_off = job.tm_x0 - c0 * 8;                           // tile byte offset of source pixel 0
     const int bx0 = blockIdx.x * TW;
     if constexpr (MODE >= 2) {
-        gather_strip_consume<SC, MODE>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE);
+        gather_strip_consume<SC, MODE, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE);
     } else if constexpr (MODE == 0) {
         switch (P->max_xtaps) {                                       // uniform over the pass
-        case 1: area_strip_consume<SC, 1, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 2: area_strip_consume<SC, 2, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 3: area_strip_consume<SC, 3, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 4: area_strip_consume<SC, 4, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 5: area_strip_consume<SC, 5, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 6: area_strip_consume<SC, 6, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 7: area_strip_consume<SC, 7, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 8: area_strip_consume<SC, 8, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 9: area_strip_consume<SC, 9, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 10: area_strip_consume<SC, 10, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 11: area_strip_consume<SC, 11, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        default: area_strip_consume<SC, 12, 0>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 1: area_strip_consume<SC, 1, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 2: area_strip_consume<SC, 2, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 3: area_strip_consume<SC, 3, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 4: area_strip_consume<SC, 4, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 5: area_strip_consume<SC, 5, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 6: area_strip_consume<SC, 6, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 7: area_strip_consume<SC, 7, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 8: area_strip_consume<SC, 8, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 9: area_strip_consume<SC, 9, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 10: area_strip_consume<SC, 10, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 11: area_strip_consume<SC, 11, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        default: area_strip_consume<SC, 12, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
         }
     } else {
         switch (P->nx) {
-        case 1: area_int_strip_consume<SC, 1>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 2: area_int_strip_consume<SC, 2>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 3: area_int_strip_consume<SC, 3>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 4: area_int_strip_consume<SC, 4>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 5: area_int_strip_consume<SC, 5>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 6: area_int_strip_consume<SC, 6>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 7: area_int_strip_consume<SC, 7>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 8: area_int_strip_consume<SC, 8>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 9: area_int_strip_consume<SC, 9>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 10: area_int_strip_consume<SC, 10>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 11: area_int_strip_consume<SC, 11>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        default: area_int_strip_consume<SC, 12>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 1: area_int_strip_consume<SC, 1, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 2: area_int_strip_consume<SC, 2, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 3: area_int_strip_consume<SC, 3, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 4: area_int_strip_consume<SC, 4, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 5: area_int_strip_consume<SC, 5, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 6: area_int_strip_consume<SC, 6, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 7: area_int_strip_consume<SC, 7, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 8: area_int_strip_consume<SC, 8, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 9: area_int_strip_consume<SC, 9, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 10: area_int_strip_consume<SC, 10, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 11: area_int_strip_consume<SC, 11, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        default: area_int_strip_consume<SC, 12, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
         }
     }
 }
