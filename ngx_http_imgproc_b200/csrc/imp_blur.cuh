@@ -25,7 +25,7 @@ constexpr int BTW = IMP_BLUR_TW, BTH = IMP_BLUR_TH;         // base-frame tile (
 constexpr int BLUR_THREADS = 256;
 
 
-template <int SC, int R>
+template <int SC, int R, bool NOCOMP>
 __global__ void __launch_bounds__(BLUR_THREADS, 4)
 imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one) {
     using D = ImpBlurDims<R>;
@@ -212,7 +212,7 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
                 px[k].a = (SC == 4) ? (((half ? hi[SC - 1] : lo[SC - 1]) >> sh8) & 255) : 255;
                 bxs[k] = cbx; bys[k] = min(y0 + 8 * g + 4 * half + k, h - 1);
             }
-            if (nops) imp_run_ops_n<4>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+            if (nops) imp_run_ops_n<4, false, NOCOMP>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
             const int ly0 = 8 * g + 4 * half;
             if (x >= tw || ly0 >= th) continue;                         // outside the tile's valid rectangle (frame edge)
             const int nk = min(4, th - ly0);                            // 4 except in the last rows of a frame

@@ -6,11 +6,11 @@
 cudaError_t imp_upload_tables_blur() { return imp_upload_tables_tu(); }
 unsigned imp_debug_flags_blur() { return imp_debug_flags_tu(); }
 
-template <int SC, int R>
+template <int SC, int R, bool NOCOMP>
 static cudaError_t launch_blur_tile(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
     static std::atomic<bool> attr_set[16];                 // per device; setting the attribute twice is harmless
     int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_blur_tile_kernel<SC, R>;
+    auto kern = imp_tiles::imp_blur_tile_kernel<SC, R, NOCOMP>;
     if (!attr_set[dev & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
@@ -26,10 +26,10 @@ static cudaError_t launch_blur_tile(const ImpLaunchGroup& g, const ImpJob* d_job
 template <int SC>
 static cudaError_t launch_blur_tile_r(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
     switch (g.tmax) {
-        case 3:  return launch_blur_tile<SC, 3>(g, d_jobs, o, st);
-        case 6:  return launch_blur_tile<SC, 6>(g, d_jobs, o, st);
-        case 9:  return launch_blur_tile<SC, 9>(g, d_jobs, o, st);
-        case 12: return launch_blur_tile<SC, 12>(g, d_jobs, o, st);
+        case 3:  return g.light ? launch_blur_tile<SC, 3, true>(g, d_jobs, o, st) : launch_blur_tile<SC, 3, false>(g, d_jobs, o, st);
+        case 6:  return g.light ? launch_blur_tile<SC, 6, true>(g, d_jobs, o, st) : launch_blur_tile<SC, 6, false>(g, d_jobs, o, st);
+        case 9:  return g.light ? launch_blur_tile<SC, 9, true>(g, d_jobs, o, st) : launch_blur_tile<SC, 9, false>(g, d_jobs, o, st);
+        case 12: return g.light ? launch_blur_tile<SC, 12, true>(g, d_jobs, o, st) : launch_blur_tile<SC, 12, false>(g, d_jobs, o, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -324,7 +324,9 @@ IMP_HD void imp_op_paper(ImpPx& p) {
 // lut: the pass's LUT area; wm*: this job's watermark.
 // LIGHT: the pass holds nothing but fused tables (ImpPass::light): the interpreter then knows only IMP_OP_LUT3 / IMP_OP_MAXLUT3,
 // which keeps the HSV / watermark / vignette code and its registers out of the kernel instantiation.
-template <int N, bool LIGHT = false>
+// NOCOMP: the pass holds no compositing op (IMP_OP_WATERMARK / IMP_OP_PAPER; ImpPass::light == 2): the instantiation leaves
+// AlphaBlendOver's float divisions and their registers out.
+template <int N, bool LIGHT = false, bool NOCOMP = false>
 IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int (&by)[N], const ImpOp* ops, int nops, const uint8_t* lut,
                           const uint8_t* wm, int wm_pitch, int wm_c) {
     if (LIGHT) {
@@ -427,6 +429,7 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
                 }
                 break;
             case IMP_OP_WATERMARK:
+                if (NOCOMP) break;
 #pragma unroll
                 for (int n = 0; n < N; n++) {
                     int x, y; imp_map_xy(op.map, bx[n], by[n], x, y);
@@ -459,6 +462,7 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
                 }
             } break;
             case IMP_OP_PAPER:
+                if (NOCOMP) break;
                 if (oc == 4) {
 #pragma unroll
                     for (int n = 0; n < N; n++) imp_op_paper(px[n]);

@@ -343,8 +343,11 @@ struct Lower {
         hdr.lut_bytes = (int)luts.size();
         hdr.out = out;
         hdr.dc = final_dc ? final_dc : hdr.oc;
-        hdr.light = 1;
-        for (const ImpOp& o : ops) if (o.kind != IMP_OP_LUT3 && o.kind != IMP_OP_MAXLUT3) hdr.light = 0;
+        hdr.light = 3;                         // bit 0: only fused tables (or no op at all); bit 1: no compositing op
+        for (const ImpOp& o : ops) {
+            if (o.kind != IMP_OP_LUT3 && o.kind != IMP_OP_MAXLUT3) hdr.light &= ~1;
+            if (o.kind == IMP_OP_WATERMARK || o.kind == IMP_OP_PAPER) hdr.light &= ~2;
+        }
         bb.b.resize(((bb.b.size() + 15) & ~size_t(15)) + 64, 0);     // tail slack: the strip kernels' 16/64-byte table copies may over-read
         hdr.blob_bytes = (int)bb.b.size();
         memcpy(bb.b.data(), &hdr, sizeof hdr);
