@@ -465,7 +465,7 @@ int batch_compile(imp_gpu_batch* b, cudaStream_t up) {
         if (variant == 2) return (h.light >> 1) & 1;
         if (variant != 1) return 0;
         const bool four = (h.light & 1) && h.kind != IMP_G_AREA_FRAC;
-        return std::max(1, std::min(four ? 4 : 3, (227 * 1024) / (variant_smem(h, variant, param) + 1024))) + ((h.light & 1) ? 8 : 0);
+        return std::max(1, std::min(four ? 4 : 3, (227 * 1024) / (variant_smem(h, variant, param) + 1024))) + ((h.light & 1) ? 8 : (h.light & 4) ? 16 : 0);
     };
     for (int k = 0; k < max_passes; k++) {
         std::vector<Pending> pend;
@@ -502,7 +502,7 @@ int batch_compile(imp_gpu_batch* b, cudaStream_t up) {
                 st.generic_blur = false;
                 st.g.kind = pend[s].kind; st.g.sc = pend[s].sc; st.g.first = (int)b->h_jobs.size(); st.g.count = (int)(e - s);
                 st.g.max_tiles = 0; st.g.smem_bytes = 16; st.g.variant = pend[s].variant; st.g.tmax = pend[s].tmax;
-                st.g.light = (pend[s].variant == 2 || pend[s].variant == 4 || pend[s].variant == 5) ? pend[s].occ : (pend[s].variant == 1 ? (pend[s].occ >= 8 ? 1 : 0) : 0);
+                st.g.light = (pend[s].variant == 2 || pend[s].variant == 4 || pend[s].variant == 5) ? pend[s].occ : (pend[s].variant == 1 ? (pend[s].occ >= 16 ? 2 : pend[s].occ >= 8 ? 1 : 0) : 0);
                 for (size_t j = s; j < e; j++) {
                     st.g.max_tiles = std::max(st.g.max_tiles, variant_tiles(pend[j].hdr, pend[s].variant));
                     st.g.smem_bytes = std::max(st.g.smem_bytes, variant_smem(pend[j].hdr, pend[s].variant, pend[s].tmax));
@@ -568,7 +568,7 @@ int launch_single(imp_gpu_plan* p, const uint8_t* src, int sp, uint8_t* dst, int
             CK(imp_launch_blur_generic(j, hp.hdr, (uint16_t*)(scratch + boff[k]), ops_smem(hp.hdr), st));
         } else {
             const int param = variant_param(hp.hdr, variant);
-            ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, variant_tiles(hp.hdr, variant), variant_smem(hp.hdr, variant, param), variant, param, variant == 2 ? ((hp.hdr.light >> 1) & 1) : (hp.hdr.light & 1)};
+            ImpLaunchGroup g{hp.hdr.kind, hp.hdr.sc, 0, 1, variant_tiles(hp.hdr, variant), variant_smem(hp.hdr, variant, param), variant, param, variant == 2 ? ((hp.hdr.light >> 1) & 1) : (hp.hdr.light & 1) ? 1 : (variant == 1 && (hp.hdr.light & 4)) ? 2 : 0};
             CK(imp_launch_group(g, nullptr, &j, st));
         }
     }

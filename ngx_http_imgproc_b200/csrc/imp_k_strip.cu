@@ -6,11 +6,11 @@
 cudaError_t imp_upload_tables_strip() { return imp_upload_tables_tu(); }
 unsigned imp_debug_flags_strip() { return imp_debug_flags_tu(); }
 
-template <int SC, int MODE, bool LIGHT>
+template <int SC, int MODE, int FL>
 static cudaError_t launch_strip(const ImpLaunchGroup& g, const ImpJob* d_jobs, const ImpJob& o, cudaStream_t st) {
     static std::atomic<bool> attr_set[16];                 // per device; setting the attribute twice is harmless
     int dev = 0; cudaGetDevice(&dev);
-    auto kern = imp_tiles::imp_strip_kernel<SC, MODE, LIGHT>;
+    auto kern = imp_tiles::imp_strip_kernel<SC, MODE, FL>;
     if (!attr_set[dev & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
@@ -29,15 +29,15 @@ cudaError_t imp_launch_strip(const ImpLaunchGroup& g, const ImpJob* d_jobs, cons
     // strip kernel modes (imp_tiles.cuh): 0 fractional INTER_AREA, 1 integer INTER_AREA, 3 INTER_LINEAR
     const int mode = g.kind == IMP_G_AREA_FRAC ? 0 : g.kind == IMP_G_AREA_INT ? 1 : g.kind == IMP_G_LINEAR ? 3 : -1;
     switch (mode * 8 + g.sc) {
-        case 0 * 8 + 1: return g.light ? launch_strip<1, 0, true>(g, d_jobs, o, st) : launch_strip<1, 0, false>(g, d_jobs, o, st);
-        case 0 * 8 + 3: return g.light ? launch_strip<3, 0, true>(g, d_jobs, o, st) : launch_strip<3, 0, false>(g, d_jobs, o, st);
-        case 0 * 8 + 4: return g.light ? launch_strip<4, 0, true>(g, d_jobs, o, st) : launch_strip<4, 0, false>(g, d_jobs, o, st);
-        case 1 * 8 + 1: return g.light ? launch_strip<1, 1, true>(g, d_jobs, o, st) : launch_strip<1, 1, false>(g, d_jobs, o, st);
-        case 1 * 8 + 3: return g.light ? launch_strip<3, 1, true>(g, d_jobs, o, st) : launch_strip<3, 1, false>(g, d_jobs, o, st);
-        case 1 * 8 + 4: return g.light ? launch_strip<4, 1, true>(g, d_jobs, o, st) : launch_strip<4, 1, false>(g, d_jobs, o, st);
-        case 3 * 8 + 1: return g.light ? launch_strip<1, 3, true>(g, d_jobs, o, st) : launch_strip<1, 3, false>(g, d_jobs, o, st);
-        case 3 * 8 + 3: return g.light ? launch_strip<3, 3, true>(g, d_jobs, o, st) : launch_strip<3, 3, false>(g, d_jobs, o, st);
-        case 3 * 8 + 4: return g.light ? launch_strip<4, 3, true>(g, d_jobs, o, st) : launch_strip<4, 3, false>(g, d_jobs, o, st);
+        case 0 * 8 + 1: return g.light == 1 ? launch_strip<1, 0, 1>(g, d_jobs, o, st) : g.light == 2 ? launch_strip<1, 0, 2>(g, d_jobs, o, st) : launch_strip<1, 0, 0>(g, d_jobs, o, st);
+        case 0 * 8 + 3: return g.light == 1 ? launch_strip<3, 0, 1>(g, d_jobs, o, st) : g.light == 2 ? launch_strip<3, 0, 2>(g, d_jobs, o, st) : launch_strip<3, 0, 0>(g, d_jobs, o, st);
+        case 0 * 8 + 4: return g.light == 1 ? launch_strip<4, 0, 1>(g, d_jobs, o, st) : g.light == 2 ? launch_strip<4, 0, 2>(g, d_jobs, o, st) : launch_strip<4, 0, 0>(g, d_jobs, o, st);
+        case 1 * 8 + 1: return g.light == 1 ? launch_strip<1, 1, 1>(g, d_jobs, o, st) : g.light == 2 ? launch_strip<1, 1, 2>(g, d_jobs, o, st) : launch_strip<1, 1, 0>(g, d_jobs, o, st);
+        case 1 * 8 + 3: return g.light == 1 ? launch_strip<3, 1, 1>(g, d_jobs, o, st) : g.light == 2 ? launch_strip<3, 1, 2>(g, d_jobs, o, st) : launch_strip<3, 1, 0>(g, d_jobs, o, st);
+        case 1 * 8 + 4: return g.light == 1 ? launch_strip<4, 1, 1>(g, d_jobs, o, st) : g.light == 2 ? launch_strip<4, 1, 2>(g, d_jobs, o, st) : launch_strip<4, 1, 0>(g, d_jobs, o, st);
+        case 3 * 8 + 1: return g.light == 1 ? launch_strip<1, 3, 1>(g, d_jobs, o, st) : g.light == 2 ? launch_strip<1, 3, 2>(g, d_jobs, o, st) : launch_strip<1, 3, 0>(g, d_jobs, o, st);
+        case 3 * 8 + 3: return g.light == 1 ? launch_strip<3, 3, 1>(g, d_jobs, o, st) : g.light == 2 ? launch_strip<3, 3, 2>(g, d_jobs, o, st) : launch_strip<3, 3, 0>(g, d_jobs, o, st);
+        case 3 * 8 + 4: return g.light == 1 ? launch_strip<4, 3, 1>(g, d_jobs, o, st) : g.light == 2 ? launch_strip<4, 3, 2>(g, d_jobs, o, st) : launch_strip<4, 3, 0>(g, d_jobs, o, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -326,7 +326,9 @@ IMP_HD void imp_op_paper(ImpPx& p) {
 // which keeps the HSV / watermark / vignette code and its registers out of the kernel instantiation.
 // NOCOMP: the pass holds no compositing op (IMP_OP_WATERMARK / IMP_OP_PAPER; ImpPass::light == 2): the instantiation leaves
 // AlphaBlendOver's float divisions and their registers out.
-template <int N, bool LIGHT = false, bool NOCOMP = false>
+// COMPONLY: nothing but compositing ops and fused tables (ImpPass::light & 4 — the standard "resize + watermark" request):
+// the HSV / vignette / gradmap code stays out.
+template <int N, bool LIGHT = false, bool NOCOMP = false, bool COMPONLY = false>
 IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int (&by)[N], const ImpOp* ops, int nops, const uint8_t* lut,
                           const uint8_t* wm, int wm_pitch, int wm_c) {
     if (LIGHT) {
@@ -348,17 +350,20 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
         const ImpOp& op = ops[k];
         switch (op.kind) {
             case IMP_OP_MODULATE: {
+                if (COMPONLY) break;
                 const int a = op.i[0], b = op.i[1], c = op.i[2];
 #pragma unroll
                 for (int n = 0; n < N; n++) imp_op_modulate(px[n], a, b, c);
             } break;
             case IMP_OP_ADDCOLOR: {
+                if (COMPONLY) break;
                 const float f0 = op.f[0], f1 = op.f[1], f2 = op.f[2], f3 = op.f[3];
                 const bool nonneg = op.i[0] != 0;
 #pragma unroll
                 for (int n = 0; n < N; n++) imp_op_addcolor(px[n], f0, f1, f2, f3, nonneg);
             } break;
             case IMP_OP_LUT_ALL: {
+                if (COMPONLY) break;
                 const uint8_t* t = lut + op.i[0];
 #pragma unroll
                 for (int n = 0; n < N; n++) {
@@ -368,6 +373,7 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
                 }
             } break;
             case IMP_OP_CONTRAST: {
+                if (COMPONLY) break;
                 const float f0 = op.f[0], f1 = op.f[1];
 #pragma unroll
                 for (int n = 0; n < N; n++) {
@@ -378,6 +384,7 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
                 }
             } break;
             case IMP_OP_GRADMAP: {
+                if (COMPONLY) break;
                 const uint8_t* t0 = lut + op.i[0];
 #pragma unroll
                 for (int n = 0; n < N; n++) {
@@ -387,6 +394,7 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
                 }
             } break;
             case IMP_OP_VIGNETTE: {
+                if (COMPONLY) break;
 #if defined(__CUDA_ARCH__)
                 const float* tab = reinterpret_cast<const float*>(((unsigned long long)(unsigned)op.i[5] << 32) | (unsigned)op.i[4]);
                 if (tab) {           // mask[|dy|][|dx|], tabulated per plan by imp_vignette_table_kernel with the code of imp_vignette_mask
@@ -413,15 +421,18 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
                 }
             } break;
             case IMP_OP_LOMO:
+                if (COMPONLY) break;
 #pragma unroll
                 for (int n = 0; n < N; n++) { px[n].g = imp_lomo1(px[n].g); px[n].r = imp_lomo1(px[n].r); }
                 break;
             case IMP_OP_RAINBOW: {
+                if (COMPONLY) break;
                 const int a = op.i[0];
 #pragma unroll
                 for (int n = 0; n < N; n++) imp_op_rainbow(px[n], a);
             } break;
             case IMP_OP_SCANLINE:
+                if (COMPONLY) break;
 #pragma unroll
                 for (int n = 0; n < N; n++) {
                     int x, y; imp_map_xy(op.map, bx[n], by[n], x, y);

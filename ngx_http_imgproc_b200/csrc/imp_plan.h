@@ -86,7 +86,8 @@ struct ImpPass {
     int xtile_off, ytile_off; // tile kernels: int2 per tile column {first px, last px}; int4 per tile row {first src row, rows, first y tap, y taps}
     int light;                // bit 0: every op of the pass is a fused table (IMP_OP_LUT3 / IMP_OP_MAXLUT3) or there is none: the strip,
                               // gather and cubic kernels then run an instantiation whose op interpreter knows only those two (fewer
-                              // registers, more CTAs per SM); bit 1: no compositing op (watermark, paper): the blur kernel's flavour
+                              // registers, more CTAs per SM); bit 1: no compositing op (watermark, paper): the blur kernel's flavour; bit 2: nothing but
+                              // compositing ops and fused tables ("resize + watermark"): the strip kernels' flavour without the HSV code
     int gt;                   // gather tile kernel (imp_gathertile.cuh; COPY / NN / LINEAR): destination tile edge, 64 or 32; 0 = none
     int tile_ytaps;           // strip kernel: y-tap entries staged per tile (max over tiles, incl. alignment slack)
     int yrow4_off;            // strip kernel: int4 per output row {byte offset of its first source row inside the tile, y taps, index of its first tap in the tile's staged taps, 0}

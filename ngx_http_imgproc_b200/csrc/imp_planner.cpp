@@ -343,10 +343,12 @@ struct Lower {
         hdr.lut_bytes = (int)luts.size();
         hdr.out = out;
         hdr.dc = final_dc ? final_dc : hdr.oc;
-        hdr.light = 3;                         // bit 0: only fused tables (or no op at all); bit 1: no compositing op
+        hdr.light = 7;                         // bit 0: only fused tables (or no op at all); bit 1: no compositing op; bit 2: only compositing + tables
         for (const ImpOp& o : ops) {
-            if (o.kind != IMP_OP_LUT3 && o.kind != IMP_OP_MAXLUT3) hdr.light &= ~1;
-            if (o.kind == IMP_OP_WATERMARK || o.kind == IMP_OP_PAPER) hdr.light &= ~2;
+            const bool table = o.kind == IMP_OP_LUT3 || o.kind == IMP_OP_MAXLUT3, comp = o.kind == IMP_OP_WATERMARK || o.kind == IMP_OP_PAPER;
+            if (!table) hdr.light &= ~1;
+            if (comp) hdr.light &= ~2;
+            if (!table && !comp) hdr.light &= ~4;
         }
         bb.b.resize(((bb.b.size() + 15) & ~size_t(15)) + 64, 0);     // tail slack: the strip kernels' 16/64-byte table copies may over-read
         hdr.blob_bytes = (int)bb.b.size();

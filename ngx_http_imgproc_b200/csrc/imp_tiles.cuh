@@ -246,7 +246,7 @@ __device__ __forceinline__ StripOpsRows strip_ops_rows(const uint8_t* s_ops, int
 
 // Shared epilogue of the strip kernels: op list + store of one pixel. Inlined: an out-of-line call (v[] through
 // local memory + call/return) measured 12-20 % slower on cfg1/cfg2 than the larger code.
-template <int SC, bool LIGHT>
+template <int SC, int FL>
 __device__ __forceinline__ void strip_epilogue(const ImpJob& job, int oc, int dc, const StripStore& st, const StripOpsRows& orows, const uint8_t* s_ops, int nops, int bx, int by, const int* v) {
     ImpPx p;
     if (SC == 1) { p.b = p.g = p.r = v[0]; p.a = 255; }
@@ -254,7 +254,7 @@ __device__ __forceinline__ void strip_epilogue(const ImpJob& job, int oc, int dc
     if (by >= orows.y0 && by <= orows.y1) {
         ImpPx px[1] = {p};
         const int xs[1] = {bx}, ys[1] = {by};
-        imp_run_ops_n<1, LIGHT>(px, oc, xs, ys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
+        imp_run_ops_n<1, FL == 1, false, FL == 2>(px, oc, xs, ys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
         p = px[0];
     }
     uint8_t* d = st.base + (ptrdiff_t)by * st.step;
@@ -263,7 +263,7 @@ __device__ __forceinline__ void strip_epilogue(const ImpJob& job, int oc, int dc
     else { d[0] = (unsigned char)p.b; d[1] = (unsigned char)p.g; d[2] = (unsigned char)p.r; }
 }
 
-template <int SC, int NT, int MODE, bool LIGHT>
+template <int SC, int NT, int MODE, int FL>
 __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* __restrict__ blob,
                                                    const uint8_t* tile0, int stage_bytes, uint64_t* full, uint64_t* empty,
                                                    const uint8_t* s_ops, int nops, int bx0, int col_off, int tiles_y, int NSTAGE) {
@@ -317,7 +317,7 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_a(empty_a + stage * 8);             // this warp is done with the stage
-        if (in_x && in_y) strip_epilogue<SC, LIGHT>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
+        if (in_x && in_y) strip_epilogue<SC, FL>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
@@ -325,7 +325,7 @@ __device__ __forceinline__ void area_strip_consume(const ImpJob& job, const ImpP
 // Integer-scale consumer (INTER_AREA NxM): no tap tables at all — output row y reads source rows y*ny .. y*ny+ny-1 and
 // output column x reads source pixels x*nx .. — and the store map is hoisted (registers are plentiful here).
 // Kept separate from the fractional consumer: sharing one body cost that one 4 % (register allocation).
-template <int SC, int NT, bool LIGHT>
+template <int SC, int NT, int FL>
 __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* tile0, int stage_bytes,
                                                        uint64_t* full, uint64_t* empty, const uint8_t* s_ops, int nops, int bx0, int col_off,
                                                        int tiles_y, int NSTAGE) {
@@ -351,7 +351,7 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
         for (int c = 0; c < SC; c++) v[c] = box_2x2 ? (v[c] + 2) >> 2 : min(rint_pos(__fmul_rn(imp_u2f(v[c]), box_scale)), 255);
         __syncwarp();
         if (lane == 0) mbar_arrive_a(empty_a + stage * 8);             // this warp is done with the stage
-        if (in_x && in_y) strip_epilogue<SC, LIGHT>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
+        if (in_x && in_y) strip_epilogue<SC, FL>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
@@ -359,7 +359,7 @@ __device__ __forceinline__ void area_int_strip_consume(const ImpJob& job, const 
 // Plain-gather consumers of the strip kernel (modes 2 = INTER_NN, 3 = INTER_LINEAR, 4 = index map / crop): the same TMA ring,
 // one output row per warp, but the pixel comes from one (NN, COPY) or 2x2 (LINEAR) staged source pixels. The per-column
 // part of the gather (source offset, x coefficients) is loaded once per strip.
-template <int SC, int MODE, bool LIGHT>
+template <int SC, int MODE, int FL>
 __device__ __forceinline__ void gather_strip_consume(const ImpJob& job, const ImpPass* __restrict__ P, const uint8_t* __restrict__ blob,
                                                      const uint8_t* tile0, int stage_bytes, uint64_t* full, uint64_t* empty,
                                                      const uint8_t* s_ops, int nops, int bx0, int col_off, int tiles_y, int NSTAGE) {
@@ -431,15 +431,16 @@ __device__ __forceinline__ void gather_strip_consume(const ImpJob& job, const Im
         fence_generic_to_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_a(empty_a + stage * 8);             // this warp is done with the stage
-        if (in_x && in_y) strip_epilogue<SC, LIGHT>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
+        if (in_x && in_y) strip_epilogue<SC, FL>(job, oc, dc, st, orows, s_ops, nops, bx, by, v);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
 }
 
 // LIGHT: the pass has no ops or only fused tables (ImpPass::light — every plain resize): the instantiation without the general
 // op interpreter fits 56 registers, so four CTAs share an SM instead of three.
-template <int SC, int MODE, bool LIGHT>
-__global__ void __launch_bounds__(STRIP_THREADS, (LIGHT && MODE != 0) ? 4 : 3)      // the fractional mode keeps 12 x weights in registers: 72
+// FL 2: compositing ops and fused tables only ("resize + watermark", cfg2 / cfg5): the interpreter without the HSV code.
+template <int SC, int MODE, int FL>
+__global__ void __launch_bounds__(STRIP_THREADS, (FL == 1 && MODE != 0) ? 4 : 3)      // the fractional mode keeps 12 x weights in registers: 72
 imp_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __grid_constant__ ImpJob one, const int NSTAGE) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int jn = blockIdx.y + blockIdx.z * 65535;
@@ -513,36 +514,36 @@ imp_strip_kernel(const ImpJob* __restrict__ jobs, int first, int count, const __
     const int col_off = job.tm_x0 - c0 * 8;                           // tile byte offset of source pixel 0
     const int bx0 = blockIdx.x * TW;
     if constexpr (MODE >= 2) {
-        gather_strip_consume<SC, MODE, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE);
+        gather_strip_consume<SC, MODE, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE);
     } else if constexpr (MODE == 0) {
         switch (P->max_xtaps) {                                       // uniform over the pass
-        case 1: area_strip_consume<SC, 1, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 2: area_strip_consume<SC, 2, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 3: area_strip_consume<SC, 3, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 4: area_strip_consume<SC, 4, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 5: area_strip_consume<SC, 5, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 6: area_strip_consume<SC, 6, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 7: area_strip_consume<SC, 7, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 8: area_strip_consume<SC, 8, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 9: area_strip_consume<SC, 9, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 10: area_strip_consume<SC, 10, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 11: area_strip_consume<SC, 11, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        default: area_strip_consume<SC, 12, 0, LIGHT>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 1: area_strip_consume<SC, 1, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 2: area_strip_consume<SC, 2, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 3: area_strip_consume<SC, 3, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 4: area_strip_consume<SC, 4, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 5: area_strip_consume<SC, 5, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 6: area_strip_consume<SC, 6, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 7: area_strip_consume<SC, 7, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 8: area_strip_consume<SC, 8, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 9: area_strip_consume<SC, 9, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 10: area_strip_consume<SC, 10, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 11: area_strip_consume<SC, 11, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        default: area_strip_consume<SC, 12, 0, FL>(job, P, blob, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
         }
     } else {
         switch (P->nx) {
-        case 1: area_int_strip_consume<SC, 1, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 2: area_int_strip_consume<SC, 2, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 3: area_int_strip_consume<SC, 3, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 4: area_int_strip_consume<SC, 4, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 5: area_int_strip_consume<SC, 5, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 6: area_int_strip_consume<SC, 6, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 7: area_int_strip_consume<SC, 7, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 8: area_int_strip_consume<SC, 8, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 9: area_int_strip_consume<SC, 9, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 10: area_int_strip_consume<SC, 10, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        case 11: area_int_strip_consume<SC, 11, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
-        default: area_int_strip_consume<SC, 12, LIGHT>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 1: area_int_strip_consume<SC, 1, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 2: area_int_strip_consume<SC, 2, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 3: area_int_strip_consume<SC, 3, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 4: area_int_strip_consume<SC, 4, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 5: area_int_strip_consume<SC, 5, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 6: area_int_strip_consume<SC, 6, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 7: area_int_strip_consume<SC, 7, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 8: area_int_strip_consume<SC, 8, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 9: area_int_strip_consume<SC, 9, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 10: area_int_strip_consume<SC, 10, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        case 11: area_int_strip_consume<SC, 11, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
+        default: area_int_strip_consume<SC, 12, FL>(job, P, tile0, stage_bytes, full, empty, s_ops, nops, bx0, col_off, tiles_y, NSTAGE); break;
         }
     }
 }
