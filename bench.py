@@ -585,6 +585,7 @@ def main():
 
     if rank != 0:
         if cx.dist is not None:
+            cx.cpu_barrier()                   # rank 0 times the CPU reference on the host cores meanwhile: wait on the CPU, not on the GPU
             cx.dist.barrier(); cx.dist.destroy_process_group()
         return
     line = {
@@ -604,8 +605,10 @@ def main():
         "plan_cache": cx.L.plan_cache_stats(),
         "extra_configs": extra_out,
     }
-    if world == 1 and not a.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(a.config, a.scale, cores)
+    if not a.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(a.config, a.scale, cores)      # at every N: the same run, the same box (north_star)
+    if cx.dist is not None:
+        cx.cpu_barrier()
     print(json.dumps(line))
     if cx.dist is not None:
         cx.dist.barrier(); cx.dist.destroy_process_group()
