@@ -84,3 +84,49 @@ def test_product_does_not_reference_the_oracle():
                     if re.search(r"\boracle\b|imp_oracle|hostsim", open(os.path.join(dp, f), errors="ignore").read()):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_headers_are_plain_c_and_a_c_host_links(tmp_path):
+    """The boundary is a C ABI for a C host (bridge.c): both public headers compile as strict C99 and a C program links against
+    libimp_gpu.so, validates a request (no GPU needed) and sees IMP_ERROR_GPU — never a fallback — from a compute call."""
+    import subprocess
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "imp_gpu.h"
+#include "imp_ops.h"
+int main(void) {
+    imp_gpu_request rq; imp_gpu_config cfg; imp_gpu_plan* plan = NULL; int step = -1, w, h, c, rc;
+    const char* filters[2] = {"gamma=1.2", "rotate=90"};
+    int owner[3]; imp_gpu_plan* plans[3];
+    memset(&rq, 0, sizeof rq); memset(&cfg, 0, sizeof cfg);
+    cfg.max_filters = 5;
+    rq.crop = "400px,300px,c,c"; rq.resize = "200"; rq.filters = filters; rq.filter_count = 2;
+    rc = imp_gpu_plan_create(&rq, &cfg, 640, 480, 3, &plan, &step);
+    if (rc != IMP_OK) return 1;
+    imp_gpu_plan_output(plan, &w, &h, &c);
+    if (w != 150 || h != 200 || c != 3 || imp_gpu_plan_passes(plan) != 1) return 2;      /* 200x150 rotated */
+    plans[0] = plans[1] = plans[2] = plan;
+    if (imp_gpu_farm_assign(3, plans, 2, IMP_FARM_SIZE_AWARE, owner) != IMP_OK || owner[0] == owner[1]) return 3;
+    rq.resize = "0,0";
+    { imp_gpu_plan* bad = NULL; if (imp_gpu_plan_create(&rq, &cfg, 640, 480, 3, &bad, &step) != IMP_ERROR_INVALID_ARGS || step != IMP_STEP_RESIZE) return 4; }
+    if (imp_gpu_device_count() == 0) {
+        unsigned char px[640 * 480 * 3], out[150 * 200 * 3];
+        memset(px, 7, sizeof px);
+        if (imp_gpu_init(0) != IMP_ERROR_GPU) return 5;
+        if (imp_gpu_run_host(plan, px, 640 * 3, out, 150 * 3) != IMP_ERROR_GPU) return 6;    /* no CPU fallback */
+        if (strlen(imp_gpu_last_error()) == 0) return 7;
+    }
+    imp_gpu_plan_destroy(plan);
+    printf("C HOST OK %d\n", (int)sizeof(IplImage));
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    pkg = os.path.join(ROOT, "ngx_http_imgproc_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                        "-L", pkg, "-limp_gpu", "-Wl,-rpath," + pkg], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "C HOST OK 144" in r.stdout, (r.returncode, r.stdout, r.stderr)
