@@ -234,6 +234,14 @@ int  imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canva
                                void* d_canvases, int canvas_pitch, void* stream);
 int  imp_gpu_gif_expand_host(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
                              unsigned char* const* canvases, int canvas_step);
+/* A whole GIF request end to end: LoadGIF's loop and RunJob's frame loop (bridge.c:576-656) without the canvases ever
+ * visiting the host. The pages are uploaded as indices (1 byte per pixel), expanded on the device, and frame f runs
+ * plans[f] (created for a canvas_w x canvas_h 4-channel source; usually one cached plan repeated) into dsts[f]; chunks
+ * of frames are in flight on `n_streams` lanes exactly as in imp_gpu_batch_run_host. plans[f] == NULL: page f only takes
+ * part in the disposal replay (LoadGIF's `page` request, advancedio.c:253-272, keeps the last page alone). Synchronous. */
+int  imp_gpu_gif_album_run_host(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
+                                imp_gpu_plan* const* plans, unsigned char* const* dsts, const int* dst_steps,
+                                int n_streams);
 
 /* ---- memory helpers so a C host needs no CUDA headers --------------------------------------------- */
 int  imp_gpu_malloc(void** d_ptr, size_t bytes);

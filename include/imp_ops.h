@@ -72,6 +72,12 @@ int  imp_BlendWithPaper(IplImage* image);          /* the reference returns void
 int  imp_Flush(IplImage** pointer);
 /* Same for all frames of an album in one overlapped batch (GIF frames; bridge.c:576-656 loops). */
 int  imp_FlushAll(IplImage** frames, int count);
+/* The album of a GIF whose canvases were NOT expanded on the host: frames[] are the canvas-sized 4-channel IplImages
+ * LoadGIF created (advancedio.c:188-193; their pixels are never read), pages[] the FreeImage pages its per-pixel loop
+ * (:195-248) would have walked. Expands on the device and runs what was recorded for each frame (a frame with nothing
+ * recorded just receives its canvas). n_pages == count: frame i is page i. count == 1 < n_pages: LoadGIF's `page`
+ * request (:264-272) — the frame is the LAST page, the earlier ones are only replayed for their disposal. */
+int  imp_FlushAllGif(IplImage** frames, int count, const imp_gpu_gif_frame* pages, int n_pages, int destructive);
 /* Forget anything recorded for `image` (call before releasing a frame that was never flushed). */
 void imp_Discard(IplImage* image);
 /* Number of operations currently recorded for `image` (0 = pixels are up to date). */

@@ -189,13 +189,32 @@ class Library:
         self.check(self.lib.imp_gpu_ascii_host(img.ctypes.data, img.strides[0], img.shape[1], img.shape[0], img.shape[2], args.encode(), out, n))
         return out.raw[:n]
 
-    def gif_expand(self, frames, cw: int, ch: int, destructive: bool):
-        """LoadGIF's canvas expansion (advancedio.c:195-248) on the device; frames as dicts: indices (HxW uint8, bottom-up; or H x pitch with `width`: the page as FreeImage pads it), left, top, dispose, key, palette (256x4)."""
+    @staticmethod
+    def gif_pages(frames):
+        """ctypes array of imp_gpu_gif_frame from dicts: indices (HxW uint8, bottom-up; or H x pitch with `width`: the page as FreeImage pads it), left, top, dispose, key, palette (256x4). Returns (array, keep-alive list)."""
         keep, arr = [], (CGifFrame * len(frames))()
         for i, f in enumerate(frames):
             idx = np.ascontiguousarray(f["indices"], np.uint8); pal = np.ascontiguousarray(f["palette"], np.uint8)
             keep += [idx, pal]
             arr[i] = CGifFrame(idx.ctypes.data, idx.strides[0], f.get("width") or idx.shape[1], idx.shape[0], f["left"], f["top"], f["dispose"], f["key"], pal.ctypes.data)
+        return arr, keep
+
+    def gif_album(self, frames, cw: int, ch: int, destructive: bool, plan: "Plan", outs=None, n_streams: int = 4):
+        """imp_gpu_gif_album_run_host: pages up as indices, canvases expanded on the device, `plan` over every frame."""
+        arr, keep = self.gif_pages(frames)
+        n = len(frames)
+        if outs is None:
+            outs = [np.empty((plan.out_h, plan.out_w, plan.out_c), np.uint8) for _ in range(n)]
+        plans = (C.c_void_p * n)(*[plan.h] * n)
+        dsts = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        steps = (C.c_int * n)(*[o.strides[0] for o in outs])
+        self.lib.imp_gpu_gif_album_run_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        self.check(self.lib.imp_gpu_gif_album_run_host(arr, n, cw, ch, 1 if destructive else 0, plans, dsts, steps, n_streams))
+        return outs
+
+    def gif_expand(self, frames, cw: int, ch: int, destructive: bool):
+        """LoadGIF's canvas expansion (advancedio.c:195-248) on the device; frames as for gif_pages."""
+        arr, keep = self.gif_pages(frames)
         outs = [np.zeros((ch, cw, 4), np.uint8) for _ in frames]
         ptrs = (C.c_void_p * len(frames))(*[o.ctypes.data for o in outs])
         self.lib.imp_gpu_gif_expand_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
@@ -381,6 +400,7 @@ class OpsLayer:
         L.imp_Watermark.argtypes = [C.POINTER(IplImage), C.POINTER(CConfig)]
         L.imp_BlendWithPaper.argtypes = [C.POINTER(IplImage)]
         L.imp_FlushAll.argtypes = [PP, C.c_int]
+        L.imp_FlushAllGif.argtypes = [PP, C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.imp_Discard.argtypes = [C.POINTER(IplImage)]
         self.keep = []
         self._cb = (self.CREATE_T(self._create), self.RELEASE_T(self._release))
@@ -410,8 +430,10 @@ class OpsLayer:
     def _release(self, pp):
         pp[0] = None
 
-    def request(self, frames, cfg: Config, crop=None, gravity=None, resize=None, filters=(), simple=False, flatten=False):
-        """Steps 3-7 of RunJob over `frames` (numpy images): returns (code, list of results or None)."""
+    def request(self, frames, cfg: Config, crop=None, gravity=None, resize=None, filters=(), simple=False, flatten=False, gif_pages=None, destructive=False):
+        """Steps 3-7 of RunJob over `frames` (numpy images): returns (code, list of results or None).
+        gif_pages (dicts as Library.gif_pages takes them): `frames` are only canvas-sized 4-channel placeholders whose pixels
+        are never read; the flush is imp_FlushAllGif (pages expanded on the device)."""
         L = self.L.lib
         self.keep = []
         ccfg, keep = cfg.to_c()
@@ -430,7 +452,11 @@ class OpsLayer:
             for p in ptrs: L.imp_Discard(p)
             return code, None
         arr = (C.POINTER(IplImage) * len(ptrs))(*ptrs)
-        code = L.imp_FlushAll(arr, len(ptrs))
+        if gif_pages is not None:
+            pages, keep_pages = Library.gif_pages(gif_pages)
+            code = L.imp_FlushAllGif(arr, len(ptrs), pages, len(gif_pages), 1 if destructive else 0)
+        else:
+            code = L.imp_FlushAll(arr, len(ptrs))
         if code:
             return code, None
         outs = []

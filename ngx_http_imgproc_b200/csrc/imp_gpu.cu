@@ -102,6 +102,7 @@ struct DevCtx {
     Buf h_up; cudaEvent_t up_ev = nullptr; bool up_pending = false;   // pinned staging of plan uploads
     std::vector<Lane*> lanes;                    // persistent staging, reused across calls
     std::mutex run_mu;                           // serialises users of `lanes`
+    Buf h_gif, d_gif, d_canvas; cudaEvent_t gif_ev = nullptr;   // GIF albums: packed pages (pinned / device), expanded BGRA canvases
 };
 DevCtx g_dev[MAX_DEV];
 std::mutex g_mu;
@@ -589,6 +590,7 @@ constexpr size_t kChunkBytes = 128u << 20;
 struct HostJobs {
     int n; imp_gpu_plan* const* plans; const unsigned char* const* srcs; const int* src_steps;
     unsigned char* const* dsts; const int* dst_steps;
+    bool src_device = false;       // srcs[] are whole frames already on this device (pitch % 16 == 0): nothing to upload
 };
 
 bool is_pinned(const void* p) {
@@ -645,11 +647,15 @@ int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
         Lay& l = lay[k];
         const size_t in_row = (size_t)p->win_w * p->src_c, out_row = (size_t)p->out_w * p->out_c;
         l.in_pitch = align16((int)in_row); l.out_pitch = align16((int)out_row);
-        l.in_off = in_total; in_total += align256((size_t)l.in_pitch * p->win_h);
+        l.in_off = in_total;
+        if (!J.src_device) in_total += align256((size_t)l.in_pitch * p->win_h);                       // landing zone of the crop window
         l.out_off = out_total; out_total += align256((size_t)l.out_pitch * p->out_h);
         l.src_pinned = is_pinned(J.srcs[i]); l.dst_pinned = is_pinned(J.dsts[i]);
         l.linear = false; l.lin_bytes = 0; l.stage_off = 0; l.hin_off = 0; l.hout_off = -1;
-        if (l.src_pinned) {
+        if (J.src_device) {
+            if ((reinterpret_cast<uintptr_t>(J.srcs[i]) & 15) || (J.src_steps[i] & 15) || (size_t)J.src_steps[i] < (size_t)p->src_w * p->src_c) return IMP_ERROR_INVALID_ARGS;
+            l.src_pinned = true;
+        } else if (l.src_pinned) {
             // A 2-D host-to-device copy pays ~0.15 us per row whatever its width (measured: 3.5 KB rows move at 23 GB/s,
             // 14 KB rows at the link's 54 GB/s). Short rows therefore travel as ONE linear copy of the rows the window
             // touches (full width) and a small kernel extracts / re-pitches the window on the device.
@@ -677,6 +683,10 @@ int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
         const size_t in_row = (size_t)p->win_w * sc;
         uint8_t* d_in = L.d_in.p + l.in_off;
         const uint8_t* win = J.srcs[i] + (size_t)p->win_y * J.src_steps[i] + (size_t)p->win_x * sc;
+        if (J.src_device) {
+            B.items.push_back(imp_gpu_batch::Item{p, J.srcs[i], J.src_steps[i], L.d_out.p + l.out_off, l.out_pitch});
+            continue;
+        }
         if (!l.src_pinned) {
             // a pageable frame (what cvDecodeImage hands RunJob) goes through the lane's pinned staging, laid out with the
             // device pitch. One core moves ~10 GB/s, a fifth of the link: windows of 4 MB and more are split over up to four
@@ -735,9 +745,9 @@ int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
     return IMP_OK;
 }
 
-int run_host_chunked(const HostJobs& J, int n_streams) {
+// `after`: an event every lane waits for before its first chunk (the producer of device-resident sources). Caller holds run_mu.
+int run_host_chunked_locked(const HostJobs& J, int n_streams, cudaEvent_t after) {
     DevCtx& ctx = g_dev[t_dev];
-    std::lock_guard<std::mutex> run_lk(ctx.run_mu);
     n_streams = std::max(1, std::min(n_streams, 8));
     while ((int)ctx.lanes.size() < n_streams) {
         Lane* L = new (std::nothrow) Lane();
@@ -747,6 +757,7 @@ int run_host_chunked(const HostJobs& J, int n_streams) {
         ctx.lanes.push_back(L);
     }
     int result = IMP_OK, chunk = 0, i = 0;
+    if (after) for (int k = 0; k < n_streams; k++) CK(cudaStreamWaitEvent(ctx.lanes[k]->st, after, 0));
     while (i < J.n && result == IMP_OK) {
         Lane& L = *ctx.lanes[chunk % n_streams];
         if ((result = lane_finish(L, J))) break;
@@ -766,6 +777,10 @@ int run_host_chunked(const HostJobs& J, int n_streams) {
     }
     for (Lane* L : ctx.lanes) { int r = lane_finish(*L, J); if (result == IMP_OK) result = r; }
     return result;
+}
+int run_host_chunked(const HostJobs& J, int n_streams) {
+    std::lock_guard<std::mutex> run_lk(g_dev[t_dev].run_mu);
+    return run_host_chunked_locked(J, n_streams, nullptr);
 }
 
 }  // namespace
@@ -853,6 +868,8 @@ void imp_gpu_shutdown(void) {
             }
             c.lanes.clear();
             c.h_up.release(true);
+            c.h_gif.release(true); c.d_gif.release(false); c.d_canvas.release(false);
+            if (c.gif_ev) { cudaEventDestroy(c.gif_ev); c.gif_ev = nullptr; }
             if (c.up_ev) cudaEventDestroy(c.up_ev);
             if (c.stream) cudaStreamDestroy(c.stream);
         }
@@ -1201,25 +1218,20 @@ int imp_gpu_ascii_host(const unsigned char* img, int step, int w, int h, int c, 
 }
 
 // ---- "next" row §8f-2: GIF canvas expansion ------------------------------------------------------------------
-int imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
-                              void* d_canvases, int canvas_pitch, void* stream) {
-    int rc = bind(); if (rc) return rc;
-    if (!frames || n <= 0 || canvas_w <= 0 || canvas_h <= 0 || !d_canvases || canvas_pitch < canvas_w * 4 || canvas_pitch % 4) return IMP_ERROR_INVALID_ARGS;
-    cudaStream_t st = pick_stream(stream);
-    // one staging buffer: [ImpGifFrame n][palettes n*1024][index planes]
+// Packed page block of a GIF: [ImpGifFrame n][palettes n*1024][index planes], device pointers already resolved against d_buf.
+static int gif_validate(const imp_gpu_gif_frame* frames, int n, size_t* meta_bytes, size_t* total) {
     size_t idx_bytes = 0;
     for (int f = 0; f < n; f++) {
         if (!frames[f].indices || !frames[f].palette || frames[f].width <= 0 || frames[f].height <= 0 || frames[f].pitch < frames[f].width) return IMP_ERROR_INVALID_ARGS;
         idx_bytes += ((size_t)frames[f].pitch * frames[f].height + 15) & ~size_t(15);
     }
-    const size_t meta_bytes = (((size_t)n * sizeof(ImpGifFrame)) + 15) & ~size_t(15), pal_bytes = (size_t)n * 1024;
-    const size_t total = meta_bytes + pal_bytes + idx_bytes;
-    uint8_t* h_buf = nullptr; uint8_t* d_buf = nullptr;
-    CK(cudaHostAlloc((void**)&h_buf, total, cudaHostAllocDefault));
-    cudaError_t e = cudaMallocAsync((void**)&d_buf, total, st);
-    if (e != cudaSuccess) { cudaFreeHost(h_buf); return fail(e, "cudaMallocAsync", __LINE__); }
+    *meta_bytes = (((size_t)n * sizeof(ImpGifFrame)) + 15) & ~size_t(15);
+    *total = *meta_bytes + (size_t)n * 1024 + idx_bytes;
+    return IMP_OK;
+}
+static void gif_pack(const imp_gpu_gif_frame* frames, int n, size_t meta_bytes, uint8_t* h_buf, const uint8_t* d_buf) {
     ImpGifFrame* meta = reinterpret_cast<ImpGifFrame*>(h_buf);
-    size_t off = meta_bytes + pal_bytes;
+    size_t off = meta_bytes + (size_t)n * 1024;
     for (int f = 0; f < n; f++) {
         const imp_gpu_gif_frame& g = frames[f];
         memcpy(h_buf + meta_bytes + (size_t)f * 1024, g.palette, 1024);
@@ -1229,6 +1241,20 @@ int imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canvas
         meta[f].dispose = g.dispose; meta[f].key = g.transparency_key; meta[f].pad_ = 0;
         off += ((size_t)g.pitch * g.height + 15) & ~size_t(15);
     }
+}
+
+int imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
+                              void* d_canvases, int canvas_pitch, void* stream) {
+    int rc = bind(); if (rc) return rc;
+    if (!frames || n <= 0 || canvas_w <= 0 || canvas_h <= 0 || !d_canvases || canvas_pitch < canvas_w * 4 || canvas_pitch % 4) return IMP_ERROR_INVALID_ARGS;
+    cudaStream_t st = pick_stream(stream);
+    size_t meta_bytes = 0, total = 0;
+    if ((rc = gif_validate(frames, n, &meta_bytes, &total))) return rc;
+    uint8_t* h_buf = nullptr; uint8_t* d_buf = nullptr;
+    CK(cudaHostAlloc((void**)&h_buf, total, cudaHostAllocDefault));
+    cudaError_t e = cudaMallocAsync((void**)&d_buf, total, st);
+    if (e != cudaSuccess) { cudaFreeHost(h_buf); return fail(e, "cudaMallocAsync", __LINE__); }
+    gif_pack(frames, n, meta_bytes, h_buf, d_buf);
     e = cudaMemcpyAsync(d_buf, h_buf, total, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = imp_launch_gif_expand(reinterpret_cast<const ImpGifFrame*>(d_buf), n, canvas_w, canvas_h, destructive ? 1 : 0, (uint8_t*)d_canvases, canvas_pitch, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // h_buf / d_buf are released below
@@ -1236,6 +1262,46 @@ int imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canvas
     cudaFreeHost(h_buf);
     if (e != cudaSuccess) return fail(e, "gif expand", __LINE__);
     return IMP_OK;
+}
+
+// A whole GIF request: the pages travel as palette indices (1 byte per pixel instead of the 4 of a decoded canvas), are
+// expanded into BGRA canvases on the device (LoadGIF's loop, advancedio.c:195-248) and feed the frame loop of RunJob
+// (bridge.c:576-656) without leaving it: grouped launches over all frames, results D2H as in imp_gpu_batch_run_host.
+int imp_gpu_gif_album_run_host(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
+                               imp_gpu_plan* const* plans, unsigned char* const* dsts, const int* dst_steps, int n_streams) {
+    int rc = bind(); if (rc) return rc;
+    if (!frames || n <= 0 || canvas_w <= 0 || canvas_h <= 0 || !plans || !dsts || !dst_steps) return IMP_ERROR_INVALID_ARGS;
+    int n_run = 0;
+    for (int f = 0; f < n; f++) {
+        const imp_gpu_plan* p = plans[f];
+        if (!p) continue;                                             // replayed for the pages after it, no result wanted
+        if (!dsts[f] || p->src_w != canvas_w || p->src_h != canvas_h || p->src_c != 4) return IMP_ERROR_INVALID_ARGS;
+        if ((size_t)dst_steps[f] < (size_t)p->out_w * p->out_c) return IMP_ERROR_INVALID_ARGS;
+        n_run++;
+    }
+    size_t meta_bytes = 0, total = 0;
+    if ((rc = gif_validate(frames, n, &meta_bytes, &total))) return rc;
+    DevCtx& ctx = g_dev[t_dev];
+    std::lock_guard<std::mutex> run_lk(ctx.run_mu);
+    const int pitch = align16(canvas_w * 4);
+    const size_t canvas_bytes = (size_t)pitch * canvas_h;
+    if ((rc = ctx.h_gif.grow(total, true)) || (rc = ctx.d_gif.grow(total, false)) || (rc = ctx.d_canvas.grow(canvas_bytes * n, false))) return rc;
+    if (!ctx.gif_ev) CK(cudaEventCreateWithFlags(&ctx.gif_ev, cudaEventDisableTiming));
+    gif_pack(frames, n, meta_bytes, ctx.h_gif.p, ctx.d_gif.p);
+    CK(cudaMemcpyAsync(ctx.d_gif.p, ctx.h_gif.p, total, cudaMemcpyHostToDevice, ctx.stream));
+    CK(imp_launch_gif_expand(reinterpret_cast<const ImpGifFrame*>(ctx.d_gif.p), n, canvas_w, canvas_h, destructive ? 1 : 0, ctx.d_canvas.p, pitch, ctx.stream));
+    CK(cudaEventRecord(ctx.gif_ev, ctx.stream));
+    std::vector<imp_gpu_plan*> run_plans; std::vector<const unsigned char*> srcs; std::vector<unsigned char*> outs; std::vector<int> steps, out_steps;
+    for (int f = 0; f < n; f++) {
+        if (!plans[f]) continue;
+        run_plans.push_back(plans[f]); srcs.push_back(ctx.d_canvas.p + (size_t)f * canvas_bytes); steps.push_back(pitch);
+        outs.push_back(dsts[f]); out_steps.push_back(dst_steps[f]);
+    }
+    if (n_run == 0) { CK(cudaStreamSynchronize(ctx.stream)); return IMP_OK; }
+    HostJobs J{n_run, run_plans.data(), srcs.data(), steps.data(), outs.data(), out_steps.data(), true};
+    try { rc = run_host_chunked_locked(J, n_streams, ctx.gif_ev); } catch (const std::bad_alloc&) { rc = IMP_ERROR_MALLOC_FAILED; }
+    if (rc != IMP_OK) cudaStreamSynchronize(ctx.stream);           // the staging buffers are reused by the next call
+    return rc;
 }
 
 int imp_gpu_gif_expand_host(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,

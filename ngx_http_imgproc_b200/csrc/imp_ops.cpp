@@ -197,22 +197,28 @@ void imp_Discard(IplImage* image) {
     g_pending.erase(it);
 }
 
-int imp_FlushAll(IplImage** frames, int count) {
+// pages != nullptr: the album of a GIF whose canvases live on the device only (imp_FlushAllGif) — every frame takes part,
+// the sources are the pages, and frames[i]'s own pixels are never read.
+static int flush_all(IplImage** frames, int count, const imp_gpu_gif_frame* pages, int n_pages, int destructive) {
     IMP_OPS_TRY
     if (!frames || count < 0) return IMP_ERROR_INVALID_ARGS;
     std::vector<imp_gpu_plan*> plans; std::vector<IplImage*> outs; std::vector<int> idx;
     std::vector<const unsigned char*> srcs; std::vector<unsigned char*> dsts; std::vector<int> ss, ds;
-    int rc = IMP_OK;
+    int rc = IMP_OK, cw = 0, ch = 0;                                  // GIF: the canvas every page is composed onto
     {
         std::lock_guard<std::mutex> lk(g_ops_mu);
         for (int i = 0; i < count && rc == IMP_OK; i++) {
-            if (!frames[i]) continue;
+            if (!frames[i]) { if (pages) rc = IMP_ERROR_INVALID_ARGS; continue; }
             auto it = g_pending.find(frames[i]);
             const bool idle = it == g_pending.end() || it->second.n_ops == 0;
             // bridge.c:613-618 turns EVERY 1-channel frame into BGR at the filter step, even when no operator was asked for:
             // such a frame still takes the (empty) plan, whose store promotes gray to B,G,R
-            if (idle && frames[i]->nChannels != 1) { if (it != g_pending.end()) g_pending.erase(it); continue; }
+            if (idle && frames[i]->nChannels != 1 && !pages) { if (it != g_pending.end()) g_pending.erase(it); continue; }
             Pending& p = idle ? entry(frames[i]) : it->second;
+            if (pages) {
+                if (i == 0) { cw = p.w; ch = p.h; }
+                if (p.c != 4 || p.w != cw || p.h != ch) { rc = IMP_ERROR_INVALID_ARGS; break; }
+            }
             imp_gpu_plan* plan = nullptr; IplImage* out = nullptr;
             rc = run_one(&frames[i], p, &plan, &out);
             if (rc) break;
@@ -221,8 +227,17 @@ int imp_FlushAll(IplImage** frames, int count) {
             dsts.push_back((unsigned char*)out->imageData); ds.push_back(out->widthStep);
         }
     }
-    if (rc == IMP_OK && !plans.empty())
-        rc = imp_gpu_batch_run_host((int)plans.size(), plans.data(), srcs.data(), ss.data(), dsts.data(), ds.data(), 4);
+    if (rc == IMP_OK && !plans.empty()) {
+        if (pages) {
+            // frame k is page k, or (a `page` request) the one frame is the last page and the earlier pages are only replayed
+            const int skip = n_pages - (int)plans.size();
+            std::vector<imp_gpu_plan*> pp((size_t)n_pages, nullptr); std::vector<unsigned char*> pd((size_t)n_pages, nullptr); std::vector<int> ps((size_t)n_pages, 0);
+            for (size_t k = 0; k < plans.size(); k++) { pp[skip + k] = plans[k]; pd[skip + k] = dsts[k]; ps[skip + k] = ds[k]; }
+            rc = imp_gpu_gif_album_run_host(pages, n_pages, cw, ch, destructive, pp.data(), pd.data(), ps.data(), 4);
+        } else {
+            rc = imp_gpu_batch_run_host((int)plans.size(), plans.data(), srcs.data(), ss.data(), dsts.data(), ds.data(), 4);
+        }
+    }
     imp_ops_release_image_fn release = g_release ? g_release : default_release;
     {
         std::lock_guard<std::mutex> lk(g_ops_mu);
@@ -240,6 +255,13 @@ int imp_FlushAll(IplImage** frames, int count) {
     }
     return rc;
     IMP_OPS_CATCH
+}
+
+int imp_FlushAll(IplImage** frames, int count) { return flush_all(frames, count, nullptr, 0, 0); }
+
+int imp_FlushAllGif(IplImage** frames, int count, const imp_gpu_gif_frame* pages, int n_pages, int destructive) {
+    if (!pages || count <= 0 || !(n_pages == count || (count == 1 && n_pages >= 1))) return IMP_ERROR_INVALID_ARGS;
+    return flush_all(frames, count, pages, n_pages, destructive);
 }
 
 int imp_Flush(IplImage** pointer) {

@@ -93,7 +93,59 @@ int Kelvin  (IplImage** pointer, char* args) { return imp_record(pointer, "kelvi
 int Rainbow (IplImage** pointer, char* args) { return imp_record(pointer, "rainbow", args); }
 int Scanline(IplImage** pointer, char* args) { return imp_record(pointer, "scanline", args); }
 
-/* Runs everything recorded for the album's frames (bridge.c:576-656 loops) as fused GPU passes: one batched call. */
+/* ---- GIF albums: LoadGIF's per-pixel loop (advancedio.c:195-248) on the device -------------------------------------
+ * With INTEGRATION.md §4's edit LoadGIF no longer composes the canvases: for every page it walks it calls
+ * imp_AlbumGifPage, which keeps a copy of the page's index bits (1 byte per pixel) and palette; the canvas-sized frames it
+ * still creates are placeholders. imp_FlushAlbum recognises the album by its last frame and expands the pages on the
+ * device, straight into the frame loop. One album is in flight per worker (RunJob is synchronous): a single slot. */
+static struct {
+    IplImage* last;                 /* Image of the newest registered page: Frames[Count-1] of the album, also after a `page` request */
+    imp_gpu_gif_frame* pages;
+    unsigned char** blocks;         /* one malloc per page: palette (1024 bytes) then the index bits */
+    int count, cap, destructive;
+} imp_gif;
+
+static void imp_gif_reset(void) {
+    int k;
+    for (k = 0; k < imp_gif.count; k++) free(imp_gif.blocks[k]);
+    imp_gif.count = 0; imp_gif.last = NULL;
+}
+
+int imp_AlbumGifPage(Album* album, int frameid, int isdestructive, const unsigned char* bits, int pitch, int width, int height,
+                     int left, int top, const void* palette) {
+    unsigned char* block;
+    imp_gpu_gif_frame* pg;
+    if (!album || frameid < 0 || !bits || !palette || pitch < width || width <= 0 || height <= 0) return IMP_ERROR_INVALID_ARGS;
+    if (frameid == 0) imp_gif_reset();
+    if (frameid != imp_gif.count) return IMP_ERROR_INVALID_ARGS;            /* LoadGIF walks the pages in order */
+    if (imp_gif.count == imp_gif.cap) {
+        int cap = imp_gif.cap ? imp_gif.cap * 2 : 64;
+        imp_gpu_gif_frame* np = (imp_gpu_gif_frame*)realloc(imp_gif.pages, sizeof(imp_gpu_gif_frame) * (size_t)cap);
+        unsigned char** nb;
+        if (!np) return IMP_ERROR_MALLOC_FAILED;
+        imp_gif.pages = np;
+        nb = (unsigned char**)realloc(imp_gif.blocks, sizeof(unsigned char*) * (size_t)cap);
+        if (!nb) return IMP_ERROR_MALLOC_FAILED;
+        imp_gif.blocks = nb; imp_gif.cap = cap;
+    }
+    block = (unsigned char*)malloc(1024 + (size_t)pitch * (size_t)height);
+    if (!block) return IMP_ERROR_MALLOC_FAILED;
+    memcpy(block, palette, 1024);
+    memcpy(block + 1024, bits, (size_t)pitch * (size_t)height);
+    pg = &imp_gif.pages[imp_gif.count];
+    pg->indices = block + 1024; pg->pitch = pitch; pg->width = width; pg->height = height;
+    pg->left = left; pg->top = top;
+    pg->dispose = album->Frames[frameid].Dispose;
+    pg->transparency_key = album->Frames[frameid].TransparencyKey;
+    pg->palette = block;
+    imp_gif.blocks[imp_gif.count++] = block;
+    imp_gif.destructive = isdestructive;
+    imp_gif.last = album->Frames[frameid].Image;
+    return IMP_OK;
+}
+
+/* Runs everything recorded for the album's frames (bridge.c:576-656 loops) as fused GPU passes: one batched call.
+ * The album of a GIF whose pages were handed to imp_AlbumGifPage takes its pixels from them (expanded on the device). */
 int imp_FlushAlbum(Album* album) {
     IplImage* stack[64];
     IplImage** fr = stack;
@@ -101,7 +153,12 @@ int imp_FlushAlbum(Album* album) {
     if (album->Count <= 0) return IMP_OK;
     if (album->Count > 64) { fr = (IplImage**)malloc(sizeof(IplImage*) * (size_t)album->Count); if (!fr) return IMP_ERROR_MALLOC_FAILED; }
     for (k = 0; k < album->Count; k++) fr[k] = album->Frames[k].Image;
-    rc = imp_FlushAll(fr, album->Count);
+    if (imp_gif.count && imp_gif.last == fr[album->Count - 1] && (imp_gif.count == album->Count || album->Count == 1)) {
+        rc = imp_FlushAllGif(fr, album->Count, imp_gif.pages, imp_gif.count, imp_gif.destructive);
+        imp_gif_reset();
+    } else {
+        rc = imp_FlushAll(fr, album->Count);
+    }
     for (k = 0; k < album->Count; k++) album->Frames[k].Image = fr[k];
     if (fr != stack) free(fr);
     return rc;

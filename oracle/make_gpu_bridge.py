@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE — builds oracle/_ref/libimp_ref_gpu.so: the reference with INTEGRATION.md's edits applied.
 
-The reference's bridge.c and filters.c are read where they lie (/root/reference); the definitions that
+The reference's bridge.c, filters.c and advancedio.c are read where they lie (/root/reference); the definitions that
 ngx_http_imgproc_b200/dropin/imp_dropin.c replaces under their own names are deleted IN MEMORY (brace-matched on the
 reference's own identifiers; no reference text is stored in this repo), RunJob gets INTEGRATION.md §2's one flush
-statement, and the result is compiled from a temporary directory together with imp_dropin.c, the reference's untouched
-helpers.c / advancedio.c and the test stubs, linked against ngx_http_imgproc_b200/libimp_gpu.so; the temporary sources are
+statement, LoadGIF's per-pixel canvas loop becomes INTEGRATION.md §4's one call, and the result is compiled from a
+temporary directory together with imp_dropin.c, the reference's untouched helpers.c and the test stubs, linked against ngx_http_imgproc_b200/libimp_gpu.so; the temporary sources are
 deleted. RunJob's operator call sites (Crop, Resize, Filter, Watermark, BlendWithPaper) are NOT edited. Only the .so is kept (git-ignored,
 travels to the GPU box). tests/test_gpu_parity.py then drives the reference's own RunJob through it on a B200 and
 compares with the unmodified CPU build (libimp_ref.so): that is the drop-in claim, executed.
@@ -82,6 +82,30 @@ def patched_filters(src: str) -> str:
     return s
 
 
+GIF_PAGE = ("        result->Error = imp_AlbumGifPage(result, frameid, isdestructive, FreeImage_GetBits(frame), FreeImage_GetPitch(frame), "
+            "w, h, left, top, palette);   /* INTEGRATION.md §4 */\n        if (result->Error) { return; }\n")
+
+
+def patched_advancedio(src: str) -> str:
+    """advancedio.c with INTEGRATION.md §4 applied: LoadGIF's per-pixel canvas loop (the `int x, y;` declaration and the
+    `for (y ...)` nest that follows it) is replaced by ONE call that hands the page to the drop-in; everything else —
+    page walking, tags, palette, 8-bit conversion, frame creation, unlocking, the `page` tail — stays as the reference wrote it."""
+    start = src.index("static void LoadGIF(")
+    m = re.compile(r'^[ \t]*int x, y;\s*\n[ \t]*for \(y = 0; y < canvasH; y\+\+\) \{', re.M).search(src, start)
+    if not m:
+        raise SystemExit("make_gpu_bridge: LoadGIF's canvas loop not found (reference layout changed?)")
+    depth, i = 1, m.end()
+    while depth and i < len(src):
+        depth += {'{': 1, '}': -1}.get(src[i], 0)
+        i += 1
+    if depth:
+        raise SystemExit("make_gpu_bridge: unbalanced braces in LoadGIF")
+    s = src[:m.start()] + GIF_PAGE + src[i:]
+    proto = ("int imp_AlbumGifPage(Album* album, int frameid, int isdestructive, const unsigned char* bits, int pitch, int width, "
+             "int height, int left, int top, const void* palette);\n")
+    return sub_once(r'(static void LoadGIF\()', lambda mm: proto + mm.group(1), s, "LoadGIF prototype")
+
+
 def main():
     lib = os.path.join(PKG, "libimp_gpu.so")
     if not os.path.exists(os.path.join(REF, "bridge.c")):
@@ -94,7 +118,7 @@ def main():
     tmp = tempfile.mkdtemp(prefix="imp_gpu_bridge_")
     try:
         gen = {}
-        for name, fn in (("bridge.c", patched_bridge), ("filters.c", patched_filters)):
+        for name, fn in (("bridge.c", patched_bridge), ("filters.c", patched_filters), ("advancedio.c", patched_advancedio)):
             with open(os.path.join(REF, name)) as f:
                 text = fn(f.read())
             gen[name] = os.path.join(tmp, name.replace(".c", "_gpu.c"))
@@ -103,7 +127,7 @@ def main():
         cmd = [os.environ.get("CC", "gcc"), "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w",
                "-I", os.path.join(HERE, "shim"), "-I", REF, "-I", os.path.join(ROOT, "include"),
                "-o", os.path.join(out_dir, "libimp_ref_gpu.so"),
-               gen["filters.c"], os.path.join(REF, "helpers.c"), gen["bridge.c"], os.path.join(REF, "advancedio.c"), DROPIN,
+               gen["filters.c"], os.path.join(REF, "helpers.c"), gen["bridge.c"], gen["advancedio.c"], DROPIN,
                os.path.join(HERE, "ref_stubs.c"), os.path.join(HERE, "fake_freeimage.c"), os.path.join(HERE, "imp_oracle.c"),
                "-L", PKG, "-limp_gpu", "-Wl,-rpath,$ORIGIN/../../ngx_http_imgproc_b200", "-lm"]
         subprocess.check_call(cmd)

@@ -363,6 +363,82 @@ def test_gif_canvas_expansion(gpu, orc):
                 assert np.array_equal(a, b)
 
 
+def _random_gif(rng, cw, ch, n):
+    frames = []
+    for f in range(n):
+        w = cw if f == 0 else int(rng.integers(1, cw + 1)); h = ch if f == 0 else int(rng.integers(1, ch + 1))
+        frames.append(dict(indices=np.ascontiguousarray(rng.integers(0, 16, (h, w), dtype=np.uint8)), left=0 if f == 0 else int(rng.integers(0, cw - w + 1)),
+                           top=0 if f == 0 else int(rng.integers(0, ch - h + 1)), dispose=int(rng.integers(0, 4)),
+                           key=int(rng.choice([-1, 0, 3, 7])), palette=rng.integers(0, 256, (256, 4), dtype=np.uint8)))
+    return frames
+
+
+def test_gif_album_pages_to_results_on_the_device(gpu, orc):
+    """A whole GIF request through imp_gpu_gif_album_run_host: pages up as indices, canvases expanded on the device, the
+    frame loop (bridge.c:576-656) over them — against the restatement of LoadGIF's loop followed by the oracle's chain on
+    every canvas. Frame counts on both sides of the chunking, one launch group per chunk."""
+    rng = np.random.default_rng(23)
+    o = orc.orc()
+    cases = [((48, 27, 5), dict(resize="96,54", simple=True), True),
+             ((131, 77, 9), dict(crop="100px,60px,c,c", resize="50", filters=["modulate=0,0,100", "colorize=704214,0.6", "rotate=90"]), False),
+             ((64, 64, 40), dict(resize="128,128,up", filters=["gamma=1.3"]), True),
+             ((33, 21, 3), dict(), True)]
+    for (cw, ch, n), rq, destructive in cases:
+        frames = _random_gif(rng, cw, ch, n)
+        canvases = o.gif_expand(frames, cw, ch, destructive)
+        code, step, plan = gpu.try_plan(cw, ch, 4, api.Config(), **rq)
+        assert code == 0
+        try:
+            before = gpu.launch_count()
+            outs = gpu.gif_album(frames, cw, ch, destructive, plan)
+            launches = gpu.launch_count() - before
+        finally:
+            plan.close()
+        assert launches <= 1 + 4 * plan.passes + 4, (n, launches)      # expansion + one grouped launch per lane chunk and pass
+        for k, (got, canvas) in enumerate(zip(outs, canvases)):
+            c2, _, ref = _oracle(orc, canvas, rq, {})
+            assert c2 == 0
+            _assert_same(got, ref, (rq, k), False)
+
+
+def test_gif_album_rejects_mismatched_plans(gpu):
+    rng = np.random.default_rng(5)
+    frames = _random_gif(rng, 40, 30, 2)
+    code, _, plan = gpu.try_plan(41, 30, 4, api.Config(), resize="20")
+    assert code == 0
+    try:
+        with pytest.raises(Exception):
+            gpu.gif_album(frames, 40, 30, True, plan)
+    finally:
+        plan.close()
+
+
+def test_ops_layer_gif_flush(gpu, orc):
+    """imp_FlushAllGif: the operators are recorded on canvas-sized placeholder frames (LoadGIF still creates them), the flush
+    takes its pixels from the pages. Same results as the host-canvas flush and as the oracle; frames with nothing recorded
+    receive their canvas."""
+    rng = np.random.default_rng(31)
+    o = orc.orc()
+    ops = api.OpsLayer(gpu)
+    cw, ch, n = 90, 52, 7
+    frames = _random_gif(rng, cw, ch, n)
+    canvases = o.gif_expand(frames, cw, ch, True)
+    for kw in (dict(resize="45,26", simple=True, filters=["flip=10"]), dict(crop="60px,40px,l,t", filters=["contrast=1.2"]), dict()):
+        place = [np.full((ch, cw, 4), 0xEE, np.uint8) for _ in range(n)]              # never read
+        code, outs = ops.request(place, api.Config(), gif_pages=frames, destructive=True, **kw)
+        assert code == 0 and len(outs) == n
+        outs = [a.copy() for a in outs]                                                # the layer's frames live until its next request
+        host_in = [c.copy() for c in canvases]                                         # untouched frames are returned as views of these
+        code2, want = ops.request(host_in, api.Config(), **kw)
+        assert code2 == 0
+        for k in range(n):
+            ref_k = want[k] if want is not None and len(want) == n else canvases[k]
+            assert np.array_equal(outs[k], ref_k), (kw, k)
+            rq = {a: b for a, b in kw.items()}
+            c3, _, ref = _oracle(orc, canvases[k], rq, {})
+            assert c3 == 0 and np.array_equal(outs[k], ref), (kw, k)
+
+
 def test_gif_expand_and_pack_golden_from_reference(gpu, orc):
     """tests/golden/golden_io_v1.npz — outputs of the reference's own advancedio.c (LoadGIF, IplToFI24/32, RunJob on GIF
     pages): sub-frames with the row[w] over-read, pages without a transparent colour (palette[-1]), every disposal."""

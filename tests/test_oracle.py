@@ -379,3 +379,17 @@ def test_integration_edits_apply_to_the_reference():
     shim = open(os.path.join(here, "ngx_http_imgproc_b200", "dropin", "imp_dropin.c")).read()
     for name in mod.BRIDGE_REPLACED + mod.FILTERS_REPLACED:
         assert re.search(r"^(?:int|void)\s+" + name + r"\s*\(", shim, flags=re.M), name
+    # LoadGIF loses its per-pixel canvas loop (and nothing else) to one imp_AlbumGifPage call
+    asrc = open("/root/reference/advancedio.c").read()
+    aout = mod.patched_advancedio(asrc)
+    load_gif = aout[aout.index("static void LoadGIF("):aout.index("static void LoadSingle(")]
+    assert load_gif.count("imp_AlbumGifPage(result, frameid, isdestructive,") == 1
+    assert "cvSetComponent" not in load_gif and "master[offset]" not in load_gif
+    for kept in ("FreeImage_LockPage(container, frameid)", "FreeImage_GetTransparentIndex(frame)", "FreeImage_ConvertTo8Bits(frame)",
+                 "cvCreateImage(cvSize(canvasW, canvasH), IPL_DEPTH_8U, 4)", "FreeImage_UnlockPage(container, frame, 0)", "if (frameid == page)",
+                 "result->Frames[0] = requested;"):
+        assert kept in load_gif, kept
+    gone = [l for l in asrc.splitlines() if l.strip() and l not in aout]
+    assert 20 <= len(gone) <= 60, len(gone)                            # the loop nest only
+    assert aout[aout.index("static void LoadSingle("):] == asrc[asrc.index("static void LoadSingle("):]
+    assert re.search(r"^int\s+imp_AlbumGifPage\s*\(", shim, flags=re.M)
