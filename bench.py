@@ -458,6 +458,53 @@ def request_latency(cx: Ctx, name: str):
             "cold_over_repeat": cold_t["p50"] / repeat["p50"]}
 
 
+def gif_album_e2e(cx: Ctx, name: str, plans, wl, steps: int):
+    """cfg3 / cfg3nn as the GIF request they describe: the frames enter as PAGES (8-bit palette indices, 1 byte per pixel over
+    PCIe instead of a decoded canvas's 4), are expanded into BGRA canvases on the device (LoadGIF's loop, advancedio.c:195-248)
+    and feed the frame loop there — imp_gpu_gif_album_run_host, pageable pages in, pinned results out, all inside the timed
+    region. Same plan, same output pixels as the e2e leg over decoded canvases (which is D2H-bound for a 2x enlargement, so
+    that leg's number is this one's ceiling); `thumbnails` is the H2D-bound counterpart: the same album shrunk 4x per axis,
+    through pages and through pinned decoded canvases."""
+    api, L, torch = cx.api, cx.L, cx.torch
+    (h, w, c), _, n = wl["jobs"][0]
+    rng = np.random.default_rng(77 + cx.rank)
+    pages = [dict(indices=rng.integers(0, 256, (h, w), dtype=np.uint8), left=0, top=0, dispose=1, key=int(rng.integers(0, 256)),
+                  palette=rng.integers(0, 256, (256, 4), dtype=np.uint8)) for _ in range(n)]
+
+    def timed(fn):
+        fn()
+        l0 = L.launch_count()
+        ts = []
+        for _ in range(steps):
+            cx.barrier()
+            t0 = time.perf_counter(); fn(); ts.append(cx.allmax(time.perf_counter() - t0))
+        return statistics.median(ts), min(ts), int((L.launch_count() - l0) // max(1, steps))
+
+    def pages_job(plan):
+        outs = [torch.empty((plan.out_h, plan.out_w, plan.out_c), dtype=torch.uint8).pin_memory() for _ in range(min(n, 32))]
+        return api.GifAlbumJob(L, pages, w, h, True, plan, [outs[k % len(outs)].numpy() for k in range(n)]), outs
+
+    job, keep = pages_job(plans[0])
+    med, best, launches = timed(lambda: job.run(L))
+    tot = cx.world * job.out_pixels
+    res = {"value": tot / med / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": job.h2d_bytes, "d2h_bytes_per_step": job.d2h_bytes,
+           "jobs_per_step": n, "steps": steps, "best": tot / best / 1e6, "kernel_launches_per_step": launches,
+           "what": "the same request entering as GIF pages (palette indices) instead of decoded BGRA canvases: expanded on the device"}
+    # H2D-bound counterpart: thumbnails of the same album
+    small = L.plan(w, h, 4, api.Config(), resize=f"{w // 4},{h // 4}", simple=(name == "cfg3nn"))
+    tjob, keep2 = pages_job(small)
+    tmed, _, _ = timed(lambda: tjob.run(L))
+    canv = [torch.from_numpy(cv).pin_memory() for cv in L.gif_expand(pages[:32], w, h, True)]
+    couts = [torch.empty((small.out_h, small.out_w, small.out_c), dtype=torch.uint8).pin_memory() for _ in range(32)]
+    hj = api.HostJobs([small] * n, [canv[k % len(canv)].numpy() for k in range(n)], [couts[k % 32].numpy() for k in range(n)])
+    cmed, _, _ = timed(lambda: hj.run(L, n_streams=4))
+    tpix = cx.world * tjob.out_pixels
+    res["thumbnails"] = {"request": f"resize={w // 4},{h // 4}", "pages": {"value": tpix / tmed / 1e6, "unit": "Mpix/s", "ms": tmed * 1e3, "h2d_bytes_per_step": tjob.h2d_bytes},
+                         "decoded_pinned_canvases": {"value": tpix / cmed / 1e6, "unit": "Mpix/s", "ms": cmed * 1e3, "h2d_bytes_per_step": n * w * h * 4}}
+    small.close()
+    return res
+
+
 def h2d_ceiling(cx: Ctx):
     """Bare pinned cudaMemcpyAsync H2D, all ranks at once: what the box gives the e2e legs to work with."""
     torch = cx.torch
@@ -578,6 +625,8 @@ def main():
         r = measure(cx, nm, st, a.warmup, max(3, a.e2e_steps // 2), shard="weak", seed_off=17)
         e = strip_private(r)
         e["config"] = config_dict(nm, r["_wl"])
+        if nm in ("cfg3", "cfg3nn") and a.e2e_steps > 0:
+            e["e2e_gif_pages"] = gif_album_e2e(cx, nm, r["_plans"], r["_wl"], max(3, a.e2e_steps // 2))
         if world == 1 and not a.no_cpu:
             e["cpu_baseline"] = cpu_baseline(nm, a.scale, cores)
         extra_out[nm] = e

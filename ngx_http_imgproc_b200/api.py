@@ -201,16 +201,7 @@ class Library:
 
     def gif_album(self, frames, cw: int, ch: int, destructive: bool, plan: "Plan", outs=None, n_streams: int = 4):
         """imp_gpu_gif_album_run_host: pages up as indices, canvases expanded on the device, `plan` over every frame."""
-        arr, keep = self.gif_pages(frames)
-        n = len(frames)
-        if outs is None:
-            outs = [np.empty((plan.out_h, plan.out_w, plan.out_c), np.uint8) for _ in range(n)]
-        plans = (C.c_void_p * n)(*[plan.h] * n)
-        dsts = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
-        steps = (C.c_int * n)(*[o.strides[0] for o in outs])
-        self.lib.imp_gpu_gif_album_run_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-        self.check(self.lib.imp_gpu_gif_album_run_host(arr, n, cw, ch, 1 if destructive else 0, plans, dsts, steps, n_streams))
-        return outs
+        return GifAlbumJob(self, frames, cw, ch, destructive, plan, outs).run(self, n_streams)
 
     def gif_expand(self, frames, cw: int, ch: int, destructive: bool):
         """LoadGIF's canvas expansion (advancedio.c:195-248) on the device; frames as for gif_pages."""
@@ -349,6 +340,32 @@ class HostJobs:
     @staticmethod
     def wait(lib: Library, ticket):
         lib.check(lib.lib.imp_gpu_batch_wait(ticket))
+
+
+class GifAlbumJob:
+    """imp_gpu_gif_album_run_host with its argument arrays built once: `pages` as Library.gif_pages takes them, one plan for
+    every frame (a frame whose entry in `plans` is None only takes part in the disposal replay), outputs given or allocated."""
+
+    def __init__(self, lib: Library, pages, cw: int, ch: int, destructive: bool, plans, outs=None):
+        n = self.n = len(pages)
+        plans = list(plans) if isinstance(plans, (list, tuple)) else [plans] * n
+        self.arr, self.keep = Library.gif_pages(pages)
+        if outs is None:
+            outs = [None if p is None else np.empty((p.out_h, p.out_w, p.out_c), np.uint8) for p in plans]
+        self.outs, self.plans = outs, plans
+        self.P = (C.c_void_p * n)(*[None if p is None else p.h for p in plans])
+        self.D = (C.c_void_p * n)(*[None if o is None else o.ctypes.data for o in outs])
+        self.DS = (C.c_int * n)(*[0 if o is None else o.strides[0] for o in outs])
+        self.geom = (cw, ch, 1 if destructive else 0)
+        self.h2d_bytes = sum(int(np.asarray(f["indices"]).size) + 1024 for f in pages)
+        self.d2h_bytes = sum(0 if p is None else p.out_w * p.out_h * p.out_c for p in plans)
+        self.out_pixels = sum(0 if p is None else p.out_w * p.out_h for p in plans)
+        lib.lib.imp_gpu_gif_album_run_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+
+    def run(self, lib: Library, n_streams=4):
+        cw, ch, d = self.geom
+        lib.check(lib.lib.imp_gpu_gif_album_run_host(self.arr, self.n, cw, ch, d, self.P, self.D, self.DS, n_streams))
+        return self.outs
 
 
 def farm_assign(lib: Library, plans: List[Plan], n_gpus: int, policy=FARM_ROUND_ROBIN) -> List[int]:

@@ -1231,16 +1231,29 @@ static int gif_validate(const imp_gpu_gif_frame* frames, int n, size_t* meta_byt
 }
 static void gif_pack(const imp_gpu_gif_frame* frames, int n, size_t meta_bytes, uint8_t* h_buf, const uint8_t* d_buf) {
     ImpGifFrame* meta = reinterpret_cast<ImpGifFrame*>(h_buf);
+    std::vector<size_t> offs((size_t)n);
     size_t off = meta_bytes + (size_t)n * 1024;
-    for (int f = 0; f < n; f++) {
-        const imp_gpu_gif_frame& g = frames[f];
-        memcpy(h_buf + meta_bytes + (size_t)f * 1024, g.palette, 1024);
-        memcpy(h_buf + off, g.indices, (size_t)g.pitch * g.height);
-        meta[f].indices = d_buf + off; meta[f].palette = d_buf + meta_bytes + (size_t)f * 1024;
-        meta[f].pitch = g.pitch; meta[f].w = g.width; meta[f].h = g.height; meta[f].left = g.left; meta[f].top = g.top;
-        meta[f].dispose = g.dispose; meta[f].key = g.transparency_key; meta[f].pad_ = 0;
-        off += ((size_t)g.pitch * g.height + 15) & ~size_t(15);
+    for (int f = 0; f < n; f++) { offs[f] = off; off += ((size_t)frames[f].pitch * frames[f].height + 15) & ~size_t(15); }
+    auto pack = [&](int f0, int f1) {
+        for (int f = f0; f < f1; f++) {
+            const imp_gpu_gif_frame& g = frames[f];
+            memcpy(h_buf + meta_bytes + (size_t)f * 1024, g.palette, 1024);
+            memcpy(h_buf + offs[f], g.indices, (size_t)g.pitch * g.height);
+            meta[f].indices = d_buf + offs[f]; meta[f].palette = d_buf + meta_bytes + (size_t)f * 1024;
+            meta[f].pitch = g.pitch; meta[f].w = g.width; meta[f].h = g.height; meta[f].left = g.left; meta[f].top = g.top;
+            meta[f].dispose = g.dispose; meta[f].key = g.transparency_key; meta[f].pad_ = 0;
+        }
+    };
+    // the pages are pageable host memory: one core copies ~10 GB/s, so a long animation (tens of MB) is split over four
+    const int parts = (off >= (8u << 20) && n >= 8) ? 4 : 1;
+    if (parts == 1) { pack(0, n); return; }
+    std::thread helpers[3];
+    for (int t = 1; t < parts; t++) {
+        const int f0 = (int)((long long)n * t / parts), f1 = (int)((long long)n * (t + 1) / parts);
+        try { helpers[t - 1] = std::thread(pack, f0, f1); } catch (...) { pack(f0, f1); }
     }
+    pack(0, n / parts);
+    for (int t = 1; t < parts; t++) if (helpers[t - 1].joinable()) helpers[t - 1].join();
 }
 
 int imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
