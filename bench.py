@@ -523,8 +523,24 @@ def h2d_ceiling(cx: Ctx):
         return n * reps / dt / 1e9
     run(st[:1], 8)
     one = run(st[:1]); four = run(st)
+    # both directions at once (what a same-size request — cfg4, or cfg3's 4x larger results — loads the link with)
+    back = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(4)]
+    def duplex(reps=32):
+        cx.barrier()
+        t0 = time.perf_counter()
+        for r in range(reps):
+            with torch.cuda.stream(st[0]):
+                ds[r % 4].copy_(hs[r % 4], non_blocking=True)
+            with torch.cuda.stream(st[1]):
+                back[r % 4].copy_(ds[4 + r % 4], non_blocking=True)
+        torch.cuda.synchronize()
+        dt = cx.allmax(time.perf_counter() - t0)
+        return n * reps / dt / 1e9
+    duplex(4)
+    both = duplex()
     return {"what": "32 MB pinned -> device copies (8 buffers cycled), all ranks concurrently, GB/s per rank: the box's ceiling for the e2e legs",
-            "one_stream": one, "four_streams": four, "aggregate_gbs": max(one, four) * cx.world}
+            "one_stream": one, "four_streams": four, "aggregate_gbs": max(one, four) * cx.world,
+            "duplex_each_direction": both, "duplex_what": "H2D and D2H of 32 MB buffers issued together on two streams: GB/s sustained in EACH direction"}
 
 
 def strip_private(d):

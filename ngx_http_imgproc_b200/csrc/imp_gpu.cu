@@ -90,6 +90,7 @@ namespace {
 
 struct Lane {            // one in-flight chunk of host jobs of the end-to-end path
     cudaStream_t st = nullptr;
+    cudaEvent_t up_done = nullptr;               // this chunk's uploads have been issued up to here: the next chunk's wait for it
     Buf d_in, d_out, d_stage;                    // device: re-pitched crop windows, results, linear landing zone of short rows
     Buf h_in, h_out;                             // pinned staging for host buffers that are not page-locked
     imp_gpu_batch batch;                         // the chunk's job table, scratch and tensor maps
@@ -659,7 +660,8 @@ int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
             // A 2-D host-to-device copy pays ~0.15 us per row whatever its width (measured: 3.5 KB rows move at 23 GB/s,
             // 14 KB rows at the link's 54 GB/s). Short rows therefore travel as ONE linear copy of the rows the window
             // touches (full width) and a small kernel extracts / re-pitches the window on the device.
-            if (J.src_steps[i] <= 8192) {
+            // (a window that IS the frame's contiguous rows is one linear copy whatever its row length)
+            if (J.src_steps[i] <= 8192 || ((size_t)J.src_steps[i] == (size_t)l.in_pitch && p->win_x == 0 && in_row == (size_t)l.in_pitch)) {
                 l.linear = true;
                 l.lin_bytes = (size_t)(p->win_h - 1) * J.src_steps[i] + (size_t)p->win_x * p->src_c + in_row;
                 const bool direct = J.src_steps[i] == l.in_pitch && p->win_x == 0;
@@ -675,6 +677,10 @@ int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
         (r = L.h_in.grow(hin_total, true)) || (r = L.h_out.grow(hout_total, true))) return r;
     imp_gpu_batch& B = L.batch;
     B.items.clear(); B.dirty = true;
+    // window extractions of the linear uploads: launched after ALL copies of the chunk, so that a kernel never sits between
+    // two copies of this stream and idles the copy engine
+    struct Repitch { const uint8_t* src; int sp; uint8_t* dst; int dp, row_bytes, rows; };
+    std::vector<Repitch> repitch;
     for (int k = 0; k < m; k++) {
         const int i = first + k;
         imp_gpu_plan* p = J.plans[i];
@@ -717,7 +723,7 @@ int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
             } else {
                 uint8_t* stage = L.d_stage.p + l.stage_off;
                 CK(cudaMemcpyAsync(stage, h_lin, l.lin_bytes, cudaMemcpyHostToDevice, L.st));
-                CK(imp_launch_repitch(stage + (size_t)p->win_x * sc, J.src_steps[i], d_in, l.in_pitch, (int)in_row, p->win_h, L.st));
+                repitch.push_back(Repitch{stage + (size_t)p->win_x * sc, J.src_steps[i], d_in, l.in_pitch, (int)in_row, p->win_h});
             }
         } else {
             CK(cudaMemcpy2DAsync(d_in, l.in_pitch, win, J.src_steps[i], in_row, p->win_h, cudaMemcpyHostToDevice, L.st));
@@ -726,6 +732,8 @@ int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
         const uint8_t* biased = d_in - ((size_t)p->win_y * l.in_pitch + (size_t)p->win_x * sc);
         B.items.push_back(imp_gpu_batch::Item{p, biased, l.in_pitch, L.d_out.p + l.out_off, l.out_pitch});
     }
+    if (L.up_done) CK(cudaEventRecord(L.up_done, L.st));
+    for (const Repitch& q : repitch) CK(imp_launch_repitch(q.src, q.sp, q.dst, q.dp, q.row_bytes, q.rows, L.st));
     if ((r = batch_compile(&B, L.st))) return r;
     if ((r = batch_launch_steps(&B, L.st))) return r;
     for (int k = 0; k < m; k++) {
@@ -754,21 +762,35 @@ int run_host_chunked_locked(const HostJobs& J, int n_streams, cudaEvent_t after)
         if (!L) return IMP_ERROR_MALLOC_FAILED;
         cudaError_t e = cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking);
         if (e != cudaSuccess) { delete L; return fail(e, "cudaStreamCreateWithFlags", __LINE__); }
+        e = cudaEventCreateWithFlags(&L->up_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) { cudaStreamDestroy(L->st); delete L; return fail(e, "cudaEventCreateWithFlags", __LINE__); }
         ctx.lanes.push_back(L);
     }
     int result = IMP_OK, chunk = 0, i = 0;
     if (after) for (int k = 0; k < n_streams; k++) CK(cudaStreamWaitEvent(ctx.lanes[k]->st, after, 0));
+    // Uploads of different lanes issued together are time-sliced by the copy engines: every chunk's upload then ends at the
+    // END of all uploads and nothing overlaps the way back (a same-size request moved 26 GB/s per direction where the duplex
+    // link gives 48). Each chunk's uploads therefore wait for the previous chunk's — they run back to back in chunk order,
+    // kernels and downloads of earlier chunks alongside — and a call is cut into at least 2 chunks per lane when its bytes
+    // allow (>= 4 MB per chunk), so that the pipeline has stages to overlap. IMP_GPU_CHAIN_H2D=0 turns both off (tuning knob).
+    static const bool chain = [] { const char* e = getenv("IMP_GPU_CHAIN_H2D"); return !e || atoi(e) != 0; }();
+    size_t total_bytes = 0;
+    for (int k = 0; k < J.n; k++) if (J.plans[k]) total_bytes += (size_t)align16(J.plans[k]->win_w * J.plans[k]->src_c) * J.plans[k]->win_h + (size_t)J.plans[k]->out_w * J.plans[k]->out_c * J.plans[k]->out_h;
+    const size_t chunk_bytes = chain ? std::min(kChunkBytes, std::max<size_t>(4u << 20, total_bytes / (2 * (size_t)n_streams))) : kChunkBytes;
+    Lane* prev = nullptr;
     while (i < J.n && result == IMP_OK) {
         Lane& L = *ctx.lanes[chunk % n_streams];
         if ((result = lane_finish(L, J))) break;
+        if (chain && prev && prev != &L && !J.src_device) CK(cudaStreamWaitEvent(L.st, prev->up_done, 0));
+        prev = &L;
         int e = i; size_t bytes = 0;
         // small batches are spread over the lanes instead of filling one chunk, so that copies and kernels still overlap
         const int max_jobs = std::max(1, std::min(kChunkJobs, (J.n + n_streams - 1) / n_streams));
         while (e < J.n && e - i < max_jobs) {
             const imp_gpu_plan* p = J.plans[e];
             if (!p) break;
-            const size_t need = (size_t)align16(p->win_w * p->src_c) * p->win_h;
-            if (e > i && bytes + need > kChunkBytes) break;
+            const size_t need = (size_t)align16(p->win_w * p->src_c) * p->win_h + (chain ? (size_t)p->out_w * p->out_c * p->out_h : 0);
+            if (e > i && bytes + need > chunk_bytes) break;
             bytes += need; e++;
         }
         if (e == i) { result = IMP_ERROR_INVALID_ARGS; break; }
@@ -863,6 +885,7 @@ void imp_gpu_shutdown(void) {
                 L->d_in.release(false); L->d_out.release(false); L->d_stage.release(false);
                 L->h_in.release(true); L->h_out.release(true);
                 batch_release(&L->batch);
+                if (L->up_done) cudaEventDestroy(L->up_done);
                 if (L->st) cudaStreamDestroy(L->st);
                 delete L;
             }

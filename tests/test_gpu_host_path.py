@@ -318,3 +318,35 @@ def test_large_frames_and_many_tiny_jobs(gpu):
         assert np.array_equal(d, p.run_host(im))
     for p in plans:
         p.close()
+
+
+def test_results_with_unaligned_rows(gpu, orc):
+    """Results whose rows are not a multiple of 16 bytes (the device pitch is): pageable destinations padded like an IplImage,
+    dense and strided pinned ones, a one-pixel-wide column of 90000 rows — the 2-D copies back deliver the oracle's bytes.
+    (Packing such rows densely on the device for ONE linear D2H was measured on B200: no gain, the D2H engine takes pitched
+    rows at full rate — unlike H2D of short rows — and same-size requests are bound by the duplex link, scratch/dense_ab.py.)"""
+    import torch
+    kw = dict(allow_experiments=True, max_filters=8, max_w=0, max_h=0)
+    cases = [((400, 1001, 3), dict(filters=["flip=10"])), ((611, 333, 3), dict(filters=["rotate=90", "gamma=1.3"])),
+             ((900, 1203, 3), dict(resize="601,450")), ((300, 500, 4), dict(crop="333px,290px,3px,3px")),
+             ((120, 77, 3), dict(filters=["flip=01"])), ((1000, 999, 3), dict(filters=["blur=1.1"]))]
+    imgs, plans, outs, keep, refs = [], [], [], [], []
+    for k, (shape, rq) in enumerate(cases * 2):
+        im = smooth_image(50 + k, *shape)
+        p = gpu.plan(shape[1], shape[0], shape[2], api.Config(**kw), **rq)
+        row = p.out_w * p.out_c
+        if k < len(cases):                                        # pageable destination (an IplImage: rows padded to 4 bytes)
+            o = np.zeros((p.out_h, (row + 3) & ~3), np.uint8)
+        else:                                                     # pinned: dense for even k, strided (2-D copy) for odd k
+            t = torch.zeros((p.out_h, row + (0 if k % 2 == 0 else 5)), dtype=torch.uint8).pin_memory()
+            keep.append(t); o = t.numpy()
+        imgs.append(im); plans.append(p); outs.append(o); refs.append(_oracle(orc, im, rq, kw)[2])
+    tall = np.ascontiguousarray(smooth_image(9, 90000, 8, 3)[:, :1])          # 1 x 90000 column: 3-byte rows, 270 KB
+    tp = gpu.plan(1, 90000, 3, api.Config(**kw), filters=["flip=01"])
+    tout = np.zeros((90000, 4), np.uint8)
+    api.run_host_batch(gpu, plans + [tp], imgs + [tall], outs + [tout], n_streams=3)
+    for p, o, r, (shape, rq) in zip(plans, outs, refs, cases * 2):
+        _same(o[:, :p.out_w * p.out_c].reshape(p.out_h, p.out_w, p.out_c), r, rq)
+    _same(tout[:, :3].reshape(90000, 1, 3), _oracle(orc, tall, dict(filters=["flip=01"]), kw)[2], "column")
+    for p in plans + [tp]:
+        p.close()
