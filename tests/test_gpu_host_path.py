@@ -350,3 +350,72 @@ def test_results_with_unaligned_rows(gpu, orc):
     _same(tout[:, :3].reshape(90000, 1, 3), _oracle(orc, tall, dict(filters=["flip=01"]), kw)[2], "column")
     for p in plans + [tp]:
         p.close()
+
+
+def test_concurrent_host_threads_share_one_device(gpu, orc):
+    """Several host threads (ctypes drops the GIL inside the library) drive the same device at once through every host entry
+    point — single requests, chunked batches, GIF albums, the operator layer, plan creation with cache hits, misses and
+    evictions: every result equals the one the same request gives alone."""
+    import threading
+    kw = dict(allow_experiments=True, max_filters=8, max_w=0, max_h=0)
+    cfg = api.Config(**kw)
+    rqs = [dict(resize="100,60"), dict(filters=["blur=1.5", "gamma=1.2"]), dict(crop="150px,100px,10px,5px", filters=["vignette=0.7"]),
+           dict(resize="64,64", filters=["blur=6", "kelvin=1"]), dict(filters=["rotate=270", "modulate=0,0,100", "colorize=704214,0.6"]),
+           dict(resize="333,200,up"), dict(resize="333,200,up", simple=True), dict(resize="90,70", filters=["gotham=1"])]
+    imgs = [smooth_image(70 + i, 120 + 7 * i, 200 + 9 * i, 3 + (i % 2)) for i in range(8)]
+    want = {}
+    for i, im in enumerate(imgs):
+        for j, rq in enumerate(rqs):
+            want[(i, j)] = gpu.run(im, cfg, **rq)
+    rng = np.random.default_rng(3)
+    pages = []
+    for f in range(12):
+        pages.append(dict(indices=np.ascontiguousarray(rng.integers(0, 16, (40, 64), dtype=np.uint8)), left=0, top=0, dispose=int(rng.integers(0, 4)),
+                          key=int(rng.choice([-1, 0, 3])), palette=rng.integers(0, 256, (256, 4), dtype=np.uint8)))
+    gplan_rq = dict(resize="32,20", filters=["flip=10"])
+    gp = gpu.plan(64, 40, 4, cfg, **gplan_rq)
+    gif_want = [o.copy() for o in gpu.gif_album(pages, 64, 40, True, gp)]
+    gp.close()
+    errors = []
+
+    def worker(t):
+        try:
+            r = np.random.default_rng(100 + t)
+            ops = api.OpsLayer(gpu) if t == 0 else None                 # the operator layer's allocator hooks are process-wide: one user
+            for it in range(25):
+                i, j = int(r.integers(0, len(imgs))), int(r.integers(0, len(rqs)))
+                kind = (it + t) % 4
+                if kind == 0:
+                    got = gpu.run(imgs[i], cfg, **rqs[j])
+                    assert np.array_equal(got, want[(i, j)]), ("run", t, it, i, j)
+                elif kind == 1:
+                    sel = [(int(r.integers(0, len(imgs))), int(r.integers(0, len(rqs)))) for _ in range(9)]
+                    plans = [gpu.plan(imgs[a].shape[1], imgs[a].shape[0], imgs[a].shape[2], cfg, **rqs[b]) for a, b in sel]
+                    outs = [np.zeros((p.out_h, p.out_w, p.out_c), np.uint8) for p in plans]
+                    api.run_host_batch(gpu, plans, [imgs[a] for a, _ in sel], outs, n_streams=2 + t % 3)
+                    for (a, b), o in zip(sel, outs):
+                        assert np.array_equal(o, want[(a, b)]), ("batch", t, it, a, b)
+                    for p in plans:
+                        p.close()
+                elif kind == 2:
+                    p = gpu.plan(64, 40, 4, cfg, **gplan_rq)
+                    outs = gpu.gif_album(pages, 64, 40, True, p)
+                    for a, b in zip(outs, gif_want):
+                        assert np.array_equal(a, b), ("gif", t, it)
+                    p.close()
+                elif ops is not None:
+                    code, outs = ops.request([imgs[i]], cfg, **{k: v for k, v in rqs[j].items()})
+                    assert code == 0 and np.array_equal(outs[0], want[(i, j)]), ("ops", t, it, i, j)
+                else:
+                    # plans of throw-away geometries: cache misses and evictions while the other threads run
+                    for k in range(40):
+                        q = gpu.plan(50 + k + 41 * t, 37 + it, 3, cfg, resize=f"{20 + k},{15 + it % 7}")
+                        q.close()
+        except Exception as e:                                           # noqa: BLE001 — reported by the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in threads: th.start()
+    for th in threads: th.join(timeout=300)
+    assert not errors, errors[:3]
+    assert not any(th.is_alive() for th in threads)
