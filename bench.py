@@ -409,6 +409,28 @@ def measure(cx: Ctx, name: str, steps: int, warmup: int, e2e_steps: int, shard: 
         res["e2e"] = {"value": tot_pix / med / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                       "jobs_per_step": len(h_plans), "steps": e2e_steps, "best": tot_pix / min(times) / 1e6, "worst": tot_pix / max(times) / 1e6,
                       "kernel_launches_per_step": int(e2e_launches), "h2d_gbs_this_rank": h2d / med / 1e9}
+        # the same call with PAGEABLE frames (what cvDecodeImage / cvCreateImage hand RunJob): every window passes through the
+        # lanes' pinned staging on the host cores first, every result back out of it. A 64-job sample.
+        if name != "cfg5":
+            m = min(64, len(h_plans))
+            pg_src, pg_dst = {}, {}
+            ps, pd = [], []
+            for k in range(m):
+                a, b = h_srcs[k], h_dsts[k]
+                if id(a) not in pg_src and len(pg_src) < 16: pg_src[id(a)] = np.array(a, copy=True)
+                if id(b) not in pg_dst and len(pg_dst) < 16: pg_dst[id(b)] = np.empty_like(b)
+                ps.append(pg_src.get(id(a), next(iter(pg_src.values())) if pg_src else a))
+                pd.append(pg_dst.get(id(b), next(iter(pg_dst.values())) if pg_dst else b))
+            pj = api.HostJobs(h_plans[:m], ps, pd)
+            pj.run(L, n_streams=4)
+            pt = []
+            for _ in range(max(3, e2e_steps // 2)):
+                cx.barrier()
+                t0 = time.perf_counter(); pj.run(L, n_streams=4); pt.append(cx.allmax(time.perf_counter() - t0))
+            ppix = cx.world * sum(p.out_w * p.out_h for p in h_plans[:m])
+            res["e2e"]["pageable_frames"] = {"value": ppix / statistics.median(pt) / 1e6, "unit": "Mpix/s", "jobs_per_step": m,
+                                             "what": "same call, pageable numpy frames in and out (staged through pinned memory by the library's copy workers)"}
+            del pj, ps, pd, pg_src, pg_dst
         res["_host"] = (h_plans, h_srcs, h_dsts, pools, outs)           # kept for the latency / farm legs of the caller
     res["_plans"] = plans
     res["_wl"] = wl

@@ -8,8 +8,15 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <unistd.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <list>
 #include <mutex>
 #include <new>
@@ -600,36 +607,137 @@ bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+// Host-side copies between pageable frames and the pinned staging run on several cores at once: one core moves 4-10 GB/s
+// (page-granular source, TLB-bound), a fraction of the link. stage_threads(): the most threads one copy is split over
+// (IMP_GPU_STAGE_THREADS, default 8 or half the cores if fewer); a copy gets one thread per 2 MB up to that.
+int stage_threads() {
+    static const int v = [] {
+        const char* e = getenv("IMP_GPU_STAGE_THREADS");
+        int n = e ? atoi(e) : 0;
+        if (n <= 0) { const unsigned hc = std::thread::hardware_concurrency(); n = (int)std::min<unsigned>(8u, std::max<unsigned>(1u, hc / 2)); }
+        return std::max(1, std::min(n, 32));
+    }();
+    return v;
+}
+int stage_parts(size_t bytes, int items) {
+    return (int)std::max<size_t>(1, std::min<size_t>({(size_t)stage_threads(), bytes >> 20, (size_t)std::max(items, 1)}));
+}
+// The big host-side copies (pageable frame -> pinned staging, pinned staging -> pageable result) use streaming stores: the
+// destination is written once and not read by this core again, so it need not be read into the cache first as a plain
+// memcpy's write-allocate does — on the B200 box one request's 29 MB window went from 2.4 to 1.2 ms, a 64-request batch
+// from 29 to 42 GB/s. IMP_GPU_STAGE_NT=0 falls back to memcpy (tuning knob).
+void copy_stream(uint8_t* dst, const uint8_t* src, size_t n) {
+#if defined(__SSE2__)
+    static const bool nt = [] { const char* e = getenv("IMP_GPU_STAGE_NT"); return !e || atoi(e) != 0; }();
+    if (nt && n >= 4096) {
+        const size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+        if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+        const size_t v = n >> 6;
+        for (size_t i = 0; i < v; i++) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i)), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 32)), d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i), a); _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 32), c); _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 48), d);
+        }
+        _mm_sfence();
+        if (n & 63) memcpy(dst + (v << 6), src + (v << 6), n & 63);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
+// The copy workers: a small persistent pool (spawning threads per copy costs ~50 us each, more than a 2 MB slice takes).
+// Created on first use — after nginx has forked its workers — and again in a child should a process fork later.
+class CopyPool {
+    std::mutex mu; std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    std::vector<std::thread> th;
+    bool stop = false; pid_t owner = 0;
+    void work() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                f = std::move(q.front()); q.pop_front();
+            }
+            f();
+        }
+    }
+public:
+    int ensure(int n) {                      // number of workers available (0: run inline)
+        std::lock_guard<std::mutex> lk(mu);
+        if (owner != getpid()) { for (std::thread& t : th) t.detach(); th.clear(); q.clear(); owner = getpid(); }   // threads do not cross fork()
+        while ((int)th.size() < n) {
+            try { th.emplace_back([this] { work(); }); } catch (...) { break; }
+        }
+        return (int)th.size();
+    }
+    void submit(std::function<void()> f) {
+        { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(f)); }
+        cv.notify_one();
+    }
+    void shutdown() {
+        std::vector<std::thread> old;
+        { std::lock_guard<std::mutex> lk(mu); if (owner != getpid()) { for (std::thread& t : th) t.detach(); th.clear(); } stop = true; old.swap(th); }
+        cv.notify_all();
+        for (std::thread& t : old) if (t.joinable()) t.join();
+        std::lock_guard<std::mutex> lk(mu); stop = false;
+    }
+};
+// never destroyed: its threads may outlive main() when the host does not call imp_gpu_shutdown (joinable std::thread destructors abort)
+CopyPool& g_copy_pool = *new CopyPool;
+
+// fn(i0, i1) over [0, n) cut into `parts` contiguous ranges: the first on the calling thread, the others on the pool
+template <class F> void run_parts(int n, int parts, F fn) {
+    if (parts > 1) parts = std::min(parts, g_copy_pool.ensure(stage_threads() - 1) + 1);
+    if (parts <= 1 || n < parts) { fn(0, n); return; }
+    struct Latch { std::mutex m; std::condition_variable c; int left; } latch;
+    latch.left = parts - 1;
+    for (int t = 1; t < parts; t++) {
+        const int i0 = (int)((long long)n * t / parts), i1 = (int)((long long)n * (t + 1) / parts);
+        g_copy_pool.submit([&latch, &fn, i0, i1] {
+            fn(i0, i1);
+            std::lock_guard<std::mutex> lk(latch.m);
+            if (--latch.left == 0) latch.c.notify_one();
+        });
+    }
+    fn(0, (int)((long long)n / parts));
+    std::unique_lock<std::mutex> lk(latch.m);
+    latch.c.wait(lk, [&] { return latch.left == 0; });
+}
+
 int lane_finish(Lane& L, const HostJobs& J) {
     if (L.pend.empty()) return IMP_OK;
     cudaError_t e = cudaStreamSynchronize(L.st);
     if (e == cudaSuccess) {
         // results for pageable destinations (the frames cvCreateImage hands out) leave the pinned staging here; a 200-frame GIF
-        // is 400 MB of it, so chunks of 8 MB and more are split over up to four threads, whole frames each
-        size_t staged = 0;
-        for (const Lane::Out& o : L.pend) if (o.staged_off >= 0) staged += (size_t)J.plans[o.job]->out_w * J.plans[o.job]->out_c * J.plans[o.job]->out_h;
-        const int parts = staged >= (32u << 20) ? 4 : staged >= (8u << 20) ? 2 : 1;
-        const Lane::Out* pend = L.pend.data(); const int np = (int)L.pend.size();
+        // is 400 MB of it
         const uint8_t* h_out = L.h_out.p;
-        auto unstage = [=, &J](int k0, int k1) {
+        // big frames one after the other, each frame's rows over the threads; the small ones of the chunk shared out whole
+        std::vector<const Lane::Out*> small; size_t small_bytes = 0;
+        for (const Lane::Out& o : L.pend) {
+            if (o.staged_off < 0) continue;
+            const imp_gpu_plan* p = J.plans[o.job];
+            const size_t row = (size_t)p->out_w * p->out_c, bytes = row * p->out_h;
+            if (bytes < (4u << 20)) { small.push_back(&o); small_bytes += bytes; continue; }
+            uint8_t* dst = J.dsts[o.job]; const int step = J.dst_steps[o.job]; const uint8_t* src = h_out + o.staged_off;
+            run_parts(p->out_h, stage_parts(bytes, p->out_h), [=](int y0, int y1) {
+                if ((size_t)step == row) copy_stream(dst + (size_t)y0 * row, src + (size_t)y0 * row, row * (size_t)(y1 - y0));
+                else for (int y = y0; y < y1; y++) copy_stream(dst + (size_t)y * step, src + (size_t)y * row, row);
+            });
+        }
+        const Lane::Out* const* sm = small.data();
+        run_parts((int)small.size(), stage_parts(small_bytes, (int)small.size()), [=, &J](int k0, int k1) {
             for (int k = k0; k < k1; k++) {
-                const Lane::Out& o = pend[k];
-                if (o.staged_off < 0) continue;
+                const Lane::Out& o = *sm[k];
                 const imp_gpu_plan* p = J.plans[o.job];
                 const size_t row = (size_t)p->out_w * p->out_c;
-                for (int y = 0; y < p->out_h; y++) memcpy(J.dsts[o.job] + (size_t)y * J.dst_steps[o.job], h_out + o.staged_off + (size_t)y * row, row);
+                if ((size_t)J.dst_steps[o.job] == row) copy_stream(J.dsts[o.job], h_out + o.staged_off, row * p->out_h);
+                else for (int y = 0; y < p->out_h; y++) copy_stream(J.dsts[o.job] + (size_t)y * J.dst_steps[o.job], h_out + o.staged_off + (size_t)y * row, row);
             }
-        };
-        if (parts == 1 || np < parts) unstage(0, np);
-        else {
-            std::thread helpers[3];
-            for (int t = 1; t < parts; t++) {
-                const int k0 = (int)((long long)np * t / parts), k1 = (int)((long long)np * (t + 1) / parts);
-                try { helpers[t - 1] = std::thread(unstage, k0, k1); } catch (...) { unstage(k0, k1); }
-            }
-            unstage(0, np / parts);
-            for (int t = 1; t < parts; t++) if (helpers[t - 1].joinable()) helpers[t - 1].join();
-        }
+        });
     }
     L.pend.clear();
     if (e != cudaSuccess) return fail(e, "cudaStreamSynchronize", __LINE__);
@@ -695,26 +803,14 @@ int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
         }
         if (!l.src_pinned) {
             // a pageable frame (what cvDecodeImage hands RunJob) goes through the lane's pinned staging, laid out with the
-            // device pitch. One core moves ~10 GB/s, a fifth of the link: windows of 4 MB and more are split over up to four
-            // threads (cfg2's 29 MB window: 2.9 ms -> 0.8 ms before the copy engine even starts)
+            // device pitch, by several cores at once (stage_threads above)
             uint8_t* h = L.h_in.p + l.hin_off;
             const int step = J.src_steps[i], pitch = l.in_pitch;
             auto stage_rows = [=](int y0, int y1) {
-                if ((size_t)step == (size_t)pitch && in_row == (size_t)pitch) memcpy(h + (size_t)y0 * pitch, win + (size_t)y0 * step, (size_t)pitch * (y1 - y0));
-                else for (int y = y0; y < y1; y++) memcpy(h + (size_t)y * pitch, win + (size_t)y * step, in_row);
+                if ((size_t)step == (size_t)pitch && in_row == (size_t)pitch) copy_stream(h + (size_t)y0 * pitch, win + (size_t)y0 * step, (size_t)pitch * (y1 - y0));
+                else for (int y = y0; y < y1; y++) copy_stream(h + (size_t)y * pitch, win + (size_t)y * step, in_row);
             };
-            const size_t bytes = in_row * p->win_h;
-            const int parts = bytes >= (16u << 20) ? 4 : bytes >= (4u << 20) ? 2 : 1;
-            if (parts == 1) stage_rows(0, p->win_h);
-            else {
-                std::thread helpers[3];
-                for (int t = 1; t < parts; t++) {
-                    const int y0 = (int)((long long)p->win_h * t / parts), y1 = (int)((long long)p->win_h * (t + 1) / parts);
-                    try { helpers[t - 1] = std::thread(stage_rows, y0, y1); } catch (...) { stage_rows(y0, y1); }     // no thread to be had: inline
-                }
-                stage_rows(0, (int)((long long)p->win_h / parts));
-                for (int t = 1; t < parts; t++) if (helpers[t - 1].joinable()) helpers[t - 1].join();
-            }
+            run_parts(p->win_h, stage_parts(in_row * p->win_h, p->win_h), stage_rows);
             CK(cudaMemcpyAsync(d_in, h, (size_t)l.in_pitch * p->win_h, cudaMemcpyHostToDevice, L.st));    // already in the device layout
         } else if (l.linear) {
             const uint8_t* h_lin = J.srcs[i] + (size_t)p->win_y * J.src_steps[i];
@@ -873,6 +969,7 @@ int imp_gpu_set_device(int device) {
 }
 
 void imp_gpu_shutdown(void) {
+    g_copy_pool.shutdown();
     cache_clear();                     // cached plans and registered overlays go first: their device memory is still reachable
     imp_wm_registry_clear();
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1261,22 +1358,14 @@ static void gif_pack(const imp_gpu_gif_frame* frames, int n, size_t meta_bytes, 
         for (int f = f0; f < f1; f++) {
             const imp_gpu_gif_frame& g = frames[f];
             memcpy(h_buf + meta_bytes + (size_t)f * 1024, g.palette, 1024);
-            memcpy(h_buf + offs[f], g.indices, (size_t)g.pitch * g.height);
+            copy_stream(h_buf + offs[f], g.indices, (size_t)g.pitch * g.height);
             meta[f].indices = d_buf + offs[f]; meta[f].palette = d_buf + meta_bytes + (size_t)f * 1024;
             meta[f].pitch = g.pitch; meta[f].w = g.width; meta[f].h = g.height; meta[f].left = g.left; meta[f].top = g.top;
             meta[f].dispose = g.dispose; meta[f].key = g.transparency_key; meta[f].pad_ = 0;
         }
     };
-    // the pages are pageable host memory: one core copies ~10 GB/s, so a long animation (tens of MB) is split over four
-    const int parts = (off >= (8u << 20) && n >= 8) ? 4 : 1;
-    if (parts == 1) { pack(0, n); return; }
-    std::thread helpers[3];
-    for (int t = 1; t < parts; t++) {
-        const int f0 = (int)((long long)n * t / parts), f1 = (int)((long long)n * (t + 1) / parts);
-        try { helpers[t - 1] = std::thread(pack, f0, f1); } catch (...) { pack(f0, f1); }
-    }
-    pack(0, n / parts);
-    for (int t = 1; t < parts; t++) if (helpers[t - 1].joinable()) helpers[t - 1].join();
+    // the pages are pageable host memory: a long animation (tens of MB) is packed by several cores (run_parts)
+    run_parts(n, stage_parts(off, n), pack);
 }
 
 int imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canvas_w, int canvas_h, int destructive,
