@@ -653,6 +653,8 @@ class CopyPool {
     std::deque<std::function<void()>> q;
     std::vector<std::thread> th;
     bool stop = false; pid_t owner = 0;
+    // after a fork() the handles name threads that do not exist in this process: they are set aside, never joined or detached
+    void abandon() { if (!th.empty()) new std::vector<std::thread>(std::move(th)); th.clear(); }
     void work() {
         for (;;) {
             std::function<void()> f;
@@ -668,7 +670,7 @@ class CopyPool {
 public:
     int ensure(int n) {                      // number of workers available (0: run inline)
         std::lock_guard<std::mutex> lk(mu);
-        if (owner != getpid()) { for (std::thread& t : th) t.detach(); th.clear(); q.clear(); owner = getpid(); }   // threads do not cross fork()
+        if (owner != getpid()) { abandon(); q.clear(); owner = getpid(); }   // threads do not cross fork()
         while ((int)th.size() < n) {
             try { th.emplace_back([this] { work(); }); } catch (...) { break; }
         }
@@ -680,7 +682,7 @@ public:
     }
     void shutdown() {
         std::vector<std::thread> old;
-        { std::lock_guard<std::mutex> lk(mu); if (owner != getpid()) { for (std::thread& t : th) t.detach(); th.clear(); } stop = true; old.swap(th); }
+        { std::lock_guard<std::mutex> lk(mu); if (owner != getpid()) abandon(); stop = true; old.swap(th); }
         cv.notify_all();
         for (std::thread& t : old) if (t.joinable()) t.join();
         std::lock_guard<std::mutex> lk(mu); stop = false;
