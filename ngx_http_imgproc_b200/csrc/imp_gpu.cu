@@ -812,8 +812,15 @@ int lane_issue(Lane& L, const HostJobs& J, int first, int last) {
                 if ((size_t)step == (size_t)pitch && in_row == (size_t)pitch) copy_stream(h + (size_t)y0 * pitch, win + (size_t)y0 * step, (size_t)pitch * (y1 - y0));
                 else for (int y = y0; y < y1; y++) copy_stream(h + (size_t)y * pitch, win + (size_t)y * step, in_row);
             };
-            run_parts(p->win_h, stage_parts(in_row * p->win_h, p->win_h), stage_rows);
-            CK(cudaMemcpyAsync(d_in, h, (size_t)l.in_pitch * p->win_h, cudaMemcpyHostToDevice, L.st));    // already in the device layout
+            // in slices of rows, each uploaded as soon as it is staged: the copy engine works on slice k while the cores stage
+            // slice k+1 (a lone request — one nginx worker — has no other job's upload to overlap its staging with)
+            const size_t bytes = in_row * p->win_h;
+            const int slices = std::min(p->win_h, (m > 1 || bytes < (16u << 20)) ? 1 : 4);      // cfg2's 29 MB window: 1.16 -> 1.04 ms; smaller ones do not repay the extra dispatches
+            for (int sidx = 0; sidx < slices; sidx++) {
+                const int r0 = (int)((long long)p->win_h * sidx / slices), r1 = (int)((long long)p->win_h * (sidx + 1) / slices);
+                run_parts(r1 - r0, stage_parts(in_row * (size_t)(r1 - r0), r1 - r0), [=](int y0, int y1) { stage_rows(r0 + y0, r0 + y1); });
+                CK(cudaMemcpyAsync(d_in + (size_t)r0 * l.in_pitch, h + (size_t)r0 * l.in_pitch, (size_t)l.in_pitch * (r1 - r0), cudaMemcpyHostToDevice, L.st));    // already in the device layout
+            }
         } else if (l.linear) {
             const uint8_t* h_lin = J.srcs[i] + (size_t)p->win_y * J.src_steps[i];
             if (J.src_steps[i] == l.in_pitch && p->win_x == 0) {
