@@ -100,6 +100,7 @@ int Scanline(IplImage** pointer, char* args) { return imp_record(pointer, "scanl
  * device, straight into the frame loop. One album is in flight per worker (RunJob is synchronous): a single slot. */
 static struct {
     IplImage* last;                 /* Image of the newest registered page: Frames[Count-1] of the album, also after a `page` request */
+    unsigned char stamp[16];        /* written into that placeholder's (never read) pixels: a recycled address cannot pass for it */
     imp_gpu_gif_frame* pages;
     unsigned char** blocks;         /* one malloc per page: palette (1024 bytes) then the index bits */
     int count, cap, destructive;
@@ -141,7 +142,23 @@ int imp_AlbumGifPage(Album* album, int frameid, int isdestructive, const unsigne
     imp_gif.blocks[imp_gif.count++] = block;
     imp_gif.destructive = isdestructive;
     imp_gif.last = album->Frames[frameid].Image;
+    {   /* RunJob may fail between LoadGIF and the flush and release the frames; a later album's frame can then live at the
+         * same address. The placeholder's pixels carry a stamp that an image decoded there would have overwritten. */
+        static unsigned long long serial = 0;
+        int nb = imp_gif.last->imageSize < 16 ? imp_gif.last->imageSize : 16;
+        serial++;
+        memcpy(imp_gif.stamp, "IMPGIFPG", 8);
+        memcpy(imp_gif.stamp + 8, &serial, 8);
+        if (nb > 0 && imp_gif.last->imageData) memcpy(imp_gif.last->imageData, imp_gif.stamp, (size_t)nb);
+    }
     return IMP_OK;
+}
+
+static int imp_gif_is_album(IplImage* last, int count) {
+    int nb;
+    if (!imp_gif.count || imp_gif.last != last || !(imp_gif.count == count || count == 1)) return 0;
+    nb = last->imageSize < 16 ? last->imageSize : 16;
+    return nb <= 0 || !last->imageData || memcmp(last->imageData, imp_gif.stamp, (size_t)nb) == 0;
 }
 
 /* Runs everything recorded for the album's frames (bridge.c:576-656 loops) as fused GPU passes: one batched call.
@@ -153,7 +170,7 @@ int imp_FlushAlbum(Album* album) {
     if (album->Count <= 0) return IMP_OK;
     if (album->Count > 64) { fr = (IplImage**)malloc(sizeof(IplImage*) * (size_t)album->Count); if (!fr) return IMP_ERROR_MALLOC_FAILED; }
     for (k = 0; k < album->Count; k++) fr[k] = album->Frames[k].Image;
-    if (imp_gif.count && imp_gif.last == fr[album->Count - 1] && (imp_gif.count == album->Count || album->Count == 1)) {
+    if (imp_gif_is_album(fr[album->Count - 1], album->Count)) {
         rc = imp_FlushAllGif(fr, album->Count, imp_gif.pages, imp_gif.count, imp_gif.destructive);
         imp_gif_reset();
     } else {

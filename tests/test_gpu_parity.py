@@ -586,6 +586,21 @@ def test_reference_runjob_with_the_gpu_path_dropped_in(gpu, orc):
         else:                                   # format=gif: every frame, through SaveGIF's (stand-in) quantiser
             assert len(raw) > 12 and orc.RefGpu.last_raw == raw, q
         checked += 1
+    # a GIF request that fails AFTER LoadGIF handed its pages over (the frames are released unflushed), then ordinary requests:
+    # the stale page registry of the drop-in must not claim a later album whose frame happens to live at a recycled address
+    blob = orc.Ref.gif_container(io["gifs"][1]["frames"])
+    for bad in ("crop=0,0&format=gif", "resize=0,0&format=gif", "filter-nosuchfilter=1&format=gif"):
+        code, step, _ = orc.Ref.run_job_blob(bad, blob)
+        gcode, gstep, _ = orc.RefGpu.run_job_blob(bad, blob)
+        assert (gcode, gstep) == (code, step) and code != 0, (bad, gcode, gstep, code, step)
+        for (h, w, c) in [(60, 80, 4), (45, 64, 4), (33, 47, 3)]:
+            img = smooth_image(h + 1, h, w, c)
+            q = "resize=31,17&filter-gamma=1.2&format=png"
+            code, step, ref = orc.Ref.run_job(q, img, cfgs[0])
+            gcode, gstep, out = orc.RefGpu.run_job(q, img, cfgs[0])
+            assert (gcode, gstep) == (code, step) and code == 0
+            _assert_same(out, ref, (bad, q, (h, w, c)), False)
+            checked += 1
     assert checked > 150
 
 
