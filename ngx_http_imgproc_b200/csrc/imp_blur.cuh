@@ -189,7 +189,9 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
             hi[c] = __byte_perm(__byte_perm(r[4], r[5], 0x0062), __byte_perm(r[6], r[7], 0x0062), 0x5410);
         }
         const int bx = x0 + x;
-        const int cbx = min(bx, w - 1);                                 // pixels of the tile beyond the frame: computed on a valid pixel, never stored
+        // pixels of a partial tile beyond the frame (up to 31 columns / 63 rows, < IMP_VIGNETTE_MARGIN) run the ops on their own
+        // out-of-frame coordinates and are never stored: position-dependent ops only compare coordinates or index tables
+        // that carry that margin
         // the out-stage address of base pixel (bx, by) is affine in by for this thread's column (cf. StripStore)
         int so0, sstep;
         {
@@ -210,7 +212,7 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
                 px[k].g = ((half ? hi[SC > 1 ? 1 : 0] : lo[SC > 1 ? 1 : 0]) >> sh8) & 255;
                 px[k].r = ((half ? hi[SC > 2 ? 2 : 0] : lo[SC > 2 ? 2 : 0]) >> sh8) & 255;
                 px[k].a = (SC == 4) ? (((half ? hi[SC - 1] : lo[SC - 1]) >> sh8) & 255) : 255;
-                bxs[k] = cbx; bys[k] = min(y0 + 8 * g + 4 * half + k, h - 1);
+                bxs[k] = bx; bys[k] = y0 + 8 * g + 4 * half + k;      // unclamped (see below): affine in k, one add per pixel in the ops
             }
             if (nops) imp_run_ops_n<4, false, NOCOMP>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
             const int ly0 = 8 * g + 4 * half;

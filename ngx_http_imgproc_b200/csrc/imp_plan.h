@@ -117,6 +117,8 @@ inline int imp_cubic_dyn_smem(int sc, int ops_bytes16, int tile_rs, int tile_row
 inline int imp_gather_dyn_smem(int gt, int ops_bytes16, int tile_rs, int tile_rows, int dc) {
     return 128 + ((ops_bytes16 + 127) & ~127) + 2 * ((tile_rs * tile_rows + 127) & ~127) + 6 * gt * 4 + (dc == 4 ? 0 : gt * gt * 3) + 64;
 }
+// vignette mask table: entries beyond the frame's largest |dx|, |dy| (>= the tile kernels' overhang: 64)
+#define IMP_VIGNETTE_MARGIN 64
 #define IMP_BLUR_TW 32
 #define IMP_BLUR_TH 64
 template <int R> struct ImpBlurDims {

@@ -563,7 +563,7 @@ int lower_filter(Lower& L, const char* request, int allow) {
             // by d2 = dx*dx + dy*dy it was half the entries, but the 32 lanes of a warp then hit 32 different sectors of
             // it; row-major in |dx| they read one or two.
             {
-                long long mx = std::max(cx, w - 1 - cx), my = std::max(cy, h - 1 - cy);
+                long long mx = std::max(cx, w - 1 - cx) + IMP_VIGNETTE_MARGIN, my = std::max(cy, h - 1 - cy) + IMP_VIGNETTE_MARGIN;
                 long long entries = (mx + 1) * (my + 1);
                 if (entries <= (16ll << 20)) { o.i[2] = (int)(mx + 1); o.i[3] = (int)(my + 1); }
             }
