@@ -355,7 +355,7 @@ def measure(cx: Ctx, name: str, steps: int, warmup: int, e2e_steps: int, shard: 
     step_ms = [s.elapsed_time(e) for s, e in evs]
     total_pix = cx.allsum(out_pix) if shard != "weak" else cx.world * out_pix
     res = {"ms_per_step": total_ms / steps, "value": total_pix * steps / (total_ms / 1e3) / 1e6, "unit": "Mpix/s",
-           "jobs_this_rank": len(mine), "gpu_launches": int(launches), "kernel_launches_per_step": batch.launches_per_run}
+           "jobs_this_rank": len(mine), "gpu_launches": int(launches), "kernel_launches_per_step": batch.launches_per_run, "steps": steps}
     achieved = algo_bytes / (float(np.mean(step_ms)) / 1e3) / 1e9
     traffic = None
     try:
@@ -659,7 +659,9 @@ def main():
             cx.cpu_barrier()
             extra_out[nm] = e
             continue
-        st = a.steps if nm != "cfg5" else max(3, a.steps // 4)
+        # sub-millisecond steps: four times the steps, so that one host-side scheduling blip between two launches (seen once: a
+        # 20-step cfg3 region of 10.5 ms measured 12.4) does not move the mean; cfg5's 70 ms steps need fewer
+        st = a.steps * 4 if nm != "cfg5" else max(3, a.steps // 4)
         r = measure(cx, nm, st, a.warmup, max(3, a.e2e_steps // 2), shard="weak", seed_off=17)
         e = strip_private(r)
         e["config"] = config_dict(nm, r["_wl"])
