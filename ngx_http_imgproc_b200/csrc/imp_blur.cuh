@@ -205,13 +205,15 @@ imp_blur_tile_kernel(const ImpJob* __restrict__ jobs, int first, int count, cons
         for (int half = 0; half < 2; half++) {
             ImpPx px[4];
             int bxs[4], bys[4];
+            const uint32_t wb = half ? hi[0] : lo[0], wg = half ? hi[SC > 1 ? 1 : 0] : lo[SC > 1 ? 1 : 0];
+            const uint32_t wr = half ? hi[SC > 2 ? 2 : 0] : lo[SC > 2 ? 2 : 0], wa = half ? hi[SC - 1] : lo[SC - 1];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int sh8 = 8 * k;
-                px[k].b = ((half ? hi[0] : lo[0]) >> sh8) & 255;
-                px[k].g = ((half ? hi[SC > 1 ? 1 : 0] : lo[SC > 1 ? 1 : 0]) >> sh8) & 255;
-                px[k].r = ((half ? hi[SC > 2 ? 2 : 0] : lo[SC > 2 ? 2 : 0]) >> sh8) & 255;
-                px[k].a = (SC == 4) ? (((half ? hi[SC - 1] : lo[SC - 1]) >> sh8) & 255) : 255;
+                // byte k of the packed rows, zero-extended: one PRMT instead of a shift and a mask
+                px[k].b = (int)__byte_perm(wb, 0u, 0x4440u + k);
+                px[k].g = (int)__byte_perm(wg, 0u, 0x4440u + k);
+                px[k].r = (int)__byte_perm(wr, 0u, 0x4440u + k);
+                px[k].a = (SC == 4) ? (int)__byte_perm(wa, 0u, 0x4440u + k) : 255;
                 bxs[k] = bx; bys[k] = y0 + 8 * g + 4 * half + k;      // unclamped (see below): affine in k, one add per pixel in the ops
             }
             if (nops) imp_run_ops_n<4, false, NOCOMP>(px, oc, bxs, bys, reinterpret_cast<const ImpOp*>(s_ops), nops, s_ops + nops * sizeof(ImpOp), job.wm, job.wm_pitch, job.wm_c);
