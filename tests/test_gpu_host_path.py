@@ -419,3 +419,33 @@ def test_concurrent_host_threads_share_one_device(gpu, orc):
     for th in threads: th.join(timeout=300)
     assert not errors, errors[:3]
     assert not any(th.is_alive() for th in threads)
+
+
+def test_pageable_frames_at_odd_addresses_and_strides(gpu, orc):
+    """The copy workers' streaming copies (16-byte stores after an unaligned head, memcpy tail): pageable sources and
+    destinations that start at odd addresses, rows of 4 KB and more with odd strides, single requests (row slices) and
+    batches, against numpy identities."""
+    cfg = api.Config(max_w=0, max_h=0)
+    rng = np.random.default_rng(12)
+    for (h, w, c, off, pad) in [(700, 1501, 3, 3, 5), (2500, 2300, 4, 1, 7), (3000, 4000, 3, 13, 0), (64, 5000, 3, 7, 11)]:
+        step = w * c + pad
+        raw = rng.integers(0, 256, off + step * h + 64, dtype=np.uint8)
+        src = np.lib.stride_tricks.as_strided(raw[off:], shape=(h, w, c), strides=(step, c, 1))
+        for rq, ref in ((dict(filters=["flip=11"]), src[::-1, ::-1]), (dict(crop=f"{w - 7}px,{h - 5}px,4px,3px"), src[3:h - 2, 4:w - 3])):
+            p = gpu.plan(w, h, c, cfg, **rq)
+            orow = p.out_w * p.out_c
+            ostep = orow + pad + 2
+            oraw = np.zeros(off + 5 + ostep * p.out_h + 64, np.uint8)
+            dst = np.lib.stride_tricks.as_strided(oraw[off + 5:], shape=(p.out_h, p.out_w, p.out_c), strides=(ostep, p.out_c, 1))
+            # one request (staged and uploaded in row slices when the window is 16 MB or more) ...
+            gpu.check(gpu.lib.imp_gpu_run_host(p.h, src.ctypes.data, step, dst.ctypes.data, ostep))
+            assert np.array_equal(dst, ref), (h, w, c, rq)
+            # ... and a batch of three into fresh destinations
+            oraws = [np.zeros_like(oraw) for _ in range(3)]
+            dsts = [np.lib.stride_tricks.as_strided(o[off + 5:], shape=(p.out_h, p.out_w, p.out_c), strides=(ostep, p.out_c, 1)) for o in oraws]
+            api.run_host_batch(gpu, [p] * 3, [src] * 3, dsts, n_streams=2)
+            for d, o in zip(dsts, oraws):
+                assert np.array_equal(d, ref), (h, w, c, rq, "batch")
+                gap = np.lib.stride_tricks.as_strided(o[off + 5 + orow:], shape=(p.out_h - 1, ostep - orow), strides=(ostep, 1))
+                assert not gap.any() and not o[:off + 5].any()              # nothing written between or before the rows
+            p.close()
