@@ -187,6 +187,20 @@ int plan_to_device(imp_gpu_plan* plan) {
         CK(imp_build_vignette_table(tab, op->i[2], op->i[3], op->f[0], op->f[1], ctx.stream));
         const unsigned long long v = (unsigned long long)(uintptr_t)tab;
         op->i[4] = (int)(unsigned)(v & 0xffffffffu); op->i[5] = (int)(unsigned)(v >> 32);
+        // With a table the device never takes the per-pixel path, so this device's copy of the op carries the lookup's affine
+        // form instead of the centre and the frame map (imp_pixel.cuh, IMP_OP_VIGNETTE): dx = ox + xa*bx + xb*by,
+        // dy = oy + ya*bx + yb*by, where dx = cx - x, x = flipx ? w-1-u : u, u = swap ? by : bx (and likewise dy)
+        {
+            const ImpFrameMap m = op->map;
+            const int sx = m.flipx ? 1 : -1, ox = op->i[0] - (m.flipx ? m.w - 1 : 0);
+            const int sy = m.flipy ? 1 : -1, oy = op->i[1] - (m.flipy ? m.h - 1 : 0);
+            op->i[0] = ox; op->i[1] = oy;
+            op->map.swap = m.swap ? 0 : sx;      // xa
+            op->map.flipx = m.swap ? sx : 0;     // xb
+            op->map.flipy = m.swap ? sy : 0;     // ya
+            op->map.w = m.swap ? 0 : sy;         // yb
+            op->map.h = 0;
+        }
     }
     if (blob_total) CK(cudaMemcpyAsync(pd.arena, ctx.h_up.p, blob_total, cudaMemcpyHostToDevice, ctx.stream));
     if (plan->wm) { rc = wm_to_device(plan->wm.get(), d); if (rc) return rc; }

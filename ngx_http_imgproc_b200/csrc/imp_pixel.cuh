@@ -399,15 +399,14 @@ IMP_HD void imp_run_ops_n(ImpPx (&px)[N], int oc, const int (&bx)[N], const int 
                 const float* tab = reinterpret_cast<const float*>(((unsigned long long)(unsigned)op.i[5] << 32) | (unsigned)op.i[4]);
                 if (tab) {           // mask[|dy|][|dx|], tabulated per plan by imp_vignette_table_kernel with the code of imp_vignette_mask
                     const int stride = op.i[2];
-                    // dx = cx - x with x = flipx ? w-1-u : u and u = swap ? by : bx, i.e. affine in the base coordinates:
-                    // dx = ox + xa*bx + xb*by, dy = oy + ya*bx + yb*by with the selects paid once per op, so that a caller
-                    // whose pixels share a column (or a row) leaves one add per pixel here. The table carries
-                    // IMP_VIGNETTE_MARGIN entries beyond the frame in both directions: tile kernels may evaluate (never
-                    // store) pixels of a partial tile that lie up to that far outside.
-                    const int swap = op.map.swap;
-                    const int sx = op.map.flipx ? 1 : -1, ox = op.i[0] - (op.map.flipx ? op.map.w - 1 : 0);
-                    const int sy = op.map.flipy ? 1 : -1, oy = op.i[1] - (op.map.flipy ? op.map.h - 1 : 0);
-                    const int xa = swap ? 0 : sx, xb = swap ? sx : 0, ya = swap ? sy : 0, yb = swap ? 0 : sy;
+                    // dx = cx - x with x = flipx ? w-1-u : u and u = swap ? by : bx is affine in the base coordinates:
+                    // dx = ox + xa*bx + xb*by, dy = oy + ya*bx + yb*by. The runtime stores that form into the device copy
+                    // of the op when it attaches the table (plan_to_device: i[0..1] = ox, oy; the map's fields = xa, xb, ya,
+                    // yb), so nothing is derived here, and a caller whose pixels share a column (or a row) leaves one add
+                    // per pixel. The table carries IMP_VIGNETTE_MARGIN entries beyond the frame in both directions: tile
+                    // kernels may evaluate (never store) pixels of a partial tile that lie up to that far outside.
+                    const int ox = op.i[0], oy = op.i[1];
+                    const int xa = op.map.swap, xb = op.map.flipx, ya = op.map.flipy, yb = op.map.w;
                     float mask[N];
 #pragma unroll
                     for (int n = 0; n < N; n++) {
