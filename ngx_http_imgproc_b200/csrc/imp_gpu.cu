@@ -713,11 +713,17 @@ template <class F> void run_parts(int n, int parts, F fn) {
     latch.left = parts - 1;
     for (int t = 1; t < parts; t++) {
         const int i0 = (int)((long long)n * t / parts), i1 = (int)((long long)n * (t + 1) / parts);
-        g_copy_pool.submit([&latch, &fn, i0, i1] {
+        try {
+            g_copy_pool.submit([&latch, &fn, i0, i1] {
+                fn(i0, i1);
+                std::lock_guard<std::mutex> lk(latch.m);
+                if (--latch.left == 0) latch.c.notify_one();
+            });
+        } catch (...) {                        // no memory for the task: this range runs here; the latch must not be left waiting
             fn(i0, i1);
             std::lock_guard<std::mutex> lk(latch.m);
-            if (--latch.left == 0) latch.c.notify_one();
-        });
+            --latch.left;
+        }
     }
     fn(0, (int)((long long)n / parts));
     std::unique_lock<std::mutex> lk(latch.m);
