@@ -19,6 +19,7 @@
  *   void BlendWithPaper(IplImage*)           filters.c:666 imp_BlendWithPaper
  *   gray->BGR block                          bridge.c:613-618  implicit (a 1-channel frame leaves imp_Flush as BGR, also when nothing was recorded)
  *   (none)                                   before bridge.c:659   imp_Flush / imp_FlushAll
+ *   LoadGIF's canvas loop                    advancedio.c:195-248  imp_FlushAllGif (pages expanded on the device; imp_AlbumGifPage in the drop-in)
  *   cvReleaseImage on an error path          bridge.c:714-722  imp_Discard first
  *
  * Not reproduced on purpose: Crop tokenising `gravity` in place (bridge.c:73), which makes the 2nd frame of a
