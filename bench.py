@@ -365,6 +365,7 @@ def measure(cx: Ctx, name: str, steps: int, warmup: int, e2e_steps: int, shard: 
     except Exception:
         traffic = None
     res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": cx.peak, "unit": "GB/s", "frac": achieved / cx.peak, "traffic": traffic,
+                       "frac_of_nominal_8000": achieved / 8000.0,      # SURVEY §8d asks for both denominators
                        "peak_source": cx.peak_src, "algorithmic_bytes_per_step": int(algo_bytes), "kernel_launches_per_step": batch.launches_per_run,
                        "ms_per_launch_group": float(np.mean(step_ms)), "ms_min": float(np.min(step_ms)), "rank": cx.rank}
     batch.close()
