@@ -1408,7 +1408,8 @@ int imp_gpu_gif_expand_device(const imp_gpu_gif_frame* frames, int n, int canvas
     CK(cudaHostAlloc((void**)&h_buf, total, cudaHostAllocDefault));
     cudaError_t e = cudaMallocAsync((void**)&d_buf, total, st);
     if (e != cudaSuccess) { cudaFreeHost(h_buf); return fail(e, "cudaMallocAsync", __LINE__); }
-    gif_pack(frames, n, meta_bytes, h_buf, d_buf);
+    try { gif_pack(frames, n, meta_bytes, h_buf, d_buf); }
+    catch (const std::bad_alloc&) { cudaFreeAsync(d_buf, st); cudaFreeHost(h_buf); return IMP_ERROR_MALLOC_FAILED; }
     e = cudaMemcpyAsync(d_buf, h_buf, total, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = imp_launch_gif_expand(reinterpret_cast<const ImpGifFrame*>(d_buf), n, canvas_w, canvas_h, destructive ? 1 : 0, (uint8_t*)d_canvases, canvas_pitch, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // h_buf / d_buf are released below
@@ -1441,6 +1442,7 @@ int imp_gpu_gif_album_run_host(const imp_gpu_gif_frame* frames, int n, int canva
     const size_t canvas_bytes = (size_t)pitch * canvas_h;
     if ((rc = ctx.h_gif.grow(total, true)) || (rc = ctx.d_gif.grow(total, false)) || (rc = ctx.d_canvas.grow(canvas_bytes * n, false))) return rc;
     if (!ctx.gif_ev) CK(cudaEventCreateWithFlags(&ctx.gif_ev, cudaEventDisableTiming));
+    try {                                                             // the C caller cannot unwind: bad_alloc ends as a code
     gif_pack(frames, n, meta_bytes, ctx.h_gif.p, ctx.d_gif.p);
     CK(cudaMemcpyAsync(ctx.d_gif.p, ctx.h_gif.p, total, cudaMemcpyHostToDevice, ctx.stream));
     CK(imp_launch_gif_expand(reinterpret_cast<const ImpGifFrame*>(ctx.d_gif.p), n, canvas_w, canvas_h, destructive ? 1 : 0, ctx.d_canvas.p, pitch, ctx.stream));
@@ -1453,7 +1455,8 @@ int imp_gpu_gif_album_run_host(const imp_gpu_gif_frame* frames, int n, int canva
     }
     if (n_run == 0) { CK(cudaStreamSynchronize(ctx.stream)); return IMP_OK; }
     HostJobs J{n_run, run_plans.data(), srcs.data(), steps.data(), outs.data(), out_steps.data(), true};
-    try { rc = run_host_chunked_locked(J, n_streams, ctx.gif_ev); } catch (const std::bad_alloc&) { rc = IMP_ERROR_MALLOC_FAILED; }
+    rc = run_host_chunked_locked(J, n_streams, ctx.gif_ev);
+    } catch (const std::bad_alloc&) { rc = IMP_ERROR_MALLOC_FAILED; }
     if (rc != IMP_OK) cudaStreamSynchronize(ctx.stream);           // the staging buffers are reused by the next call
     return rc;
 }
